@@ -1,0 +1,354 @@
+#!/usr/bin/env python
+"""bench.py -- samples/s of the DLRM fwd+bwd+optimizer hot path on N B200s (contract in the task
+statement).  One "step" = one pass of the hot path (forward, loss, backward, fused row-wise-Adagrad
+embedding update, dense update) over one synthetic batch.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload cfg2|cfg1]
+
+Workload at N=1: BASELINE.json configs[2] ("cfg2": 26 tables x 1e6 rows x dim 128, bot 13-512-256-128,
+top 479-1024-512-256-1, batch 2048, --data-generation=random distribution, fwd+bwd+RWSAdagrad);
+`--workload cfg1` times the forward only (configs[1]).  N>1: the same model with tables sharded
+table-wise, per-GPU batch fixed at 2048 (weak scaling).
+
+Timing hygiene: a ring of >= 16 distinct pre-generated batches (their touched rows, 138 MB per batch,
+exceed the 126 MB L2 many times over) -> "inputs larger than L2"; CUDA events on the launching
+stream; max over ranks; nvidia-smi clocks sampled during the timed region.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+CFG = dict(m_spa=128, rows=1_000_000, T=26, ln_bot=[13, 512, 256, 128], top_tail=[1024, 512, 256, 1],
+           B=2048, lmax=10)
+
+
+def model_dims(T=CFG["T"]):
+    D = CFG["m_spa"]
+    ln_emb = [CFG["rows"]] * T
+    ln_top = [D + (T + 1) * T // 2] + CFG["top_tail"]
+    return D, ln_emb, CFG["ln_bot"], ln_top
+
+
+# ------------------------------------------------------------------------------ clocks
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index=0):
+        self.rows, self.proc, self.thr, self.gpu = [], None, None, gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.proc = None
+            return
+        self.thr = threading.Thread(target=self._read, daemon=True)
+        self.thr.start()
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.time(), line.strip()))
+
+    def stop(self, t0, t1):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], None, set()
+        for ts, line in self.rows:
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                clk, mx_ = float(f[1]), float(f[2])
+            except ValueError:
+                continue
+            mx = mx_
+            if t0 - 0.05 <= ts <= t1 + 0.15:
+                sm.append(clk)
+                for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"),
+                                     f[5:9]):
+                    if val.lower().startswith("active"):
+                        reasons.add(name)
+        if not sm:  # region shorter than the sampling period: use every sample
+            sm = [float(l.split(",")[1]) for _, l in self.rows if len(l.split(",")) >= 9] or [0.0]
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------ CPU baseline
+def cpu_baseline(train=True, budget_s=20.0, threads=None):
+    """The torch-CPU port of the oracle (same ATen ops as the reference's CPU path), timed on the
+    host cores on a bounded sample of the same workload."""
+    from oracle.torch_cpu_port import CpuDLRM, RowWiseAdagradCPU, time_cpu_steps
+    from dlrm_b200.data import make_batch
+
+    if threads:
+        torch.set_num_threads(threads)
+    cores = torch.get_num_threads()
+    D, ln_emb, ln_bot, ln_top = model_dims()
+    rows = CFG["rows"]
+    note = ""
+    try:
+        model = CpuDLRM(D, ln_emb, ln_bot, ln_top, loss="bce")
+    except (RuntimeError, MemoryError):  # host RAM too small for 13.3 GB of tables
+        rows = 100_000
+        ln_emb = [rows] * CFG["T"]
+        model = CpuDLRM(D, ln_emb, ln_bot, ln_top, loss="bce")
+        note = " (rows capped at 1e5: host RAM)"
+    opt = RowWiseAdagradCPU(model.parameters(), lr=0.01)
+    rng = np.random.default_rng(99)
+    batches = [make_batch(rng, ln_emb, CFG["B"], 13, CFG["lmax"], pin=False).reference_format()
+               for _ in range(4)]
+    batches = [(X, [o for o in lS_o], lS_i, T) for X, lS_o, lS_i, T in batches]
+    time_cpu_steps(model, opt, batches, 2, train)  # warm-up
+    t1 = time_cpu_steps(model, opt, batches, 3, train) / 3
+    n = int(max(5, min(200, budget_s / max(t1, 1e-4))))
+    dt = time_cpu_steps(model, opt, batches, n, train)
+    sps = n * CFG["B"] / dt
+    return {"value": sps, "unit": "samples/s", "cores": cores, "kind": "port",
+            "sample": "%d steps of batch %d, %s, 26x%dx128 tables%s, torch %s CPU, %d threads" % (
+                n, CFG["B"], "fwd+bwd+RWSAdagrad" if train else "fwd only", rows, note,
+                torch.__version__, cores),
+            "ms_per_step": 1e3 * dt / n}
+
+
+def reference_arm(args):
+    """`--impl reference`: the reference's CPU implementation of the path (its torch-CPU port: the
+    Python reference cannot travel to the GPU box), all host threads, same config/metric."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    train = args.workload != "cfg1"
+    per_step_budget = 1.0
+    cb = cpu_baseline(train, budget_s=max(5.0, per_step_budget * (args.steps + args.warmup)))
+    line = {
+        "impl": "reference", "metric": metric_name(train), "value": cb["value"], "unit": "samples/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": cb["ms_per_step"],
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "fp32",
+        "data": "synthetic", "config": config_dict(args, 1),
+        "cpu_baseline": cb,
+        "e2e": {"value": cb["value"], "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+
+
+def metric_name(train):
+    return "samples/sec (fwd+bwd) MLPerf-DLRM synthetic" if train else "samples/sec (fwd) MLPerf-DLRM synthetic"
+
+
+def config_dict(args, n):
+    return {"workload": "cfg2: 26x1e6x128 tables, bot 13-512-256-128, top 479-1024-512-256-1, "
+                        "batch 2048/GPU, random data Lmax=10, fwd+bwd+RWSAdagrad" if args.workload != "cfg1"
+            else "cfg1: same model, forward only",
+            "global_batch": CFG["B"] * n, "parallelism": "table-wise x%d + dp%d" % (n, n) if n > 1 else "single",
+            "l2_policy": "ring of %d distinct batches (inputs larger than L2)" % args.ring,
+            "gemm": args.gemm}
+
+
+# ------------------------------------------------------------------------------ our arm
+def bytes_fwd_gather(nnz, T, B, D):
+    """rows read + indices + offsets + pooled output written."""
+    return nnz * D * 4 + nnz * 8 + T * B * 8 + T * B * D * 4
+
+
+def ours(args):
+    from dlrm_b200.data import DeviceBatch, make_batch
+    from dlrm_b200.engine import Engine
+
+    n = args.gpus
+    if n > 1:
+        from dlrm_b200 import dist as ddist
+
+        return ddist.bench_main(args, CFG, metric_name, config_dict, ClockSampler)
+    torch.cuda.set_device(0)
+    dev = "cuda:0"
+    train = args.workload != "cfg1"
+    D, ln_emb, ln_bot, ln_top = model_dims()
+    B, T = CFG["B"], CFG["T"]
+    eng = Engine(D, ln_emb, ln_bot, ln_top, loss="bce", sigmoid_top=len(ln_top) - 2, device=dev,
+                 max_batch=B, gemm=args.gemm)
+    eng.init_params(0)
+    eng.ensure_optimizer_state("rwsadagrad")
+    rng = np.random.default_rng(1234)
+    host = [make_batch(rng, ln_emb, B, 13, CFG["lmax"]) for _ in range(args.ring)]
+    devb = []
+    for hb in host:
+        db = DeviceBatch(hb.layout, dev)
+        db.load(hb, non_blocking=False)
+        devb.append(db)
+    torch.cuda.synchronize()
+    lr = 0.01
+    gather_ev = []
+
+    def step(db, timed=False):
+        if train:
+            if timed:
+                # events around the gather on the launching stream (roofline.achieved)
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                eng._gather_events = (e0, e1)
+                gather_ev.append((e0, e1, db.nnz))
+            eng.train_step(db.X, db.sparse, db.target, lr, "rwsadagrad")
+            eng._gather_events = None
+        else:
+            eng.forward(db.X, db.sparse)
+
+    # ---- device-resident value
+    for w in range(args.warmup):
+        step(devb[w % args.ring])
+    torch.cuda.synchronize()
+    sampler = ClockSampler(0)
+    sampler.start()
+    time.sleep(0.25)
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    t0 = time.time()
+    launches0 = eng.n_launch
+    ev0.record()
+    for s in range(args.steps):
+        step(devb[(args.warmup + s) % args.ring], timed=True)
+    ev1.record()
+    launches = eng.n_launch - launches0
+    torch.cuda.synchronize()
+    t1 = time.time()
+    clocks = sampler.stop(t0, t1)
+    ms = ev0.elapsed_time(ev1) / args.steps
+    value = B / (ms * 1e-3)
+
+    # ---- gather roofline (events recorded inside the timed region)
+    peaks = {}
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as fh:
+            peaks = json.load(fh)
+    except Exception:
+        pass
+    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s"
+    roof = None
+    if gather_ev:
+        tg = np.array([a.elapsed_time(b) for a, b, _ in gather_ev]) * 1e-3
+        by = np.array([bytes_fwd_gather(nz, T, B, D) for _, _, nz in gather_ev], dtype=np.float64)
+        ach = float(by.sum() / tg.sum() / 1e9)
+        roof = {"kernel": "emb_fwd_vec_kernel (multi-table EmbeddingBag gather)", "bound": "hbm",
+                "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak,
+                "traffic": None, "peak_source": peak_src, "avg_launch_us": float(tg.mean() * 1e6),
+                "algorithmic_bytes_per_launch": float(by.mean())}
+    else:
+        roof = measure_gather_alone(eng, devb, args, hbm_peak, peak_src, T, B, D)
+
+    # ---- e2e: host buffers, H2D of the packed batch + D2H of the loss inside the timed region
+    stage = [DeviceBatch(host[0].layout, dev) for _ in range(2)]
+    copy_stream = torch.cuda.Stream()
+    loss_host = torch.zeros(1).pin_memory()
+    main = torch.cuda.current_stream()
+    h2d = 0
+
+    def e2e_loop(nsteps, base):
+        nonlocal h2d
+        ready = [torch.cuda.Event(), torch.cuda.Event()]
+        freed = [torch.cuda.Event(), torch.cuda.Event()]
+        for f in freed:
+            f.record(main)
+        with torch.cuda.stream(copy_stream):
+            copy_stream.wait_event(freed[0])
+            h2d += stage[0].load(host[base % args.ring])
+            ready[0].record(copy_stream)
+        for s in range(nsteps):
+            cur, nxt = s & 1, (s + 1) & 1
+            if s + 1 < nsteps:
+                with torch.cuda.stream(copy_stream):
+                    copy_stream.wait_event(freed[nxt])
+                    h2d += stage[nxt].load(host[(base + s + 1) % args.ring])
+                    ready[nxt].record(copy_stream)
+            main.wait_event(ready[cur])
+            if train:
+                loss = eng.train_step(stage[cur].X, stage[cur].sparse, stage[cur].target, lr, "rwsadagrad")
+                loss_host.copy_(loss, non_blocking=True)
+            else:
+                p = eng.forward(stage[cur].X, stage[cur].sparse)
+                loss_host.copy_(p[:1, 0], non_blocking=True)
+            freed[cur].record(main)
+        main.synchronize()
+
+    e2e_loop(args.warmup, 0)
+    h2d = 0
+    torch.cuda.synchronize()
+    ev0.record()
+    e2e_loop(args.steps, args.warmup)
+    ev1.record()
+    torch.cuda.synchronize()
+    ms_e2e = ev0.elapsed_time(ev1) / args.steps
+    e2e = {"value": B / (ms_e2e * 1e-3), "unit": "samples/s", "h2d_bytes_per_step": int(h2d / args.steps),
+           "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e,
+           "note": "packed pinned batch -> one cudaMemcpyAsync on a copy stream (double-buffered), "
+                   "loss read back every step"}
+
+    cb = cpu_baseline(train, budget_s=args.cpu_budget) if not args.no_cpu else None
+    line = {
+        "metric": metric_name(train), "value": value, "unit": "samples/s", "n_gpus": 1, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "fp32", "data": "synthetic", "config": config_dict(args, 1),
+        "roofline": roof, "cpu_baseline": cb, "e2e": e2e,
+        "gpu_launches": int(launches), "clocks": clocks,
+    }
+    print(json.dumps(line))
+
+
+def measure_gather_alone(eng, devb, args, hbm_peak, peak_src, T, B, D):
+    FD = eng.F * eng.D
+    out = eng.Tbuf.view(-1)[eng.D:]
+    for w in range(3):
+        eng.emb_forward(devb[w % len(devb)].sparse, out, FD, eng.D)
+    evs = []
+    for s in range(args.steps):
+        db = devb[s % len(devb)]
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        eng.emb_forward(db.sparse, out, FD, eng.D)
+        e1.record()
+        evs.append((e0, e1, db.nnz))
+    torch.cuda.synchronize()
+    tg = np.array([a.elapsed_time(b) for a, b, _ in evs]) * 1e-3
+    by = np.array([bytes_fwd_gather(nz, T, B, D) for _, _, nz in evs], dtype=np.float64)
+    ach = float(by.sum() / tg.sum() / 1e9)
+    return {"kernel": "emb_fwd_vec_kernel (multi-table EmbeddingBag gather)", "bound": "hbm", "achieved": ach,
+            "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak, "traffic": None, "peak_source": peak_src,
+            "avg_launch_us": float(tg.mean() * 1e6), "algorithmic_bytes_per_launch": float(by.mean())}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="cfg2", choices=["cfg2", "cfg1"])
+    ap.add_argument("--ring", type=int, default=16)
+    ap.add_argument("--gemm", default="simt")
+    ap.add_argument("--cpu-budget", type=float, default=15.0)
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+    if args.impl == "reference":
+        return reference_arm(args)
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; dlrm_b200 has no CPU path (use --impl reference for the CPU arm)")
+    ours(args)
+
+
+if __name__ == "__main__":
+    main()

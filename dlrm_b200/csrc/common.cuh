@@ -1,0 +1,56 @@
+// Shared helpers for libdlrm_b200.so (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/dlrm_b200.h"
+
+namespace dlrm {
+
+// thread-local error text behind dlrm_b200_last_error()
+char* err_buf();
+int set_error(const char* fmt, ...);
+int get_tunable(int id);
+
+enum Tunable {
+  TUNE_EMB_BAGS_PER_GROUP = 0,  // bags processed back to back by one lane group
+  TUNE_EMB_UNROLL = 1,          // rows in flight per lane group (4 or 8)
+  TUNE_EMB_BLOCK = 2,           // threads per CTA in the gather
+  TUNE_UPD_BLOCK = 3,
+  TUNE_GEMM_SPLITK = 4,
+  TUNE_COUNT = 16
+};
+
+#define DLRM_CHECK_LAUNCH(name)                                                         \
+  do {                                                                                  \
+    cudaError_t e__ = cudaGetLastError();                                               \
+    if (e__ != cudaSuccess)                                                             \
+      return dlrm::set_error("%s: launch failed: %s", name, cudaGetErrorString(e__));   \
+  } while (0)
+
+#define DLRM_CUDA(call)                                                                 \
+  do {                                                                                  \
+    cudaError_t e__ = (call);                                                           \
+    if (e__ != cudaSuccess)                                                             \
+      return dlrm::set_error("%s failed: %s", #call, cudaGetErrorString(e__));          \
+  } while (0)
+
+static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+// 128-bit read-only load that does not allocate in L1 (rows are touched once per kernel)
+__device__ __forceinline__ float4 ldg_stream_f4(const float* p) {
+  float4 v;
+  asm("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+               : "l"(p));
+  return v;
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+}  // namespace dlrm

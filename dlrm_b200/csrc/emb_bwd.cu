@@ -1,0 +1,338 @@
+// Embedding backward fused with the sparse optimizer step.
+//
+// Replaces: autograd _embedding_bag_backward -> sparse COO grad (dlrm_s_pytorch.py:1613) and
+// optimizer.step() (:1620): optim/rwsadagrad.py:117-143 (coalesce, mean of squares, momentum,
+// scaled sparse add) or torch.optim.SGD's sparse add.  No [nnz, D] gradient tensor is ever
+// materialised: the gradient of a (table,row) occurrence IS the dY row of its bag.
+//
+// Coalescing (the update is non-linear, so occurrences of the same row must be summed first,
+// optim/rwsadagrad.py:118-120) is done without a sort:
+//   link   : every occurrence `pos` of a row threads itself onto a per-row list with one
+//            atomicExch on head[row] (int32 per table row, zero between steps):
+//                link[pos] = { previous head, bag of pos };  head[row] = pos + 1
+//            Depends on the indices only -> can overlap the forward pass.
+//   update : one warp per bag.  Occurrence `pos` owns its row iff head[row] == pos + 1 (the
+//            last arrival).  The owner walks the list, sorts the members by position when there
+//            are <= 32 (deterministic sum in ascending position == grad.coalesce() order), adds
+//            their dY rows, applies the optimizer to the 512-byte weight row in registers and
+//            resets head[row] = 0.  Non-owners do nothing.  Rows without duplicates (the common
+//            case at 1e6-row tables) never touch link[] beyond their own entry and reuse the
+//            bag's own dY row, which is loaded once per bag.
+#include "common.cuh"
+
+namespace dlrm {
+
+struct EmbBwdTable {
+  float* w;
+  float* mom;
+  int* head;
+  const void* idx;
+  const void* off;
+  long long nnz;
+  long long pair_base;
+};
+
+struct EmbBwdParams {
+  EmbBwdTable t[DLRM_B200_MAX_TABLES_PER_CALL];
+  int2* link;        // [total nnz] {next, bag}
+  const float* dY;
+  long long dy_stride_sample;
+  long long dy_stride_table;
+  long long batch;
+  int dim;
+  int include_last;
+  int optimizer;
+  float lr;
+  float eps;
+};
+
+template <typename idx_t>
+__device__ __forceinline__ long long bag_end2(const idx_t* off, long long b, long long batch,
+                                              long long nnz, int include_last) {
+  return (include_last || b + 1 < batch) ? (long long)off[b + 1] : nnz;
+}
+
+// ---------------------------------------------------------------------------------------------
+// link: one thread per occurrence; its bag is found by binary search in the offsets (L2 hits).
+// ---------------------------------------------------------------------------------------------
+template <typename idx_t>
+__global__ void __launch_bounds__(256) emb_link_kernel(const __grid_constant__ EmbBwdParams P) {
+  const EmbBwdTable& tb = P.t[blockIdx.y];
+  const idx_t* __restrict__ idx = static_cast<const idx_t*>(tb.idx);
+  const idx_t* __restrict__ off = static_cast<const idx_t*>(tb.off);
+  // packed format: offsets are global positions into one shared index array, so a table's
+  // occurrences are [off[0], off[batch]); reference format: [0, nnz)
+  const long long jbeg = (long long)off[0];
+  const long long nnz = P.include_last ? (long long)off[P.batch] : tb.nnz;
+  for (long long j = jbeg + (long long)blockIdx.x * blockDim.x + threadIdx.x; j < nnz;
+       j += (long long)gridDim.x * blockDim.x) {
+    // largest b with off[b] <= j  (empty bags share an offset: pick the last of the run)
+    long long lo = 0, hi = P.batch - 1;
+    while (lo < hi) {
+      const long long mid = (lo + hi + 1) >> 1;
+      if ((long long)off[mid] <= j) lo = mid; else hi = mid - 1;
+    }
+    const long long r = idx[j];
+    const long long pos = tb.pair_base + j;
+    const int prev = atomicExch(tb.head + r, (int)(pos + 1));
+    P.link[pos] = make_int2(prev, (int)lo);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// update.  W = elements per lane per step (4 = float4 path, 1 = scalar path), NV steps.
+// lane columns: c(v) = lane*W + v*32*W.
+// ---------------------------------------------------------------------------------------------
+template <int W>
+struct Pack {
+  float x[W];
+};
+
+template <int W>
+__device__ __forceinline__ Pack<W> ld_pack(const float* p) {
+  Pack<W> r;
+  if (W == 4) {
+    const float4 v = *reinterpret_cast<const float4*>(p);
+    r.x[0] = v.x; r.x[1 % W] = v.y; r.x[2 % W] = v.z; r.x[3 % W] = v.w;
+  } else {
+    r.x[0] = *p;
+  }
+  return r;
+}
+template <int W>
+__device__ __forceinline__ void st_pack(float* p, const Pack<W>& r) {
+  if (W == 4) {
+    *reinterpret_cast<float4*>(p) = make_float4(r.x[0], r.x[1 % W], r.x[2 % W], r.x[3 % W]);
+  } else {
+    *p = r.x[0];
+  }
+}
+
+template <int W, int NV, typename idx_t>
+__global__ void __launch_bounds__(256) emb_update_kernel(const __grid_constant__ EmbBwdParams P) {
+  const EmbBwdTable& tb = P.t[blockIdx.y];
+  const idx_t* __restrict__ idx = static_cast<const idx_t*>(tb.idx);
+  const idx_t* __restrict__ off = static_cast<const idx_t*>(tb.off);
+  const int D = P.dim;
+  const int lane = threadIdx.x & 31;
+  const long long b = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (b >= P.batch) return;
+  const long long start = off[b];
+  const long long end = bag_end2<idx_t>(off, b, P.batch, tb.nnz, P.include_last);
+  if (start >= end) return;
+  const float* dYk = P.dY + (long long)blockIdx.y * P.dy_stride_table;
+
+  bool col_ok[NV];
+  Pack<W> g_self[NV];
+#pragma unroll
+  for (int v = 0; v < NV; ++v) {
+    col_ok[v] = lane * W + v * 32 * W < D;
+    if (col_ok[v]) g_self[v] = ld_pack<W>(dYk + b * P.dy_stride_sample + lane * W + v * 32 * W);
+  }
+  const float inv_d = 1.0f / (float)D;
+
+  for (long long j0 = start; j0 < end; j0 += 32) {
+    const long long j = j0 + lane;
+    long long my_r = 0;
+    int my_head = 0, my_next = 0;
+    const long long my_pos = tb.pair_base + j;
+    if (j < end) {
+      my_r = idx[j];
+      my_head = tb.head[my_r];
+      my_next = P.link[my_pos].x;
+    }
+    unsigned owners = __ballot_sync(0xffffffffu, j < end && my_head == (int)(my_pos + 1));
+    while (owners) {
+      const int src = __ffs(owners) - 1;
+      owners &= owners - 1;
+      const long long r = __shfl_sync(0xffffffffu, my_r, src);
+      int nxt = __shfl_sync(0xffffffffu, my_next, src);
+      float* wrow = tb.w + r * D;
+      // issue the weight-row read first: it is the long-latency (HBM) access
+      Pack<W> w[NV];
+#pragma unroll
+      for (int v = 0; v < NV; ++v)
+        if (col_ok[v]) w[v] = ld_pack<W>(wrow + lane * W + v * 32 * W);
+      float m_old = 0.f;
+      if (P.optimizer == DLRM_OPT_RWSADAGRAD) m_old = tb.mom[r];
+
+      Pack<W> g[NV];
+      if (nxt == 0) {
+#pragma unroll
+        for (int v = 0; v < NV; ++v) g[v] = g_self[v];
+      } else {
+        // duplicates: gather members (self first), in chunks of 32, sorted by position
+#pragma unroll
+        for (int v = 0; v < NV; ++v)
+#pragma unroll
+          for (int e = 0; e < W; ++e) g[v].x[e] = 0.f;
+        int cnt = 1;
+        int mpos = (lane == 0) ? (int)(tb.pair_base + j0 + src) : 0x7fffffff;
+        int mbag = (int)b;
+        while (true) {
+          if (nxt != 0 && cnt < 32) {
+            const int2 e = P.link[nxt - 1];
+            if (lane == cnt) { mpos = nxt - 1; mbag = e.y; }
+            ++cnt;
+            nxt = e.x;
+            if (nxt != 0 && cnt < 32) continue;
+          }
+          // rank of my member among the chunk (positions are unique)
+          int rank = 0;
+          for (int i = 0; i < cnt; ++i) rank += (__shfl_sync(0xffffffffu, mpos, i) < mpos) ? 1 : 0;
+          for (int q = 0; q < cnt; ++q) {
+            const unsigned who = __ballot_sync(0xffffffffu, lane < cnt && rank == q);
+            const int bag = __shfl_sync(0xffffffffu, mbag, __ffs(who) - 1);
+#pragma unroll
+            for (int v = 0; v < NV; ++v) {
+              if (col_ok[v]) {
+                const Pack<W> t = ld_pack<W>(dYk + (long long)bag * P.dy_stride_sample + lane * W + v * 32 * W);
+#pragma unroll
+                for (int e = 0; e < W; ++e) g[v].x[e] += t.x[e];
+              }
+            }
+          }
+          if (nxt == 0) break;
+          cnt = 0;
+          mpos = 0x7fffffff;
+        }
+      }
+
+      if (P.optimizer == DLRM_OPT_RWSADAGRAD) {
+        float sq = 0.f;
+#pragma unroll
+        for (int v = 0; v < NV; ++v)
+          if (col_ok[v])
+#pragma unroll
+            for (int e = 0; e < W; ++e) sq = fmaf(g[v].x[e], g[v].x[e], sq);
+        sq = warp_sum(sq);
+        const float m_new = m_old + sq * inv_d;
+        const float stdv = sqrtf(m_new) + P.eps;
+        const float nlr = -P.lr;
+#pragma unroll
+        for (int v = 0; v < NV; ++v)
+          if (col_ok[v]) {
+#pragma unroll
+            for (int e = 0; e < W; ++e) w[v].x[e] = fmaf(nlr, g[v].x[e] / stdv, w[v].x[e]);
+            st_pack<W>(wrow + lane * W + v * 32 * W, w[v]);
+          }
+        if (lane == 0) tb.mom[r] = m_new;
+      } else {
+        const float nlr = -P.lr;
+#pragma unroll
+        for (int v = 0; v < NV; ++v)
+          if (col_ok[v]) {
+#pragma unroll
+            for (int e = 0; e < W; ++e) w[v].x[e] = fmaf(nlr, g[v].x[e], w[v].x[e]);
+            st_pack<W>(wrow + lane * W + v * 32 * W, w[v]);
+          }
+      }
+      if (lane == 0) tb.head[r] = 0;
+    }
+  }
+}
+
+static int fill_params(EmbBwdParams& P, const dlrm_emb_bwd_table_t* tables, int num_tables,
+                       const char* who) {
+  if (num_tables < 0 || num_tables > DLRM_B200_MAX_TABLES_PER_CALL)
+    return set_error("%s: num_tables=%d out of range [0,%d]", who, num_tables,
+                     DLRM_B200_MAX_TABLES_PER_CALL);
+  for (int k = 0; k < num_tables; ++k) {
+    if (!tables[k].head || !tables[k].offsets || (!tables[k].indices && tables[k].nnz > 0))
+      return set_error("%s: table %d has a NULL pointer", who, k);
+    if (tables[k].pair_base + tables[k].nnz > 0x7ffffffeLL)
+      return set_error("%s: more than 2^31-2 index occurrences in one call", who);
+    P.t[k].w = tables[k].weight;
+    P.t[k].mom = tables[k].momentum;
+    P.t[k].head = tables[k].head;
+    P.t[k].idx = tables[k].indices;
+    P.t[k].off = tables[k].offsets;
+    P.t[k].nnz = tables[k].nnz;
+    P.t[k].pair_base = tables[k].pair_base;
+  }
+  return 0;
+}
+
+}  // namespace dlrm
+
+extern "C" int dlrm_b200_emb_bwd_link(const dlrm_emb_bwd_table_t* tables, int num_tables,
+                                      int64_t batch, int idx_bytes, int include_last,
+                                      int32_t* next, void* stream) {
+  using namespace dlrm;
+  EmbBwdParams P{};
+  if (int rc = fill_params(P, tables, num_tables, "emb_bwd_link")) return rc;
+  if (idx_bytes != 4 && idx_bytes != 8) return set_error("emb_bwd_link: idx_bytes=%d", idx_bytes);
+  if (num_tables == 0 || batch == 0) return 0;
+  if (!next) return set_error("emb_bwd_link: next is NULL");
+  P.link = reinterpret_cast<int2*>(next);
+  P.batch = batch;
+  P.include_last = include_last;
+  long long max_nnz = 0;
+  for (int k = 0; k < num_tables; ++k) max_nnz = tables[k].nnz > max_nnz ? tables[k].nnz : max_nnz;
+  if (max_nnz == 0) return 0;
+  const int block = 256;
+  long long gx = (max_nnz + block - 1) / block;
+  if (gx > 65535) gx = 65535;  // grid-stride loop covers the rest
+  dim3 grid((unsigned)gx, (unsigned)num_tables);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (idx_bytes == 8) emb_link_kernel<long long><<<grid, block, 0, st>>>(P);
+  else emb_link_kernel<int><<<grid, block, 0, st>>>(P);
+  DLRM_CHECK_LAUNCH("emb_link_kernel");
+  return 0;
+}
+
+extern "C" int dlrm_b200_emb_bwd_update(const dlrm_emb_bwd_table_t* tables, int num_tables, int dim,
+                                        int64_t batch, int idx_bytes, int include_last,
+                                        const int32_t* next, const float* dY,
+                                        int64_t dy_stride_sample, int64_t dy_stride_table,
+                                        int optimizer, float lr, float eps, void* stream) {
+  using namespace dlrm;
+  EmbBwdParams P{};
+  if (int rc = fill_params(P, tables, num_tables, "emb_bwd_update")) return rc;
+  if (idx_bytes != 4 && idx_bytes != 8) return set_error("emb_bwd_update: idx_bytes=%d", idx_bytes);
+  if (optimizer != DLRM_OPT_SGD && optimizer != DLRM_OPT_RWSADAGRAD)
+    return set_error("emb_bwd_update: optimizer=%d", optimizer);
+  if (dim <= 0 || dim > 1024) return set_error("emb_bwd_update: dim=%d unsupported (1..1024)", dim);
+  if (num_tables == 0 || batch == 0) return 0;
+  if (!next || !dY) return set_error("emb_bwd_update: NULL next/dY");
+  bool vec = (dim % 4 == 0) && aligned16(dY) && dy_stride_sample % 4 == 0 && dy_stride_table % 4 == 0;
+  for (int k = 0; k < num_tables; ++k) {
+    if (!tables[k].weight) return set_error("emb_bwd_update: table %d weight NULL", k);
+    if (optimizer == DLRM_OPT_RWSADAGRAD && !tables[k].momentum)
+      return set_error("emb_bwd_update: table %d momentum NULL", k);
+    vec = vec && aligned16(tables[k].weight);
+  }
+  P.link = reinterpret_cast<int2*>(const_cast<int32_t*>(next));
+  P.dY = dY;
+  P.dy_stride_sample = dy_stride_sample;
+  P.dy_stride_table = dy_stride_table;
+  P.batch = batch;
+  P.dim = dim;
+  P.include_last = include_last;
+  P.optimizer = optimizer;
+  P.lr = lr;
+  P.eps = eps;
+  const int block = 256;
+  dim3 grid((unsigned)((batch + (block / 32) - 1) / (block / 32)), (unsigned)num_tables);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+#define UPD(Wd, NV)                                                                    \
+  do {                                                                                 \
+    if (idx_bytes == 8) emb_update_kernel<Wd, NV, long long><<<grid, block, 0, st>>>(P); \
+    else emb_update_kernel<Wd, NV, int><<<grid, block, 0, st>>>(P);                     \
+    DLRM_CHECK_LAUNCH("emb_update_kernel");                                            \
+    return 0;                                                                          \
+  } while (0)
+  if (vec) {
+    if (dim <= 128) UPD(4, 1);
+    if (dim <= 256) UPD(4, 2);
+    if (dim <= 512) UPD(4, 4);
+    UPD(4, 8);
+  }
+  if (dim <= 32) UPD(1, 1);
+  if (dim <= 64) UPD(1, 2);
+  if (dim <= 128) UPD(1, 4);
+  if (dim <= 256) UPD(1, 8);
+  if (dim <= 512) UPD(1, 16);
+  UPD(1, 32);
+#undef UPD
+}

@@ -1,0 +1,244 @@
+// Batched multi-table EmbeddingBag(sum) forward -- replaces the T separate
+// nn.EmbeddingBag calls of DLRM_Net.apply_emb (dlrm_s_pytorch.py:407-462).
+//
+// One launch covers every table.  A "lane group" of G = dim/4 lanes (32 for dim 128) owns a
+// bag: each lane keeps ONE float4 accumulator per 4G columns and adds the rows of the bag in
+// index order, so the result is bit-identical to the reference CPU kernel (sequential fp32).
+// A row of dim 128 is a single 512-byte, fully coalesced warp request (4 x 128B lines).
+// Memory-level parallelism comes from (a) up to U rows in flight per group (indices are read
+// with one coalesced load per G positions and broadcast with warp shuffles), (b) the indices
+// of the next bag being prefetched while the rows of the current bag are in flight, and
+// (c) 8..16 warps per CTA x many CTAs per SM.
+#include "common.cuh"
+
+namespace dlrm {
+
+struct EmbFwdTable {
+  const float* w;
+  const void* idx;
+  const void* off;
+  const float* rw;
+  long long nnz;
+};
+
+struct EmbFwdParams {
+  EmbFwdTable t[DLRM_B200_MAX_TABLES_PER_CALL];
+  float* out;
+  long long stride_sample;
+  long long stride_table;
+  long long batch;
+  int dim;
+  int include_last;
+  int bags_per_group;
+};
+
+template <typename idx_t>
+__device__ __forceinline__ long long bag_end(const idx_t* off, long long b, long long batch,
+                                             long long nnz, int include_last) {
+  return (include_last || b + 1 < batch) ? (long long)off[b + 1] : nnz;
+}
+
+// G lanes per bag, NV float4 per lane (dim = 4*G*NV when exact; columns >= dim are masked)
+template <int G, int NV, int U, typename idx_t, bool WEIGHTED>
+__global__ void __launch_bounds__(256) emb_fwd_vec_kernel(const __grid_constant__ EmbFwdParams P) {
+  const EmbFwdTable& tb = P.t[blockIdx.y];
+  const idx_t* __restrict__ idx = static_cast<const idx_t*>(tb.idx);
+  const idx_t* __restrict__ off = static_cast<const idx_t*>(tb.off);
+  const float* __restrict__ W = tb.w;
+  const int D = P.dim;
+  constexpr int GROUPS_PER_WARP = 32 / G;
+  const int lane = threadIdx.x & 31;
+  const int gl = lane % G;   // lane inside the group
+  const int grp = lane / G;  // group inside the warp
+  const unsigned gmask = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << (grp * G));
+  const long long group_id =
+      ((long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * GROUPS_PER_WARP + grp;
+  const int S = P.bags_per_group;
+  const long long b0 = group_id * S;
+  if (b0 >= P.batch) return;
+  const int nb = (int)min((long long)S, P.batch - b0);
+
+  // bag boundaries of this group's run of bags: one coalesced load, then shuffles.
+  // (S <= G is enforced by the host so lane gl can hold boundary gl.)
+  long long my_bound = 0;
+  if (gl <= nb) {
+    const long long b = b0 + gl;
+    my_bound = (b < P.batch) ? (long long)off[b] : 0;
+    if (gl == nb) my_bound = bag_end<idx_t>(off, b - 1, P.batch, tb.nnz, P.include_last);
+  }
+  long long start = __shfl_sync(gmask, my_bound, 0, G);
+  long long end = __shfl_sync(gmask, my_bound, 1, G);
+  // first index chunk of bag 0
+  long long my_row = (start + gl < end) ? (long long)idx[start + gl] : 0;
+
+  for (int s = 0; s < nb; ++s) {
+    // prefetch boundaries + first index chunk of the next bag
+    long long nstart = 0, nend = 0, next_row = 0;
+    if (s + 1 < nb) {
+      nstart = end;
+      nend = __shfl_sync(gmask, my_bound, s + 2, G);
+      next_row = (nstart + gl < nend) ? (long long)idx[nstart + gl] : 0;
+    }
+    float4 acc[NV];
+#pragma unroll
+    for (int v = 0; v < NV; ++v) acc[v] = make_float4(0.f, 0.f, 0.f, 0.f);
+
+    for (long long j0 = start; j0 < end; j0 += G) {
+      if (j0 != start) my_row = (j0 + gl < end) ? (long long)idx[j0 + gl] : 0;
+      const int n = (int)min((long long)G, end - j0);
+      for (int jj = 0; jj < n; jj += U) {
+        float4 val[U][NV];
+        float wgt[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          const long long r = __shfl_sync(gmask, my_row, jj + u, G);  // jj+u < G always (U | G or guarded)
+          if (jj + u < n) {
+            const float* rp = W + r * D + gl * 4;
+#pragma unroll
+            for (int v = 0; v < NV; ++v) {
+              if (gl * 4 + v * G * 4 < D) val[u][v] = ldg_stream_f4(rp + v * G * 4);
+            }
+            if (WEIGHTED) wgt[u] = __ldg(tb.rw + r);
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          if (jj + u < n) {
+#pragma unroll
+            for (int v = 0; v < NV; ++v) {
+              if (WEIGHTED) {
+                acc[v].x = fmaf(wgt[u], val[u][v].x, acc[v].x);
+                acc[v].y = fmaf(wgt[u], val[u][v].y, acc[v].y);
+                acc[v].z = fmaf(wgt[u], val[u][v].z, acc[v].z);
+                acc[v].w = fmaf(wgt[u], val[u][v].w, acc[v].w);
+              } else {
+                acc[v].x += val[u][v].x;
+                acc[v].y += val[u][v].y;
+                acc[v].z += val[u][v].z;
+                acc[v].w += val[u][v].w;
+              }
+            }
+          }
+        }
+      }
+    }
+    float* op = P.out + (b0 + s) * P.stride_sample + (long long)blockIdx.y * P.stride_table + gl * 4;
+#pragma unroll
+    for (int v = 0; v < NV; ++v) {
+      if (gl * 4 + v * G * 4 < D) *reinterpret_cast<float4*>(op + v * G * 4) = acc[v];
+    }
+    start = nstart;
+    end = nend;
+    my_row = next_row;
+  }
+}
+
+// any dim / any alignment: one thread per output element, sequential over the bag
+template <typename idx_t, bool WEIGHTED>
+__global__ void emb_fwd_scalar_kernel(const __grid_constant__ EmbFwdParams P) {
+  const EmbFwdTable& tb = P.t[blockIdx.y];
+  const idx_t* __restrict__ idx = static_cast<const idx_t*>(tb.idx);
+  const idx_t* __restrict__ off = static_cast<const idx_t*>(tb.off);
+  const int D = P.dim;
+  const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= P.batch * D) return;
+  const long long b = e / D;
+  const int d = (int)(e % D);
+  const long long start = off[b];
+  const long long end = bag_end<idx_t>(off, b, P.batch, tb.nnz, P.include_last);
+  float acc = 0.f;
+  for (long long j = start; j < end; ++j) {
+    const long long r = idx[j];
+    const float x = tb.w[r * D + d];
+    acc = WEIGHTED ? fmaf(tb.rw[r], x, acc) : acc + x;
+  }
+  P.out[b * P.stride_sample + (long long)blockIdx.y * P.stride_table + d] = acc;
+}
+
+template <int G, int NV, int U, typename idx_t, bool WEIGHTED>
+static int launch_vec(const EmbFwdParams& P, int num_tables, cudaStream_t st) {
+  const int block = 256;
+  const long long groups_per_block = (long long)(block / 32) * (32 / G);
+  const long long groups = (P.batch + P.bags_per_group - 1) / P.bags_per_group;
+  dim3 grid((unsigned)((groups + groups_per_block - 1) / groups_per_block), (unsigned)num_tables);
+  emb_fwd_vec_kernel<G, NV, U, idx_t, WEIGHTED><<<grid, block, 0, st>>>(P);
+  DLRM_CHECK_LAUNCH("emb_fwd_vec_kernel");
+  return 0;
+}
+
+template <typename idx_t, bool WEIGHTED>
+static int dispatch(const EmbFwdParams& Pin, int num_tables, bool vec_ok, cudaStream_t st) {
+  EmbFwdParams P = Pin;
+  const int D = P.dim;
+  if (vec_ok) {
+    const int u8 = get_tunable(TUNE_EMB_UNROLL) != 4;
+    int S = get_tunable(TUNE_EMB_BAGS_PER_GROUP);
+    if (S <= 0) S = 4;
+#define VEC(G, NV)                                                                   \
+  do {                                                                               \
+    P.bags_per_group = S < (G) ? S : (G)-1;                                          \
+    if ((G) >= 8 && u8) return launch_vec<G, NV, 8, idx_t, WEIGHTED>(P, num_tables, st); \
+    return launch_vec<G, NV, ((G) >= 4 ? 4 : (G)), idx_t, WEIGHTED>(P, num_tables, st);  \
+  } while (0)
+    if (D == 16) VEC(4, 1);  // dim 4 / 8: scalar kernel (a group must hold S+1 bag bounds)
+    if (D == 32) VEC(8, 1);
+    if (D == 64) VEC(16, 1);
+    if (D > 64 && D <= 128) VEC(32, 1);
+    if (D > 128 && D <= 256) VEC(32, 2);
+    if (D > 256 && D <= 512) VEC(32, 4);
+#undef VEC
+  }
+  const int block = 256;
+  const long long n = P.batch * D;
+  dim3 grid((unsigned)((n + block - 1) / block), (unsigned)num_tables);
+  emb_fwd_scalar_kernel<idx_t, WEIGHTED><<<grid, block, 0, st>>>(P);
+  DLRM_CHECK_LAUNCH("emb_fwd_scalar_kernel");
+  return 0;
+}
+
+}  // namespace dlrm
+
+extern "C" int dlrm_b200_emb_bag_fwd(const dlrm_emb_fwd_table_t* tables, int num_tables, int dim,
+                                     int64_t batch, int idx_bytes, int include_last, float* out,
+                                     int64_t out_stride_sample, int64_t out_stride_table,
+                                     void* stream) {
+  using namespace dlrm;
+  if (num_tables < 0 || num_tables > DLRM_B200_MAX_TABLES_PER_CALL)
+    return set_error("emb_bag_fwd: num_tables=%d out of range [0,%d]", num_tables,
+                     DLRM_B200_MAX_TABLES_PER_CALL);
+  if (dim <= 0) return set_error("emb_bag_fwd: dim=%d", dim);
+  if (idx_bytes != 4 && idx_bytes != 8) return set_error("emb_bag_fwd: idx_bytes=%d", idx_bytes);
+  if (batch == 0 || num_tables == 0) return 0;
+  if (batch < 0 || batch * (int64_t)dim > (int64_t)0x7fffffff * 256)
+    return set_error("emb_bag_fwd: batch=%lld too large", (long long)batch);
+  EmbFwdParams P;
+  bool weighted = false, any_unweighted = false;
+  bool vec_ok = (dim % 4 == 0) && dim <= 512 && aligned16(out) && out_stride_sample % 4 == 0 &&
+                out_stride_table % 4 == 0;
+  for (int k = 0; k < num_tables; ++k) {
+    P.t[k].w = tables[k].weight;
+    P.t[k].idx = tables[k].indices;
+    P.t[k].off = tables[k].offsets;
+    P.t[k].rw = tables[k].row_weights;
+    P.t[k].nnz = tables[k].nnz;
+    if (!tables[k].weight || !tables[k].offsets || (!tables[k].indices && tables[k].nnz > 0))
+      return set_error("emb_bag_fwd: table %d has a NULL pointer", k);
+    if (tables[k].row_weights) weighted = true; else any_unweighted = true;
+    vec_ok = vec_ok && aligned16(tables[k].weight);
+  }
+  if (weighted && any_unweighted)
+    return set_error("emb_bag_fwd: row_weights must be given for all tables of a call or none");
+  P.out = out;
+  P.stride_sample = out_stride_sample;
+  P.stride_table = out_stride_table;
+  P.batch = batch;
+  P.dim = dim;
+  P.include_last = include_last;
+  P.bags_per_group = 1;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (idx_bytes == 8)
+    return weighted ? dispatch<long long, true>(P, num_tables, vec_ok, st)
+                    : dispatch<long long, false>(P, num_tables, vec_ok, st);
+  return weighted ? dispatch<int, true>(P, num_tables, vec_ok, st)
+                  : dispatch<int, false>(P, num_tables, vec_ok, st);
+}

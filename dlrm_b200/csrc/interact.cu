@@ -1,0 +1,194 @@
+// interact_features (dlrm_s_pytorch.py:483-504), "dot" op, forward and backward, CUDA-core fp32.
+// Fuses torch.cat -> torch.bmm -> Z[:, li, lj] -> torch.cat into one pass over T:
+// the operand T[b] = [x; ly_0; ...; ly_{T-1}] is read IN PLACE from the buffer the bottom MLP and
+// the gather wrote, the strict-lower-triangle flatten happens in the epilogue, and x is copied
+// into R[:, 0:D] on the way.
+#include "common.cuh"
+
+namespace dlrm {
+
+// ------------------------------------------------------------------------------------------
+// forward: 3x3 register blocks of the Gram matrix, lower-triangular blocks only.
+// smem per sample: T rows padded to Fp = 3*ceil(F/3) rows of (D+1) floats (conflict-free
+// column walks) + the flattened interactions (coalesced write-out).
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(192) interact_fwd_kernel(const float* __restrict__ T, long long ldt,
+                                                           float* __restrict__ R, long long ldr,
+                                                           long long batch, int F, int D, int itself,
+                                                           int spb) {
+  extern __shared__ float smem[];
+  const int nb = (F + 2) / 3;
+  const int Fp = nb * 3;
+  const int LD = D + 1;
+  const int tps = nb * (nb + 1) / 2;                 // threads (blocks) per sample
+  const int npairs = itself ? F * (F + 1) / 2 : F * (F - 1) / 2;
+  const int per_sample = Fp * LD + npairs;
+  const long long s0 = (long long)blockIdx.x * spb;
+  const int ns = (int)min((long long)spb, batch - s0);
+
+  // load T (zero-padded rows), copy x to R[:, 0:D]
+  for (int e = threadIdx.x; e < ns * Fp * D; e += blockDim.x) {
+    const int s = e / (Fp * D);
+    const int rem = e - s * Fp * D;
+    const int f = rem / D, d = rem - f * D;
+    float v = 0.f;
+    if (f < F) v = T[(s0 + s) * ldt + (long long)f * D + d];
+    smem[s * per_sample + f * LD + d] = v;
+    if (f == 0) R[(s0 + s) * ldr + d] = v;
+  }
+  __syncthreads();
+
+  for (int item = threadIdx.x; item < ns * tps; item += blockDim.x) {
+    const int s = item / tps;
+    const int q = item - s * tps;
+    // q -> (a, c) with c <= a:  a = floor((sqrt(8q+1)-1)/2)
+    int a = (int)((sqrtf(8.f * q + 1.f) - 1.f) * 0.5f);
+    while ((a + 1) * (a + 2) / 2 <= q) ++a;
+    while (a * (a + 1) / 2 > q) --a;
+    const int c = q - a * (a + 1) / 2;
+    const float* Ts = smem + s * per_sample;
+    const float* ra = Ts + (3 * a) * LD;
+    const float* rc = Ts + (3 * c) * LD;
+    float z[3][3] = {{0.f, 0.f, 0.f}, {0.f, 0.f, 0.f}, {0.f, 0.f, 0.f}};
+    for (int d = 0; d < D; ++d) {
+      const float a0 = ra[d], a1 = ra[LD + d], a2 = ra[2 * LD + d];
+      const float c0 = rc[d], c1 = rc[LD + d], c2 = rc[2 * LD + d];
+      z[0][0] = fmaf(a0, c0, z[0][0]); z[0][1] = fmaf(a0, c1, z[0][1]); z[0][2] = fmaf(a0, c2, z[0][2]);
+      z[1][0] = fmaf(a1, c0, z[1][0]); z[1][1] = fmaf(a1, c1, z[1][1]); z[1][2] = fmaf(a1, c2, z[1][2]);
+      z[2][0] = fmaf(a2, c0, z[2][0]); z[2][1] = fmaf(a2, c1, z[2][1]); z[2][2] = fmaf(a2, c2, z[2][2]);
+    }
+    float* Zs = smem + s * per_sample + Fp * LD;
+#pragma unroll
+    for (int x = 0; x < 3; ++x)
+#pragma unroll
+      for (int y = 0; y < 3; ++y) {
+        const int i = 3 * a + x, j = 3 * c + y;
+        if (i < F && (j < i || (itself && j == i))) {
+          const int p = itself ? i * (i + 1) / 2 + j : i * (i - 1) / 2 + j;
+          Zs[p] = z[x][y];
+        }
+      }
+  }
+  __syncthreads();
+  for (int e = threadIdx.x; e < ns * npairs; e += blockDim.x) {
+    const int s = e / npairs, p = e - s * npairs;
+    R[(s0 + s) * ldr + D + p] = smem[s * per_sample + Fp * LD + p];
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// backward: dT[i][d] = sum_j S[i][j] T[j][d] (+ dR[d] for i == 0),  S = dZ + dZ^T.
+// One thread owns a column d of one sample: T[:, d] lives in registers, S rows are read as
+// broadcast float4 from shared memory.
+// ------------------------------------------------------------------------------------------
+template <int MAXF>
+__global__ void __launch_bounds__(128) interact_bwd_kernel(const float* __restrict__ T, long long ldt,
+                                                           const float* __restrict__ dR, long long lddr,
+                                                           float* __restrict__ dT, long long lddt,
+                                                           long long batch, int F, int D, int itself,
+                                                           int mask0, int spb) {
+  extern __shared__ __align__(16) float smem[];
+  const int F4 = (F + 3) & ~3;
+  const long long s0 = (long long)blockIdx.x * spb;
+  const int ns = (int)min((long long)spb, batch - s0);
+  // S[s][i][j], row stride F4, zero padded
+  for (int e = threadIdx.x; e < ns * F * F4; e += blockDim.x) {
+    const int s = e / (F * F4);
+    const int rem = e - s * F * F4;
+    const int i = rem / F4, j = rem - i * F4;
+    float v = 0.f;
+    if (j < F) {
+      const float* g = dR + (s0 + s) * lddr + D;
+      if (i == j) {
+        if (itself) v = 2.f * g[i * (i + 1) / 2 + i];
+      } else {
+        const int hi = i > j ? i : j, lo = i > j ? j : i;
+        v = g[itself ? hi * (hi + 1) / 2 + lo : hi * (hi - 1) / 2 + lo];
+      }
+    }
+    smem[e] = v;
+  }
+  __syncthreads();
+  for (int item = threadIdx.x; item < ns * D; item += blockDim.x) {
+    const int s = item / D, d = item - s * D;
+    const float* Tb = T + (s0 + s) * ldt + d;
+    float t[MAXF];
+#pragma unroll
+    for (int j = 0; j < MAXF; ++j) t[j] = (j < F) ? Tb[(long long)j * D] : 0.f;
+    const float* Ss = smem + s * F * F4;
+    float* out = dT + (s0 + s) * lddt + d;
+    for (int i = 0; i < F; ++i) {
+      float acc = (i == 0) ? dR[(s0 + s) * lddr + d] : 0.f;
+#pragma unroll
+      for (int j4 = 0; j4 < MAXF / 4; ++j4) {
+        if (j4 * 4 < F) {
+          const float4 sv = *reinterpret_cast<const float4*>(Ss + i * F4 + j4 * 4);
+          acc = fmaf(sv.x, t[j4 * 4 + 0], acc);
+          acc = fmaf(sv.y, t[j4 * 4 + 1], acc);
+          acc = fmaf(sv.z, t[j4 * 4 + 2], acc);
+          acc = fmaf(sv.w, t[j4 * 4 + 3], acc);
+        }
+      }
+      if (i == 0 && mask0 == DLRM_ACT_RELU) acc = (t[0] > 0.f) ? acc : 0.f;
+      if (i == 0 && mask0 == DLRM_ACT_SIGMOID) acc *= (1.0f - t[0]) * t[0];
+      out[(long long)i * D] = acc;
+    }
+  }
+}
+
+}  // namespace dlrm
+
+extern "C" int dlrm_b200_interact_fwd(const float* T, int64_t ldt, float* R, int64_t ldr,
+                                      int64_t batch, int num_features, int dim, int itself,
+                                      void* stream) {
+  using namespace dlrm;
+  if (batch == 0) return 0;
+  if (num_features < 1 || dim < 1) return set_error("interact_fwd: F=%d D=%d", num_features, dim);
+  const int F = num_features, D = dim;
+  const int nb = (F + 2) / 3, Fp = nb * 3, tps = nb * (nb + 1) / 2;
+  const int npairs = itself ? F * (F + 1) / 2 : F * (F - 1) / 2;
+  const size_t per_sample = ((size_t)Fp * (D + 1) + npairs) * sizeof(float);
+  if (per_sample > 200 * 1024)
+    return set_error("interact_fwd: F=%d D=%d needs %zu B of shared memory per sample (max 200 KB)",
+                     F, D, per_sample);
+  int spb = 192 / tps;
+  if (spb < 1) spb = 1;
+  while (spb > 1 && spb * per_sample > 56 * 1024) --spb;
+  const size_t smem = spb * per_sample;
+  static thread_local size_t configured = 0;
+  if (smem > 48 * 1024 && smem > configured) {
+    DLRM_CUDA(cudaFuncSetAttribute(interact_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   200 * 1024));
+    configured = 200 * 1024;
+  }
+  const long long grid = (batch + spb - 1) / spb;
+  interact_fwd_kernel<<<(unsigned)grid, 192, smem, static_cast<cudaStream_t>(stream)>>>(
+      T, ldt, R, ldr, batch, F, D, itself, spb);
+  DLRM_CHECK_LAUNCH("interact_fwd_kernel");
+  return 0;
+}
+
+extern "C" int dlrm_b200_interact_bwd(const float* T, int64_t ldt, const float* dR, int64_t lddr,
+                                      float* dT, int64_t lddt, int64_t batch, int num_features,
+                                      int dim, int itself, int mask_feature0, void* stream) {
+  using namespace dlrm;
+  if (batch == 0) return 0;
+  const int F = num_features, D = dim;
+  if (F < 1 || D < 1) return set_error("interact_bwd: F=%d D=%d", F, D);
+  if (F > 64) return set_error("interact_bwd: num_features=%d > 64 not supported yet", F);
+  const int F4 = (F + 3) & ~3;
+  int spb = 128 / D;
+  if (spb < 1) spb = 1;
+  const size_t smem = (size_t)spb * F * F4 * sizeof(float);
+  if (smem > 48 * 1024) return set_error("interact_bwd: shared memory %zu too large", smem);
+  const long long grid = (batch + spb - 1) / spb;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (F <= 8)
+    interact_bwd_kernel<8><<<(unsigned)grid, 128, smem, st>>>(T, ldt, dR, lddr, dT, lddt, batch, F, D, itself, mask_feature0, spb);
+  else if (F <= 32)
+    interact_bwd_kernel<32><<<(unsigned)grid, 128, smem, st>>>(T, ldt, dR, lddr, dT, lddt, batch, F, D, itself, mask_feature0, spb);
+  else
+    interact_bwd_kernel<64><<<(unsigned)grid, 128, smem, st>>>(T, ldt, dR, lddr, dT, lddt, batch, F, D, itself, mask_feature0, spb);
+  DLRM_CHECK_LAUNCH("interact_bwd_kernel");
+  return 0;
+}

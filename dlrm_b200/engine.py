@@ -1,0 +1,460 @@
+"""Device-side engine of the DLRM hot path on one B200.
+
+Owns the HBM layout (one table arena, one dense-parameter arena, activation/gradient buffers
+written in place by the producing kernels) and sequences the C-ABI kernels of
+``include/dlrm_b200.h`` for
+
+    forward            == DLRM_Net.sequential_forward          (dlrm_s_pytorch.py:587-612)
+    train_step         == forward + loss_fn_wrap + backward + optimizer.step()  (:1575-1621)
+
+PyTorch is used for device memory and streams only; every FLOP/byte of the path runs in
+libdlrm_b200.so.  No CPU fallback exists: a missing library or device raises.
+
+HBM layout (fp32 unless noted)
+  tables   [sum_k rows_k, D]   one allocation; table k = rows [row_base_k, row_base_k + rows_k)
+  momentum [sum_k rows_k]      RWSAdagrad row-wise accumulator (optim/rwsadagrad.py:91-95)
+  head     [sum_k rows_k] i32  per-row list heads for the sort-free coalesce (zero between steps)
+  dense    [P]                 bot W0,b0,W1,b1,... top W0,b0,...  (+ grad arena, + Adagrad sums)
+  T        [B, F, D]           interaction operand: feature 0 <- last bottom-MLP epilogue,
+                               feature 1+k <- gather of table k (torch.cat K3 eliminated)
+  R        [B, ldr]            [x | tril(T T^T)]  (ldr = num_int rounded up to a multiple of 4)
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+from typing import List, Optional, Sequence
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import (ACT_NONE, ACT_RELU, ACT_SIGMOID, GEMM_SIMT_FP32, LOSS_BCE, LOSS_MSE, LOSS_WBCE,
+                   OPT_RWSADAGRAD, OPT_SGD, EmbBwdTable, EmbFwdTable)
+
+_LOSS = {"mse": LOSS_MSE, "bce": LOSS_BCE, "wbce": LOSS_WBCE}
+_OPT = {"sgd": OPT_SGD, "rwsadagrad": OPT_RWSADAGRAD}
+
+
+def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+@dataclass
+class SparseInput:
+    """Sparse side of one batch, on the device.
+
+    reference format : ``indices[k]`` 1-D per table, ``offsets[k]`` [B] (lS_i / lS_o of
+                       dlrm_s_pytorch.py:517); include_last = False.
+    packed format    : all tables share one ``indices`` array, ``offsets[k]`` holds B+1 GLOBAL
+                       positions into it; include_last = True (CUDA-graph friendly: sizes live on
+                       the device, pointers never change).
+    """
+    indices: List[torch.Tensor]
+    offsets: List[torch.Tensor]
+    batch: int
+    include_last: bool = False
+    nnz_total: int = -1
+
+    @property
+    def idx_bytes(self) -> int:
+        return self.indices[0].element_size()
+
+
+class Engine:
+    def __init__(self, m_spa: int, ln_emb: Sequence[int], ln_bot: Sequence[int], ln_top: Sequence[int],
+                 *, op: str = "dot", itself: bool = False, sigmoid_bot: int = -1, sigmoid_top: int = -1,
+                 loss: str = "bce", loss_threshold: float = 0.0, loss_ws=None, device="cuda:0",
+                 max_batch: int = 2048, gemm: str = "simt", table_rows_local: Optional[Sequence[int]] = None):
+        if not torch.cuda.is_available():
+            raise RuntimeError("dlrm_b200.Engine needs a CUDA device (B200, sm_100a); there is no CPU path")
+        self.device = torch.device(device)
+        self.lib = _lib.lib()
+        sm, major, minor = _lib.device_info(self.device.index or 0)
+        self.sm_count = sm
+        self.D = int(m_spa)
+        self.ln_emb = [int(v) for v in ln_emb]
+        self.ln_bot = [int(v) for v in ln_bot]
+        self.ln_top = [int(v) for v in ln_top]
+        self.T = len(self.ln_emb)
+        self.F = self.T + 1
+        self.op, self.itself = op, bool(itself)
+        if op not in ("dot", "cat"):
+            raise ValueError("arch_interaction_op=%s is not supported" % op)
+        self.sigmoid_bot, self.sigmoid_top = int(sigmoid_bot), int(sigmoid_top)
+        self.loss_kind = _LOSS[loss]
+        self.loss_threshold = float(loss_threshold)
+        self.gemm = GEMM_SIMT_FP32 if gemm == "simt" else gemm
+        if self.ln_bot[-1] != self.D:
+            raise ValueError("bottom MLP output %d != sparse feature size %d" % (self.ln_bot[-1], self.D))
+        if op == "dot":
+            self.num_int = self.D + (self.F * (self.F + 1) // 2 if itself else self.F * (self.F - 1) // 2)
+        else:
+            self.num_int = self.F * self.D
+        if self.ln_top[0] != self.num_int:
+            raise ValueError("# of feature interactions %d does not match first dimension of top mlp %d"
+                             % (self.num_int, self.ln_top[0]))
+        dev = self.device
+        # ---- tables
+        rows = np.asarray(self.ln_emb, dtype=np.int64)
+        self.row_base = np.concatenate([[0], np.cumsum(rows)]).astype(np.int64)
+        self.total_rows = int(self.row_base[-1])
+        self.tables = torch.empty((self.total_rows, self.D), dtype=torch.float32, device=dev)
+        self.head = torch.zeros(self.total_rows, dtype=torch.int32, device=dev)
+        self.momentum: Optional[torch.Tensor] = None
+        self.row_weights: Optional[torch.Tensor] = None  # weighted pooling v_W_l, arena [total_rows]
+        # ---- dense arena
+        self.dense_slices = []  # (name, layer, kind, offset, shape)
+        ofs = 0
+        for name, ln in (("bot", self.ln_bot), ("top", self.ln_top)):
+            for i in range(len(ln) - 1):
+                n_in, n_out = ln[i], ln[i + 1]
+                self.dense_slices.append((name, i, "W", ofs, (n_out, n_in)))
+                ofs += n_out * n_in
+                ofs = (ofs + 3) & ~3  # keep every tensor 16-byte aligned
+                self.dense_slices.append((name, i, "b", ofs, (n_out,)))
+                ofs += n_out
+                ofs = (ofs + 3) & ~3
+        self.dense_numel = ofs
+        self.dense = torch.zeros(ofs, dtype=torch.float32, device=dev)
+        self.dense_grad = torch.zeros(ofs, dtype=torch.float32, device=dev)
+        self.dense_state: Optional[torch.Tensor] = None
+        self.W = {"bot": [], "top": []}
+        self.b = {"bot": [], "top": []}
+        self.dW = {"bot": [], "top": []}
+        self.db = {"bot": [], "top": []}
+        for name, i, kind, o, shape in self.dense_slices:
+            n = int(np.prod(shape))
+            (self.W if kind == "W" else self.b)[name].append(self.dense[o:o + n].view(shape))
+            (self.dW if kind == "W" else self.db)[name].append(self.dense_grad[o:o + n].view(shape))
+        self.loss_ws = None
+        if loss_ws is not None:
+            self.loss_ws = torch.as_tensor(loss_ws, dtype=torch.float32, device=dev)
+        self.opt_step = 0
+        self.n_launch = 0            # kernels launched by this engine (bench: gpu_launches)
+        self._gather_events = None   # optional (start, end) CUDA events recorded around the gather
+        self._alloc_activations(int(max_batch))
+
+    # ------------------------------------------------------------------ buffers
+    def _alloc_activations(self, B: int):
+        dev, f32 = self.device, torch.float32
+        self.max_batch = B
+        D, F = self.D, self.F
+        self.Tbuf = torch.zeros((B, F, D), dtype=f32, device=dev)
+        self.ldr = (self.num_int + 3) & ~3
+        self.Rbuf = torch.zeros((B, self.ldr), dtype=f32, device=dev) if self.op == "dot" else None
+        nb, nt = len(self.ln_bot) - 1, len(self.ln_top) - 1
+        # post-activation outputs of every layer (last bottom layer lives in Tbuf[:, 0, :])
+        self.bot_act = [torch.empty((B, self.ln_bot[i + 1]), dtype=f32, device=dev) for i in range(nb - 1)]
+        self.top_act = [torch.empty((B, self.ln_top[i + 1]), dtype=f32, device=dev) for i in range(nt)]
+        # gradients w.r.t. pre-activations
+        self.bot_gz = [torch.empty((B, self.ln_bot[i + 1]), dtype=f32, device=dev) for i in range(nb - 1)]
+        self.top_gz = [torch.empty((B, self.ln_top[i + 1]), dtype=f32, device=dev) for i in range(nt)]
+        self.dT = torch.zeros((B, F, D), dtype=f32, device=dev)
+        self.dR = torch.zeros((B, self.ldr), dtype=f32, device=dev) if self.op == "dot" else None
+        self.loss_buf = torch.zeros(1, dtype=f32, device=dev)
+        self.scratch = torch.zeros(1024, dtype=f32, device=dev)
+        self.link = None  # int32 [2 * nnz capacity]
+
+    def _ensure_link(self, nnz_total: int):
+        if self.link is None or self.link.numel() < 2 * nnz_total:
+            cap = max(2 * nnz_total, 1024)
+            self.link = torch.empty(cap, dtype=torch.int32, device=self.device)
+
+    def table(self, k: int) -> torch.Tensor:
+        return self.tables[int(self.row_base[k]):int(self.row_base[k + 1])]
+
+    def ensure_optimizer_state(self, optimizer: str):
+        if optimizer == "rwsadagrad":
+            if self.momentum is None:
+                self.momentum = torch.zeros(self.total_rows, dtype=torch.float32, device=self.device)
+            if self.dense_state is None:
+                self.dense_state = torch.zeros_like(self.dense)
+
+    # ------------------------------------------------------------------ parameters
+    def load_params(self, params: dict):
+        """params = dict(emb=[W_k], bot=[(W,b)...], top=[(W,b)...], v_W_l=None|[...]) of numpy /
+        torch arrays (the layout of the oracle and of the reference's state_dict)."""
+        with torch.no_grad():
+            for k, Wk in enumerate(params["emb"]):
+                self.table(k).copy_(torch.as_tensor(Wk, dtype=torch.float32))
+            for name in ("bot", "top"):
+                for i, (Wl, bl) in enumerate(params[name]):
+                    self.W[name][i].copy_(torch.as_tensor(Wl, dtype=torch.float32))
+                    self.b[name][i].copy_(torch.as_tensor(bl, dtype=torch.float32))
+            if params.get("v_W_l") is not None:
+                self.row_weights = torch.empty(self.total_rows, dtype=torch.float32, device=self.device)
+                for k, w in enumerate(params["v_W_l"]):
+                    self.row_weights[int(self.row_base[k]):int(self.row_base[k + 1])].copy_(
+                        torch.as_tensor(w, dtype=torch.float32))
+
+    def init_params(self, seed: int = 0):
+        """Same distributions as create_emb / create_mlp (dlrm_s_pytorch.py:221-228, :280-284),
+        drawn on the device (26 x 1e6 x 128 takes 150 s with the reference's numpy init)."""
+        g = torch.Generator(device=self.device)
+        g.manual_seed(seed)
+        with torch.no_grad():
+            for k, n in enumerate(self.ln_emb):
+                a = float(np.sqrt(1.0 / n))
+                self.table(k).uniform_(-a, a, generator=g)
+            for name, ln in (("bot", self.ln_bot), ("top", self.ln_top)):
+                for i in range(len(ln) - 1):
+                    n, m = ln[i], ln[i + 1]
+                    self.W[name][i].normal_(0.0, float(np.sqrt(2.0 / (m + n))), generator=g)
+                    self.b[name][i].normal_(0.0, float(np.sqrt(1.0 / m)), generator=g)
+
+    # ------------------------------------------------------------------ descriptors
+    def _fwd_desc(self, sp: SparseInput, tables=None):
+        ks = range(self.T) if tables is None else tables
+        arr = (EmbFwdTable * len(ks))()
+        for n, k in enumerate(ks):
+            d = arr[n]
+            d.weight = self.tables.data_ptr() + int(self.row_base[k]) * self.D * 4
+            d.indices = sp.indices[k].data_ptr() if sp.indices[k].numel() else 0
+            d.offsets = sp.offsets[k].data_ptr()
+            d.row_weights = (self.row_weights.data_ptr() + int(self.row_base[k]) * 4
+                             if self.row_weights is not None else None)
+            d.nnz = sp.indices[k].numel()
+            d.rows = self.ln_emb[k]
+        return arr
+
+    def _bwd_desc(self, sp: SparseInput, tables=None):
+        ks = range(self.T) if tables is None else tables
+        arr = (EmbBwdTable * len(ks))()
+        base = 0
+        for n, k in enumerate(ks):
+            d = arr[n]
+            d.weight = self.tables.data_ptr() + int(self.row_base[k]) * self.D * 4
+            d.momentum = (self.momentum.data_ptr() + int(self.row_base[k]) * 4
+                          if self.momentum is not None else None)
+            d.head = self.head.data_ptr() + int(self.row_base[k]) * 4
+            d.indices = sp.indices[k].data_ptr() if sp.indices[k].numel() else 0
+            d.offsets = sp.offsets[k].data_ptr()
+            d.nnz = sp.indices[k].numel()
+            d.rows = self.ln_emb[k]
+            d.pair_base = 0 if sp.include_last else base
+            base += sp.indices[k].numel()
+        total = sp.nnz_total if sp.include_last else base
+        return arr, total
+
+    # ------------------------------------------------------------------ kernels
+    def _act(self, which: str, i: int) -> int:
+        sig = self.sigmoid_bot if which == "bot" else self.sigmoid_top
+        return ACT_SIGMOID if i == sig else ACT_RELU
+
+    def emb_forward(self, sp: SparseInput, out: torch.Tensor, stride_sample: int, stride_table: int):
+        chk = _lib.check
+        for c0 in range(0, self.T, _lib.MAX_TABLES):
+            ks = list(range(c0, min(self.T, c0 + _lib.MAX_TABLES)))
+            desc = self._fwd_desc(sp, ks)
+            chk(self.lib.dlrm_b200_emb_bag_fwd(desc, len(ks), self.D, sp.batch, sp.idx_bytes,
+                                               int(sp.include_last),
+                                               out.data_ptr() + c0 * stride_table * 4, stride_sample,
+                                               stride_table, _stream()), "emb_bag_fwd")
+            self.n_launch += 1
+
+    def mlp_forward(self, which: str, x: torch.Tensor, ldx: int, B: int, outs: List[torch.Tensor],
+                    lds: List[int]):
+        ln = self.ln_bot if which == "bot" else self.ln_top
+        for i in range(len(ln) - 1):
+            K, N = ln[i], ln[i + 1]
+            _lib.check(self.lib.dlrm_b200_linear_fwd(x.data_ptr(), ldx, self.W[which][i].data_ptr(), K,
+                                                     self.b[which][i].data_ptr(), outs[i].data_ptr(),
+                                                     lds[i], B, N, K, self._act(which, i), self.gemm,
+                                                     _stream()), "linear_fwd")
+            self.n_launch += 1
+            x, ldx = outs[i], lds[i]
+
+    def _bot_outs(self, B):
+        outs = list(self.bot_act) + [self.Tbuf]
+        lds = [t.shape[1] for t in self.bot_act] + [self.F * self.D]
+        return outs, lds
+
+    def _top_in(self):
+        if self.op == "dot":
+            return self.Rbuf, self.ldr
+        return self.Tbuf, self.F * self.D
+
+    def forward(self, X: torch.Tensor, sp: SparseInput) -> torch.Tensor:
+        """sequential_forward.  X [B, m_den] fp32 on the device.  Returns p [B, n_out] (a view of an
+        engine buffer, valid until the next call); clamped iff 0 < loss_threshold < 1."""
+        B = sp.batch
+        if B > self.max_batch:
+            self._alloc_activations(B)
+        FD = self.F * self.D
+        outs, lds = self._bot_outs(B)
+        self.mlp_forward("bot", X, X.stride(0), B, outs, lds)
+        if self.T:
+            ev = self._gather_events
+            if ev is not None:
+                ev[0].record()
+            self.emb_forward(sp, self.Tbuf.view(-1)[self.D:], FD, self.D)
+            if ev is not None:
+                ev[1].record()
+        if self.op == "dot":
+            _lib.check(self.lib.dlrm_b200_interact_fwd(self.Tbuf.data_ptr(), FD, self.Rbuf.data_ptr(),
+                                                       self.ldr, B, self.F, self.D, int(self.itself),
+                                                       _stream()), "interact_fwd")
+            self.n_launch += 1
+        xin, ldx = self._top_in()
+        self.mlp_forward("top", xin, ldx, B, self.top_act, [t.shape[1] for t in self.top_act])
+        p = self.top_act[-1][:B]
+        if 0.0 < self.loss_threshold < 1.0:
+            return torch.clamp(p, self.loss_threshold, 1.0 - self.loss_threshold)
+        return p
+
+    def emb_link(self, sp: SparseInput):
+        """Thread this batch's (table,row) occurrences onto per-row lists.  Indices only: may be
+        issued on a side stream, concurrently with the forward pass."""
+        total = sp.nnz_total if sp.include_last else sum(int(i.numel()) for i in sp.indices)
+        self._ensure_link(total)
+        for c0 in range(0, self.T, _lib.MAX_TABLES):
+            ks = list(range(c0, min(self.T, c0 + _lib.MAX_TABLES)))
+            desc, _ = self._bwd_desc_chunk(sp, ks)
+            _lib.check(self.lib.dlrm_b200_emb_bwd_link(desc, len(ks), sp.batch, sp.idx_bytes,
+                                                       int(sp.include_last), self.link.data_ptr(),
+                                                       _stream()), "emb_bwd_link")
+            self.n_launch += 1
+
+    def _bwd_desc_chunk(self, sp, ks):
+        # pair_base must be global over ALL tables of the batch, not per chunk
+        arr, total = self._bwd_desc(sp, range(self.T))
+        sub = (EmbBwdTable * len(ks))()
+        for n, k in enumerate(ks):
+            C.memmove(C.byref(sub[n]), C.byref(arr[k]), C.sizeof(EmbBwdTable))
+        return sub, total
+
+    def emb_update(self, sp: SparseInput, dY: torch.Tensor, stride_sample: int, stride_table: int,
+                   optimizer: str, lr: float, eps: float = 1e-10):
+        for c0 in range(0, self.T, _lib.MAX_TABLES):
+            ks = list(range(c0, min(self.T, c0 + _lib.MAX_TABLES)))
+            desc, _ = self._bwd_desc_chunk(sp, ks)
+            _lib.check(self.lib.dlrm_b200_emb_bwd_update(desc, len(ks), self.D, sp.batch, sp.idx_bytes,
+                                                         int(sp.include_last), self.link.data_ptr(),
+                                                         dY.data_ptr() + c0 * stride_table * 4,
+                                                         stride_sample, stride_table, _OPT[optimizer],
+                                                         lr, eps, _stream()), "emb_bwd_update")
+            self.n_launch += 1
+
+    def mlp_backward(self, which: str, x_in: torch.Tensor, ldx: int, in_act: int, B: int,
+                     acts: List[torch.Tensor], act_ld: List[int], gz: List[torch.Tensor],
+                     gz_ld: List[int], dx: Optional[torch.Tensor], lddx: int):
+        """gz[-1] holds the gradient w.r.t. the last pre-activation.  Produces dW/db for every
+        layer and (if dx is given) the gradient w.r.t. the stack input, times in_act'(x_in)."""
+        ln = self.ln_bot if which == "bot" else self.ln_top
+        s = _stream()
+        for i in reversed(range(len(ln) - 1)):
+            K, N = ln[i], ln[i + 1]
+            xin, ldxi = (x_in, ldx) if i == 0 else (acts[i - 1], act_ld[i - 1])
+            _lib.check(self.lib.dlrm_b200_linear_wgrad(gz[i].data_ptr(), gz_ld[i], xin.data_ptr(), ldxi,
+                                                       self.dW[which][i].data_ptr(), K,
+                                                       self.db[which][i].data_ptr(), B, N, K, self.gemm, s),
+                       "linear_wgrad")
+            self.n_launch += 2  # GEMM + column sum (bias grad)
+            if i > 0:
+                _lib.check(self.lib.dlrm_b200_linear_dgrad(gz[i].data_ptr(), gz_ld[i],
+                                                           self.W[which][i].data_ptr(), K,
+                                                           acts[i - 1].data_ptr(), act_ld[i - 1],
+                                                           self._act(which, i - 1), gz[i - 1].data_ptr(),
+                                                           gz_ld[i - 1], B, N, K, self.gemm, s),
+                           "linear_dgrad")
+                self.n_launch += 1
+            elif dx is not None:
+                _lib.check(self.lib.dlrm_b200_linear_dgrad(gz[0].data_ptr(), gz_ld[0],
+                                                           self.W[which][0].data_ptr(), K,
+                                                           _ptr(x_in) if in_act != ACT_NONE else None, ldx,
+                                                           in_act, dx.data_ptr(), lddx, B, N, K, self.gemm, s),
+                           "linear_dgrad")
+                self.n_launch += 1
+
+    def loss_and_grad(self, target: torch.Tensor, B: int, want_grad: bool = True):
+        p = self.top_act[-1]
+        n = B * p.shape[1]
+        last = self._act("top", len(self.ln_top) - 2)
+        _lib.check(self.lib.dlrm_b200_loss_fwd_bwd(p.data_ptr(), target.data_ptr(), _ptr(self.loss_ws), n,
+                                                   self.loss_kind, self.loss_threshold, last,
+                                                   self.loss_buf.data_ptr(),
+                                                   self.top_gz[-1].data_ptr() if want_grad else None,
+                                                   self.scratch.data_ptr(), _stream()), "loss_fwd_bwd")
+        self.n_launch += 1
+        return self.loss_buf
+
+    def backward(self, X: torch.Tensor, sp: SparseInput, target: torch.Tensor):
+        """Everything between the loss and the parameter gradients.  Leaves dense grads in
+        dense_grad and the per-bag embedding grads in dT[:, 1:, :]."""
+        B = sp.batch
+        FD = self.F * self.D
+        self.loss_and_grad(target, B)
+        top_ld = [t.shape[1] for t in self.top_act]
+        xin, ldx = self._top_in()
+        bot_last_act = self._act("bot", len(self.ln_bot) - 2)
+        if self.op == "dot":
+            self.mlp_backward("top", xin, ldx, ACT_NONE, B, self.top_act, top_ld, self.top_gz, top_ld,
+                              self.dR, self.ldr)
+            _lib.check(self.lib.dlrm_b200_interact_bwd(self.Tbuf.data_ptr(), FD, self.dR.data_ptr(), self.ldr,
+                                                       self.dT.data_ptr(), FD, B, self.F, self.D,
+                                                       int(self.itself), bot_last_act, _stream()),
+                       "interact_bwd")
+            self.n_launch += 1
+        else:
+            # cat: dR == dT; feature 0 additionally goes through the bottom MLP's last activation
+            self.mlp_backward("top", xin, ldx, ACT_NONE, B, self.top_act, top_ld, self.top_gz, top_ld,
+                              None, 0)
+            K, N = self.ln_top[0], self.ln_top[1]
+            s = _stream()
+            Wp = self.W["top"][0].data_ptr()
+            _lib.check(self.lib.dlrm_b200_linear_dgrad(self.top_gz[0].data_ptr(), top_ld[0], Wp, K,
+                                                       self.Tbuf.data_ptr(), FD, bot_last_act,
+                                                       self.dT.data_ptr(), FD, B, N, self.D, self.gemm, s),
+                       "linear_dgrad")
+            if self.T:
+                _lib.check(self.lib.dlrm_b200_linear_dgrad(self.top_gz[0].data_ptr(), top_ld[0],
+                                                           Wp + self.D * 4, K, None, 0, ACT_NONE,
+                                                           self.dT.data_ptr() + self.D * 4, FD, B, N,
+                                                           K - self.D, self.gemm, s), "linear_dgrad")
+            self.n_launch += 2
+        acts, lds = self._bot_outs(B)
+        gz = list(self.bot_gz) + [self.dT]
+        gz_ld = [t.shape[1] for t in self.bot_gz] + [FD]
+        self.mlp_backward("bot", X, X.stride(0), ACT_NONE, B, acts, lds, gz, gz_ld, None, 0)
+
+    def dense_step(self, optimizer: str, lr: float, eps: float = 1e-10):
+        _lib.check(self.lib.dlrm_b200_dense_update(self.dense.data_ptr(), self.dense_grad.data_ptr(),
+                                                   _ptr(self.dense_state), self.dense_numel, _OPT[optimizer],
+                                                   lr, eps, _stream()), "dense_update")
+        self.n_launch += 1
+
+    def train_step(self, X: torch.Tensor, sp: SparseInput, target: torch.Tensor, lr: float,
+                   optimizer: str = "rwsadagrad", lr_decay: float = 0.0, link_done: bool = False):
+        """forward + loss + backward + optimizer.step().  Returns the loss (1-element device
+        tensor, not synchronised)."""
+        self.ensure_optimizer_state(optimizer)
+        if not link_done and self.T:
+            self.emb_link(sp)
+        self.forward(X, sp)
+        self.backward(X, sp, target)
+        self.opt_step += 1
+        clr = lr / (1.0 + (self.opt_step - 1.0) * lr_decay) if optimizer == "rwsadagrad" else lr
+        if self.T:
+            self.emb_update(sp, self.dT.view(-1)[self.D:], self.F * self.D, self.D, optimizer, clr)
+        self.dense_step(optimizer, clr)
+        return self.loss_buf
+
+
+def sparse_from_reference(lS_o, lS_i, device) -> SparseInput:
+    """lS_o: [T,B] tensor or list; lS_i: list of 1-D tensors or stacked 2-D tensor
+    (dlrm_s_pytorch.py:129-145 conventions).  Moves to `device` if needed (no dtype change)."""
+    if isinstance(lS_i, torch.Tensor):
+        lS_i = [lS_i[k] for k in range(lS_i.shape[0])]
+    if isinstance(lS_o, torch.Tensor):
+        lS_o = [lS_o[k] for k in range(lS_o.shape[0])]
+    idx = [t.to(device).contiguous() for t in lS_i]
+    off = [t.to(device).contiguous() for t in lS_o]
+    B = int(off[0].numel()) if off else 0
+    if idx and off and idx[0].dtype != off[0].dtype:
+        raise RuntimeError("indices and offsets must have the same dtype (int64 or int32)")
+    return SparseInput(idx, off, B, False)

@@ -1,0 +1,168 @@
+/*
+ * dlrm_b200.h -- C ABI of libdlrm_b200.so: the B200 (sm_100a) kernels behind the
+ * DLRM_Net forward/backward hot path of facebookresearch/dlrm.
+ *
+ * The reference has NO native interface for this path: every op below replaces an
+ * ATen call made from dlrm_s_pytorch.py (cited per entry point).  A maintainer of
+ * the reference binds these with ctypes; dlrm_b200/_lib.py is
+ * exactly that binding.
+ *
+ * Conventions
+ *   - extern "C", plain pointers and sizes; no torch types.
+ *   - every pointer is a DEVICE pointer on the current CUDA device unless marked
+ *     [host]; the caller (PyTorch) owns all memory, the library allocates nothing
+ *     and keeps no pointer beyond the call (except inside explicit handles).
+ *   - `stream` is a cudaStream_t passed as void* (0 = legacy default stream).
+ *     All work is enqueued asynchronously on it; no hidden synchronisation, so
+ *     every entry point is legal inside CUDA-graph stream capture.
+ *   - return 0 on success, <0 on error; dlrm_b200_last_error() gives the text
+ *     (thread-local).  Unsupported shapes are errors, never silent fallbacks.
+ *   - float = IEEE fp32.  Index/offset tensors are int64 (idx_bytes=8) or int32
+ *     (idx_bytes=4), both arrays of one call having the same width, exactly as
+ *     nn.EmbeddingBag accepts them; they are consumed bit-for-bit, never copied.
+ */
+#ifndef DLRM_B200_H_
+#define DLRM_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DLRM_B200_ABI_VERSION 1
+#define DLRM_B200_MAX_TABLES_PER_CALL 64 /* larger T: split into several calls */
+
+/* activations of create_mlp (dlrm_s_pytorch.py:237-241) */
+enum { DLRM_ACT_NONE = 0, DLRM_ACT_RELU = 1, DLRM_ACT_SIGMOID = 2 };
+/* loss functions (dlrm_s_pytorch.py:385-393) */
+enum { DLRM_LOSS_MSE = 0, DLRM_LOSS_BCE = 1, DLRM_LOSS_WBCE = 2 };
+/* sparse optimizers: torch.optim.SGD (dlrm_s_pytorch.py:1343) / optim/rwsadagrad.py */
+enum { DLRM_OPT_SGD = 0, DLRM_OPT_RWSADAGRAD = 1 };
+/* GEMM back ends */
+enum { DLRM_GEMM_SIMT_FP32 = 0, DLRM_GEMM_TC_BF16X3 = 1, DLRM_GEMM_TC_BF16 = 2 };
+
+int dlrm_b200_abi_version(void);
+const char* dlrm_b200_last_error(void);
+/* sm count / compute capability of `device`; error unless cc >= 10.0 */
+int dlrm_b200_device_info(int device, int* sm_count, int* cc_major, int* cc_minor);
+
+/* ------------------------------------------------------------------------------------------
+ * apply_emb  (dlrm_s_pytorch.py:407-462: one nn.EmbeddingBag(mode="sum") call per table)
+ * ONE launch for all tables:  out[b, k, :] = sum_{j in bag(k,b)} rw_k[idx_k[j]] * W_k[idx_k[j], :]
+ * accumulated sequentially in index order (bit-identical to the reference CPU kernel when
+ * row_weights == NULL).  Bag b of table k is idx[off[b] .. off[b+1]) and the last bag runs to
+ * nnz (EmbeddingBag without include_last_offset) unless include_last != 0, in which case
+ * offsets has batch+1 entries and `nnz` is ignored (graph-replay friendly).  Empty bag -> 0.
+ * ------------------------------------------------------------------------------------------ */
+typedef struct {
+  const float* weight;      /* [rows, dim] row-major, 16-byte aligned when dim % 4 == 0 */
+  const void* indices;      /* [nnz]   int64 / int32 */
+  const void* offsets;      /* [batch] (or [batch+1] when include_last) same type */
+  const float* row_weights; /* NULL, or [rows]: v_W_l[k] (weighted pooling, :425-428) */
+  int64_t nnz;
+  int64_t rows;             /* for bounds checks in debug builds */
+} dlrm_emb_fwd_table_t;
+
+int dlrm_b200_emb_bag_fwd(const dlrm_emb_fwd_table_t* tables /*[host]*/, int num_tables, int dim,
+                          int64_t batch, int idx_bytes, int include_last,
+                          float* out, int64_t out_stride_sample, int64_t out_stride_table,
+                          void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Embedding backward fused with the sparse optimizer
+ * (autograd _embedding_bag_backward, dlrm_s_pytorch.py:1613 + optimizer.step() :1620:
+ *  optim/rwsadagrad.py:117-143 or torch.optim.SGD sparse add).
+ *
+ * Step 1, dlrm_b200_emb_bwd_link: depends on the indices only (can run on a side stream
+ * during the forward pass).  Threads every (table,row) occurrence of the batch onto a
+ * per-row list: prev = atomicExch(&head[row], pos+1); next[pos] = prev.  `head` is an int32
+ * array over all rows of the table, zero on entry and zero again after step 2.
+ * Step 2, dlrm_b200_emb_bwd_update: one warp per bag; the list head (= unique owner of a row)
+ * sums dY over the row's occurrences in ascending position (== grad.coalesce()), then
+ *   RWSAdagrad: momentum[row] += mean_d(g^2); W[row] -= lr * g / (sqrt(momentum[row]) + eps)
+ *   SGD:        W[row] -= lr * g
+ * `lr` is the already-decayed clr of optim/rwsadagrad.py:115.
+ * dY[b, k, :] is read at dY + b*dy_stride_sample + k*dy_stride_table.
+ * ------------------------------------------------------------------------------------------ */
+typedef struct {
+  float* weight;        /* [rows, dim] updated in place */
+  float* momentum;      /* [rows] (RWSAdagrad) or NULL (SGD) */
+  int32_t* head;        /* [rows] zero-initialised scratch, self-cleaning */
+  const void* indices;  /* as in forward */
+  const void* offsets;
+  int64_t nnz;
+  int64_t rows;
+  int64_t pair_base;    /* first slot of this table in next[] / (sum of nnz of earlier tables) */
+} dlrm_emb_bwd_table_t;
+
+int dlrm_b200_emb_bwd_link(const dlrm_emb_bwd_table_t* tables /*[host]*/, int num_tables,
+                           int64_t batch, int idx_bytes, int include_last,
+                           int32_t* next /*[total nnz]*/, void* stream);
+
+int dlrm_b200_emb_bwd_update(const dlrm_emb_bwd_table_t* tables /*[host]*/, int num_tables, int dim,
+                             int64_t batch, int idx_bytes, int include_last,
+                             const int32_t* next, const float* dY, int64_t dy_stride_sample,
+                             int64_t dy_stride_table, int optimizer, float lr, float eps,
+                             void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * apply_mlp layer (dlrm_s_pytorch.py:399-405: nn.Linear -> addmm, + ReLU / Sigmoid modules)
+ *   fwd  : Y[M,N]  = act(X[M,K] W[N,K]^T + bias[N])
+ *   dgrad: dX[M,K] = (dY[M,N] W[N,K]) * act'(Xact[M,K])   (Xact = output of the previous
+ *          layer, NULL / DLRM_ACT_NONE when the input is not an activation)
+ *   wgrad: dW[N,K] = dY[M,N]^T X[M,K];  dbias[N] = sum_m dY[m,n]
+ * ld* are row strides in elements.  backend = DLRM_GEMM_*.
+ * ------------------------------------------------------------------------------------------ */
+int dlrm_b200_linear_fwd(const float* X, int64_t ldx, const float* W, int64_t ldw, const float* bias,
+                         float* Y, int64_t ldy, int64_t M, int64_t N, int64_t K, int act,
+                         int backend, void* stream);
+int dlrm_b200_linear_dgrad(const float* dY, int64_t lddy, const float* W, int64_t ldw,
+                           const float* Xact, int64_t ldxa, int act_prev,
+                           float* dX, int64_t lddx, int64_t M, int64_t N, int64_t K,
+                           int backend, void* stream);
+int dlrm_b200_linear_wgrad(const float* dY, int64_t lddy, const float* X, int64_t ldx,
+                           float* dW, int64_t lddw, float* dbias, int64_t M, int64_t N, int64_t K,
+                           int backend, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * interact_features (dlrm_s_pytorch.py:483-515), op == "dot":
+ *   T[b] = [x[b]; ly_0[b]; ...] (F x D, read in place at T + b*ldt, feature stride D)
+ *   R[b, 0:D] = x[b];  R[b, D + tri(i,j)] = <T[b,i], T[b,j]>  for j < i (+ diagonal if itself),
+ *   row-major strict lower triangle (1,0),(2,0),(2,1),...  (cat/bmm/index/cat fused: K3-K6).
+ * bwd: dT[b] = (dZ + dZ^T) T[b] (+ dR[b,0:D] on feature 0), with dZ scattered from dR[b, D:];
+ *   feature 0 of dT is multiplied by act'(x), act = mask_feature0 (DLRM_ACT_*: the bottom MLP's
+ *   last activation; DLRM_ACT_NONE = no mask).
+ * op == "cat" is a pure layout (R == T flattened): no kernel, handled by strides on the host.
+ * ------------------------------------------------------------------------------------------ */
+int dlrm_b200_interact_fwd(const float* T, int64_t ldt, float* R, int64_t ldr, int64_t batch,
+                           int num_features, int dim, int itself, void* stream);
+int dlrm_b200_interact_bwd(const float* T, int64_t ldt, const float* dR, int64_t lddr,
+                           float* dT, int64_t lddt, int64_t batch, int num_features, int dim,
+                           int itself, int mask_feature0, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * loss_fn_wrap (dlrm_s_pytorch.py:148-156; MSELoss/BCELoss(mean), wbce) + clamp (:607-610)
+ * + backward through the loss, the clamp and the last activation:
+ *   z = clamp(p, thr, 1-thr) iff 0 < thr < 1;  loss = mean(l(z,t) [* ws[t]])
+ *   gz[i] = dloss/dz[i] * [thr <= p <= 1-thr] * act'(p[i])     (act = last layer's activation)
+ * n = batch * outputs (contiguous).  loss_out: 1 float; gz may be NULL (inference).
+ * `scratch` >= 1024 floats.  Deterministic (fixed reduction tree).
+ * ------------------------------------------------------------------------------------------ */
+int dlrm_b200_loss_fwd_bwd(const float* p, const float* target, const float* loss_ws /*[2] or NULL*/,
+                           int64_t n, int loss_kind, float loss_threshold, int last_act,
+                           float* loss_out, float* gz, float* scratch, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Dense parameters of optimizer.step(): flat arenas (all bot/top W and b, contiguous).
+ *   SGD:        p -= lr * g
+ *   RWSAdagrad dense branch (optim/rwsadagrad.py:145-148): s += g*g; p -= lr * g / (sqrt(s)+eps)
+ * ------------------------------------------------------------------------------------------ */
+int dlrm_b200_dense_update(float* param, const float* grad, float* state /*NULL for SGD*/,
+                           int64_t n, int optimizer, float lr, float eps, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DLRM_B200_H_ */

@@ -1,0 +1,48 @@
+"""CPU-side checks of the C-ABI boundary: the in-tree library loads and exports every symbol that
+include/dlrm_b200.h declares (no compute calls: there is no GPU here)."""
+import os
+import re
+
+from dlrm_b200 import _build, _lib
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def header_symbols():
+    src = open(os.path.join(ROOT, "include", "dlrm_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(dlrm_b200_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_library_exports_every_declared_symbol():
+    lib = _lib.lib()
+    syms = header_symbols()
+    assert len(syms) >= 13
+    for s in syms:
+        assert hasattr(lib, s), "libdlrm_b200.so does not export " + s
+    assert sorted(_lib.SYMBOLS) == syms, "dlrm_b200/_lib.py and the header disagree"
+
+
+def test_abi_version_and_error_text():
+    lib = _lib.lib()
+    assert lib.dlrm_b200_abi_version() == 1
+    # argument validation happens before any CUDA call -> testable without a device
+    rc = lib.dlrm_b200_emb_bag_fwd(None, 1000, 128, 1, 8, 0, None, 0, 0, None)
+    assert rc != 0
+    assert b"num_tables" in lib.dlrm_b200_last_error()
+
+
+def test_built_for_sm100a_only():
+    out = os.popen("cuobjdump -lelf %s 2>/dev/null" % _build.LIB).read()
+    assert "sm_100a" in out
+    assert "sm_90" not in out and "sm_80" not in out
+
+
+def test_product_does_not_import_oracle():
+    """The oracle is the checker: nothing under dlrm_b200/ may import or execute it."""
+    pkg = os.path.join(ROOT, "dlrm_b200")
+    for dp, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".cpp", ".h")):
+                txt = open(os.path.join(dp, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", txt, flags=re.M), f

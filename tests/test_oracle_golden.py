@@ -137,3 +137,40 @@ def test_empty_and_ragged_bags():
     assert np.array_equal(out[4], np.zeros(8, np.float32))
     # no bags at all
     assert O.emb_bag_sum(W, np.zeros(0, np.int64), np.zeros(0, np.int64)).shape == (0, 8)
+
+
+# ---- the torch-CPU port used as the timed CPU baseline on the GPU box
+@pytest.mark.parametrize("name", [c for c in ALL_CASES if c != "cfg0_weighted"])
+def test_torch_port_matches_reference(name):
+    import torch
+
+    from oracle.torch_cpu_port import CpuDLRM, RowWiseAdagradCPU
+
+    g = Golden(name)
+    m = CpuDLRM(g.m_spa, g.ln_emb, g.ln_bot, g.ln_top, op=g.op, itself=g.itself, loss=g.loss,
+                loss_threshold=g.thr)
+    m.load(g.params())
+
+    def tb(s):
+        X, off, idx, T = g.batch(s)
+        return (torch.from_numpy(X), [torch.from_numpy(o) for o in off], [torch.from_numpy(i) for i in idx],
+                torch.from_numpy(T))
+
+    X, o, i, T = tb(0)
+    with torch.no_grad():
+        p = m(X, o, i).numpy()
+    assert np.array_equal(p, g["f_out"]), "same ATen ops -> identical forward"
+    opt = RowWiseAdagradCPU(m.parameters(), lr=float(g["rwsadagrad_lr"]))
+    losses = []
+    for s in range(g.nsteps):
+        X, o, i, T = tb(s)
+        E = m.loss_fn(m(X, o, i), T)
+        losses.append(E.item())
+        opt.zero_grad()
+        E.backward()
+        opt.step()
+    np.testing.assert_allclose(losses, g["rwsadagrad_losses"], rtol=0, atol=1e-6)
+    X, o, i, T = tb(g.nsteps)
+    with torch.no_grad():
+        pa = m(X, o, i).numpy()
+    np.testing.assert_allclose(pa, g["rwsadagrad_p_after"], rtol=0, atol=1e-6)
