@@ -27,6 +27,26 @@ class EmbBwdTable(C.Structure):
                 ("rows", C.c_int64), ("pair_base", C.c_int64)]
 
 
+class GemmTcDesc(C.Structure):
+    _fields_ = [("A_hi", C.c_void_p), ("A_lo", C.c_void_p), ("lda", C.c_int64), ("a_mn_major", C.c_int),
+                ("B_hi", C.c_void_p), ("B_lo", C.c_void_p), ("ldb", C.c_int64), ("b_mn_major", C.c_int),
+                ("M", C.c_int64), ("N", C.c_int64), ("K", C.c_int64),
+                ("mode_x3", C.c_int), ("split_k", C.c_int), ("tile_n", C.c_int), ("act", C.c_int),
+                ("mask_act", C.c_int),
+                ("mask_hi", C.c_void_p), ("mask_lo", C.c_void_p), ("ldmask", C.c_int64),
+                ("out_f32", C.c_void_p), ("ld_f32", C.c_int64), ("slab_stride", C.c_int64),
+                ("out_hi", C.c_void_p), ("out_lo", C.c_void_p), ("ld_out", C.c_int64),
+                ("outT_hi", C.c_void_p), ("outT_lo", C.c_void_p), ("ld_outT", C.c_int64),
+                ("out_col", C.c_void_p), ("col_index", C.c_int64), ("col_slab_stride", C.c_int64)]
+
+
+class DenseLayer(C.Structure):
+    _fields_ = [("W", C.c_void_p), ("b", C.c_void_p), ("sW", C.c_void_p), ("sb", C.c_void_p),
+                ("dW", C.c_void_p), ("db", C.c_void_p), ("pack_hi", C.c_void_p), ("pack_lo", C.c_void_p),
+                ("slab_stride", C.c_int64), ("N", C.c_int64), ("K", C.c_int64), ("ld_pack", C.c_int64),
+                ("num_slabs", C.c_int64)]
+
+
 _lib = None
 
 # every symbol include/dlrm_b200.h declares (tests check the .so exports all of them)
@@ -36,6 +56,8 @@ SYMBOLS = [
     "dlrm_b200_linear_fwd", "dlrm_b200_linear_dgrad", "dlrm_b200_linear_wgrad",
     "dlrm_b200_interact_fwd", "dlrm_b200_interact_bwd", "dlrm_b200_loss_fwd_bwd",
     "dlrm_b200_dense_update",
+    "dlrm_b200_gemm_tc_plan_create", "dlrm_b200_gemm_tc_plan_info", "dlrm_b200_gemm_tc_run",
+    "dlrm_b200_gemm_tc_plan_destroy", "dlrm_b200_split_bf16", "dlrm_b200_dense_update_pack",
 ]
 
 
@@ -56,6 +78,12 @@ def _declare(lib):
     lib.dlrm_b200_interact_bwd.argtypes = [vp, i64, vp, i64, vp, i64, i64, i32, i32, i32, i32, vp]
     lib.dlrm_b200_loss_fwd_bwd.argtypes = [vp, vp, vp, i64, i32, f32, i32, vp, vp, vp, vp]
     lib.dlrm_b200_dense_update.argtypes = [vp, vp, vp, i64, i32, f32, f32, vp]
+    lib.dlrm_b200_gemm_tc_plan_create.argtypes = [C.POINTER(GemmTcDesc), C.POINTER(vp)]
+    lib.dlrm_b200_gemm_tc_plan_info.argtypes = [vp, C.POINTER(i32), C.POINTER(i32), C.POINTER(i32), C.POINTER(i32)]
+    lib.dlrm_b200_gemm_tc_run.argtypes = [vp, vp]
+    lib.dlrm_b200_gemm_tc_plan_destroy.argtypes = [vp]
+    lib.dlrm_b200_split_bf16.argtypes = [vp, i64, i64, i64, vp, vp, i64, vp]
+    lib.dlrm_b200_dense_update_pack.argtypes = [C.POINTER(DenseLayer), i32, i32, f32, f32, vp]
     for name in SYMBOLS:
         fn = getattr(lib, name)
         if name != "dlrm_b200_last_error":
@@ -95,3 +123,33 @@ def device_info(device=0):
     sm, ma, mi = C.c_int(), C.c_int(), C.c_int()
     check(lib().dlrm_b200_device_info(device, C.byref(sm), C.byref(ma), C.byref(mi)), "device_info")
     return sm.value, ma.value, mi.value
+
+
+class GemmTcPlan:
+    """RAII wrapper of a tcgen05 GEMM plan (TMA descriptors + launch geometry)."""
+
+    def __init__(self, **kw):
+        d = GemmTcDesc()
+        for k, v in kw.items():
+            if not hasattr(d, k):
+                raise AttributeError(k)
+            setattr(d, k, v)
+        self.desc = d
+        self.handle = C.c_void_p()
+        check(lib().dlrm_b200_gemm_tc_plan_create(C.byref(d), C.byref(self.handle)), "gemm_tc_plan_create")
+
+    def info(self):
+        a, b, c, e = C.c_int(), C.c_int(), C.c_int(), C.c_int()
+        check(lib().dlrm_b200_gemm_tc_plan_info(self.handle, C.byref(a), C.byref(b), C.byref(c), C.byref(e)))
+        return dict(tile_n=a.value, stages=b.value, splits=c.value, ctas=e.value)
+
+    def run(self, stream):
+        check(lib().dlrm_b200_gemm_tc_run(self.handle, stream), "gemm_tc_run")
+
+    def __del__(self):
+        try:
+            if self.handle:
+                lib().dlrm_b200_gemm_tc_plan_destroy(self.handle)
+                self.handle = None
+        except Exception:
+            pass

@@ -1,0 +1,494 @@
+// tcgen05 / TMEM / TMA GEMM for the MLP layers (forward, dgrad, wgrad) on sm_100a.
+//
+//   D[M,N] = sum_k A(m,k) * B(n,k)        bf16 operands, fp32 accumulation in tensor memory.
+//
+// Precision modes
+//   BF16   : one MMA per k-step (operands rounded to bf16).
+//   BF16X3 : fp32-grade result from bf16 tensor cores.  Every fp32 operand x is stored as the pair
+//            hi = bf16(x), lo = bf16(x - hi); the kernel issues hi*hi + hi*lo + lo*hi per k-step
+//            (the dropped lo*lo and residual terms are <= 2^-16 relative per product), which keeps
+//            the logits within 1e-5 of the reference's fp32 CPU forward (BASELINE.json north_star;
+//            measured in tests/test_gpu_gemm_tc.py).  4 operand tiles per stage instead of 2.
+//
+// Structure (one 128 x BN output tile per CTA, optional split-K over gridDim.z):
+//   warp 0     : TMA producer  -- cp.async.bulk.tensor.2d into a 128B-swizzled smem ring, mbarrier
+//                complete_tx signalling.
+//   warp 1     : allocates TMEM, one elected lane issues tcgen05.mma (cta_group::1, kind::f16,
+//                UMMA 128 x BN x 16), tcgen05.commit releases smem stages / publishes the accumulator.
+//   warps 2..5 : epilogue -- tcgen05.ld (32x32b.x32) of their TMEM lane quadrant, fused
+//                activation / activation-gradient mask, then fp32 and/or (hi,lo) bf16 stores in
+//                normal and transposed layout (the operand layouts of the next GEMMs).
+// Operands may be K-major ([rows, K] with K contiguous) or MN-major ([K, rows] with rows
+// contiguous, e.g. dY^T read straight from dY): the UMMA descriptors and instruction descriptor
+// carry the majorness, so no transposed copy is needed for MN-major inputs.
+#include <cuda.h>
+#include <cuda_bf16.h>
+
+#include "common.cuh"
+
+namespace dlrm {
+
+constexpr int TC_BM = 128;
+constexpr int TC_BK = 64;  // 64 bf16 = 128 bytes = one swizzle row
+
+struct TcArgs {
+  long long M, N, K;
+  int x3;
+  int a_mn, b_mn;  // operand majorness (0 = K-major, 1 = MN-major)
+  int kb_per_split, num_kb;
+  int act;
+  int mask_act;
+  const __nv_bfloat16* mask_hi;
+  const __nv_bfloat16* mask_lo;
+  long long ldmask;
+  float* out_f32;
+  long long ld_f32, slab_stride;
+  __nv_bfloat16* out_hi;
+  __nv_bfloat16* out_lo;
+  long long ld_out;
+  __nv_bfloat16* outT_hi;
+  __nv_bfloat16* outT_lo;
+  long long ld_outT;
+  float* out_col;
+  long long col_index, col_slab_stride;
+};
+
+// ------------------------------------------------------------------------------------------ PTX
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t.reg .pred P1;\n\t"
+      "WAIT_LOOP:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
+      "@P1 bra DONE;\n\t"
+      "bra WAIT_LOOP;\n\t"
+      "DONE:\n\t}" ::"r"(bar),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int x, int y) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
+      "l"(map), "r"(bar), "r"(x), "r"(y)
+      : "memory");
+}
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                          uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// UMMA shared-memory descriptor (cute::UMMA::SmemDescriptor): start>>4 [0,14), LBO>>4 [16,30),
+// SBO>>4 [32,46), version=1 [46,48), layout SWIZZLE_128B=2 [61,64).
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((addr >> 4) & 0x3FFF);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+
+__device__ __forceinline__ float apply_act_tc(float v, int act) {
+  if (act == DLRM_ACT_RELU) return fmaxf(v, 0.f);
+  if (act == DLRM_ACT_SIGMOID) return 1.0f / (1.0f + expf(-v));
+  return v;
+}
+
+// ------------------------------------------------------------------------------------------ kernel
+// smem per stage: A_hi [A_lo] B_hi [B_lo]; every tile 1024-byte aligned.
+template <int BN>
+__global__ void __launch_bounds__(192, 1)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__ CUtensorMap tmAl,
+               const __grid_constant__ CUtensorMap tmBh, const __grid_constant__ CUtensorMap tmBl,
+               const TcArgs g, int stages) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  constexpr uint32_t A_BYTES = TC_BM * TC_BK * 2;  // 16 KB
+  constexpr uint32_t B_BYTES = BN * TC_BK * 2;
+  const uint32_t stage_bytes = (g.x3 ? 2u : 1u) * (A_BYTES + B_BYTES);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)stages * stage_bytes);
+  // bars[0..stages) full, [stages..2*stages) empty, [2*stages] accumulator ready
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * stages + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int m0 = blockIdx.y * TC_BM, n0 = blockIdx.x * BN;
+  const int kb0 = blockIdx.z * g.kb_per_split;
+  const int kb1 = min(g.num_kb, kb0 + g.kb_per_split);
+  const uint32_t smem_base = smem_u32(smem);
+  const uint32_t bar_base = smem_u32(bars);
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < stages; ++s) {
+      mbar_init(bar_base + 8 * s, 1);
+      mbar_init(bar_base + 8 * (stages + s), 1);
+    }
+    mbar_init(bar_base + 8 * (2 * stages), 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    // allocate BN fp32 accumulator columns (power of two >= 32)
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                 "r"((uint32_t)(BN < 32 ? 32 : BN))
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int kb = kb0; kb < kb1; ++kb) {
+        mbar_wait(bar_base + 8 * (stages + stage), phase ^ 1);
+        const uint32_t full = bar_base + 8 * stage;
+        mbar_expect_tx(full, stage_bytes);
+        uint32_t dst = smem_base + stage * stage_bytes;
+        const int k0 = kb * TC_BK;
+        // A tile(s)
+        for (int part = 0; part < (g.x3 ? 2 : 1); ++part) {
+          const CUtensorMap* map = part ? &tmAl : &tmAh;
+          if (!g.a_mn) {
+            tma_load_2d(dst, map, full, k0, m0);                       // box {64 k, 128 m}
+          } else {
+            tma_load_2d(dst, map, full, m0, k0);                       // box {64 m, 64 k} x 2
+            tma_load_2d(dst + A_BYTES / 2, map, full, m0 + 64, k0);
+          }
+          dst += A_BYTES;
+        }
+        for (int part = 0; part < (g.x3 ? 2 : 1); ++part) {
+          const CUtensorMap* map = part ? &tmBl : &tmBh;
+          if (!g.b_mn) {
+            tma_load_2d(dst, map, full, k0, n0);                       // box {64 k, BN n}
+          } else {
+#pragma unroll
+            for (int h = 0; h < BN / 64; ++h) tma_load_2d(dst + h * 8192, map, full, n0 + 64 * h, k0);
+          }
+          dst += B_BYTES;
+        }
+        if (++stage == stages) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer
+    // instruction descriptor: D=f32 (1<<4), A=B=bf16 (1<<7, 1<<10), majorness bits 15/16,
+    // N>>3 at [17,23), M>>4 at [24,29)
+    const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)g.a_mn << 15) |
+                           ((uint32_t)g.b_mn << 16) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+    int stage = 0;
+    uint32_t phase = 0;
+    uint32_t accum = 0;
+    for (int kb = kb0; kb < kb1; ++kb) {
+      mbar_wait(bar_base + 8 * stage, phase);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      if (lane == 0) {
+        const uint32_t sa_hi = smem_base + stage * stage_bytes;
+        const uint32_t sa_lo = sa_hi + A_BYTES;
+        const uint32_t sb_hi = sa_hi + (g.x3 ? 2u : 1u) * A_BYTES;
+        const uint32_t sb_lo = sb_hi + B_BYTES;
+#pragma unroll
+        for (int k = 0; k < TC_BK / 16; ++k) {
+          // K-major SW128: rows of 128 B, 8-row groups 1024 B apart (SBO), k-step = +32 B.
+          // MN-major SW128: [64 k rows][64 mn] boxes: k-groups 1024 B apart (SBO), 64-wide mn blocks
+          //                 8192 B apart (LBO), k-step (16 rows) = +2048 B.
+          const uint32_t a_off = g.a_mn ? k * 2048u : k * 32u;
+          const uint32_t b_off = g.b_mn ? k * 2048u : k * 32u;
+          const uint32_t a_lbo = g.a_mn ? 8192u : 16u, b_lbo = g.b_mn ? 8192u : 16u;
+          const uint64_t ah = make_smem_desc(sa_hi + a_off, a_lbo, 1024);
+          const uint64_t bh = make_smem_desc(sb_hi + b_off, b_lbo, 1024);
+          if (g.x3) {
+            const uint64_t al = make_smem_desc(sa_lo + a_off, a_lbo, 1024);
+            const uint64_t bl = make_smem_desc(sb_lo + b_off, b_lbo, 1024);
+            umma_bf16(tmem_base, al, bh, idesc, accum);
+            umma_bf16(tmem_base, ah, bl, idesc, 1u);
+            umma_bf16(tmem_base, ah, bh, idesc, 1u);
+          } else {
+            umma_bf16(tmem_base, ah, bh, idesc, accum);
+          }
+          accum = 1u;
+        }
+        umma_commit(bar_base + 8 * (stages + stage));              // smem stage free when MMAs retire
+        if (kb == kb1 - 1) umma_commit(bar_base + 8 * (2 * stages));  // accumulator complete
+      }
+      __syncwarp();
+      if (++stage == stages) { stage = 0; phase ^= 1; }
+    }
+  } else {
+    // ------------------------------------------------------------------ epilogue (warps 2..5)
+    const int quad = warp & 3;  // TMEM lane quadrant this warp may access
+    mbar_wait(bar_base + 8 * (2 * stages), 0);
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const long long m = (long long)m0 + quad * 32 + lane;
+    const bool m_ok = m < g.M;
+    float* of32 = g.out_f32 ? g.out_f32 + (long long)blockIdx.z * g.slab_stride : nullptr;
+    float* ocol = g.out_col ? g.out_col + (long long)blockIdx.z * g.col_slab_stride : nullptr;
+#pragma unroll 1
+    for (int c = 0; c < BN / 32; ++c) {
+      uint32_t r[32];
+      tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(c * 32), r);
+      const long long nb = (long long)n0 + c * 32;
+      if (nb >= g.N) break;
+      float v[32];
+#pragma unroll
+      for (int j = 0; j < 32; ++j) v[j] = apply_act_tc(__uint_as_float(r[j]), g.act);
+      const bool full = nb + 32 <= g.N;
+      if (g.mask_act != DLRM_ACT_NONE && m_ok) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          if (full || nb + j < g.N) {
+            const long long o = m * g.ldmask + nb + j;
+            float y = __bfloat162float(g.mask_hi[o]);
+            if (g.mask_act == DLRM_ACT_RELU) {
+              v[j] = y > 0.f ? v[j] : 0.f;
+            } else {
+              if (g.mask_lo) y += __bfloat162float(g.mask_lo[o]);
+              v[j] *= (1.0f - y) * y;
+            }
+          }
+        }
+      }
+      if (of32 && m_ok) {
+        float* p = of32 + m * g.ld_f32 + nb;
+        const bool colsplit = ocol != nullptr && g.col_index >= nb && g.col_index < nb + 32;
+        if (full && !colsplit && (g.ld_f32 & 3) == 0) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(p + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            if (nb + j < g.N) {
+              if (ocol && nb + j == g.col_index) ocol[m] = v[j];
+              else if (!ocol || nb + j < g.col_index) p[j] = v[j];
+            }
+          }
+        }
+      }
+      if (g.out_hi || g.outT_hi) {
+        __nv_bfloat16 hi[32], lo[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          hi[j] = __float2bfloat16_rn(v[j]);
+          lo[j] = __float2bfloat16_rn(v[j] - __bfloat162float(hi[j]));
+        }
+        if (g.out_hi && m_ok) {
+          __nv_bfloat16* ph = g.out_hi + m * g.ld_out + nb;
+          __nv_bfloat16* pl = g.out_lo ? g.out_lo + m * g.ld_out + nb : nullptr;
+          if (full) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 8) {
+              *reinterpret_cast<uint4*>(ph + j) = *reinterpret_cast<const uint4*>(&hi[j]);
+              if (pl) *reinterpret_cast<uint4*>(pl + j) = *reinterpret_cast<const uint4*>(&lo[j]);
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (nb + j < g.N) { ph[j] = hi[j]; if (pl) pl[j] = lo[j]; }
+          }
+        }
+        if (g.outT_hi && m_ok) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            if (full || nb + j < g.N) {
+              const long long o = (nb + j) * g.ld_outT + m;
+              g.outT_hi[o] = hi[j];
+              if (g.outT_lo) g.outT_lo[o] = lo[j];
+            }
+          }
+        }
+      }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  }
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base),
+                 "r"((uint32_t)(BN < 32 ? 32 : BN))
+                 : "memory");
+  }
+}
+
+// ------------------------------------------------------------------------------------------ host
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+// 2-D bf16 tensor [outer, inner] with `ld` elements between outer rows; box {box_inner, box_outer}
+static int make_map(CUtensorMap* map, const void* ptr, long long inner, long long outer, long long ld,
+                    int box_inner, int box_outer) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) return set_error("gemm_tc: cuTensorMapEncodeTiled not available");
+  if ((reinterpret_cast<uintptr_t>(ptr) & 15) || (ld * 2) % 16)
+    return set_error("gemm_tc: operand pointer/ld not 16-byte aligned (ld=%lld)", ld);
+  cuuint64_t dims[2] = {(cuuint64_t)inner, (cuuint64_t)outer};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
+  cuuint32_t box[2] = {(cuuint32_t)box_inner, (cuuint32_t)box_outer};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return set_error("gemm_tc: cuTensorMapEncodeTiled failed (%d)", (int)r);
+  return 0;
+}
+
+struct TcPlan {
+  CUtensorMap tmAh, tmAl, tmBh, tmBl;
+  TcArgs args;
+  int bn, stages, splits;
+  size_t smem;
+  dim3 grid;
+};
+
+template <int BN>
+static int launch_tc(const TcPlan& p, cudaStream_t st) {
+  static bool configured = false;
+  if (!configured) {
+    DLRM_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    configured = true;
+  }
+  gemm_tc_kernel<BN><<<p.grid, 192, p.smem, st>>>(p.tmAh, p.tmAl, p.tmBh, p.tmBl, p.args, p.stages);
+  DLRM_CHECK_LAUNCH("gemm_tc_kernel");
+  return 0;
+}
+
+}  // namespace dlrm
+
+extern "C" int dlrm_b200_gemm_tc_plan_create(const dlrm_gemm_tc_desc_t* d, void** plan_out) {
+  using namespace dlrm;
+  if (!d || !plan_out) return set_error("gemm_tc_plan_create: NULL argument");
+  if (d->M <= 0 || d->N <= 0 || d->K <= 0) return set_error("gemm_tc: empty problem M=%lld N=%lld K=%lld", (long long)d->M, (long long)d->N, (long long)d->K);
+  if (!d->A_hi || !d->B_hi || (d->mode_x3 && (!d->A_lo || !d->B_lo)))
+    return set_error("gemm_tc: NULL operand");
+  TcPlan* p = new TcPlan();
+  TcArgs& a = p->args;
+  a.M = d->M; a.N = d->N; a.K = d->K;
+  a.x3 = d->mode_x3 ? 1 : 0;
+  a.a_mn = d->a_mn_major ? 1 : 0;
+  a.b_mn = d->b_mn_major ? 1 : 0;
+  a.act = d->act; a.mask_act = d->mask_act;
+  a.mask_hi = static_cast<const __nv_bfloat16*>(d->mask_hi);
+  a.mask_lo = static_cast<const __nv_bfloat16*>(d->mask_lo);
+  a.ldmask = d->ldmask;
+  a.out_f32 = d->out_f32; a.ld_f32 = d->ld_f32; a.slab_stride = d->slab_stride;
+  a.out_hi = static_cast<__nv_bfloat16*>(d->out_hi); a.out_lo = static_cast<__nv_bfloat16*>(d->out_lo);
+  a.ld_out = d->ld_out;
+  a.outT_hi = static_cast<__nv_bfloat16*>(d->outT_hi); a.outT_lo = static_cast<__nv_bfloat16*>(d->outT_lo);
+  a.ld_outT = d->ld_outT;
+  a.out_col = d->out_col; a.col_index = d->col_index; a.col_slab_stride = d->col_slab_stride;
+  if (a.mask_act != DLRM_ACT_NONE && !a.mask_hi) { delete p; return set_error("gemm_tc: mask_act without mask_hi"); }
+  if (a.out_hi && (a.ld_out % 8)) { delete p; return set_error("gemm_tc: ld_out must be a multiple of 8"); }
+  // tile width: keep >= ~64 CTAs when N is small
+  const long long mt = (d->M + TC_BM - 1) / TC_BM;
+  int bn = 128;
+  if (d->tile_n == 32 || d->tile_n == 64 || d->tile_n == 128) bn = d->tile_n;
+  else {
+    while (bn > 32 && mt * ((d->N + bn - 1) / bn) < 96) bn >>= 1;
+    if (d->N <= 32) bn = 32; else if (d->N <= 64 && bn > 64) bn = 64;
+  }
+  if (a.b_mn && bn < 64) bn = 64;  // MN-major boxes are 64 wide
+  p->bn = bn;
+  a.num_kb = (int)((d->K + TC_BK - 1) / TC_BK);
+  int splits = d->split_k > 1 ? d->split_k : 1;
+  if (splits > a.num_kb) splits = a.num_kb;
+  a.kb_per_split = (a.num_kb + splits - 1) / splits;
+  splits = (a.num_kb + a.kb_per_split - 1) / a.kb_per_split;  // no empty split
+  p->splits = splits;
+  if (splits > 1 && (a.out_hi || a.outT_hi || a.act != DLRM_ACT_NONE || a.mask_act != DLRM_ACT_NONE)) {
+    delete p; return set_error("gemm_tc: split-K only supports fp32 slab outputs");
+  }
+  const size_t stage_bytes = (size_t)(a.x3 ? 2 : 1) * (TC_BM * TC_BK * 2 + bn * TC_BK * 2);
+  int stages = (int)((200 * 1024) / stage_bytes);
+  if (stages > 8) stages = 8;
+  if (stages > a.kb_per_split) stages = a.kb_per_split < 2 ? 2 : a.kb_per_split;
+  p->stages = stages;
+  p->smem = stages * stage_bytes + (2 * stages + 1) * 8 + 16 + 1024;
+  p->grid = dim3((unsigned)((d->N + bn - 1) / bn), (unsigned)mt, (unsigned)splits);
+  int rc = 0;
+  // operand maps.  K-major: tensor [rows, K]; MN-major: tensor [K, rows].
+  if (!a.a_mn) {
+    rc |= make_map(&p->tmAh, d->A_hi, d->K, d->M, d->lda, TC_BK, TC_BM);
+    rc |= make_map(&p->tmAl, a.x3 ? d->A_lo : d->A_hi, d->K, d->M, d->lda, TC_BK, TC_BM);
+  } else {
+    rc |= make_map(&p->tmAh, d->A_hi, d->M, d->K, d->lda, 64, TC_BK);
+    rc |= make_map(&p->tmAl, a.x3 ? d->A_lo : d->A_hi, d->M, d->K, d->lda, 64, TC_BK);
+  }
+  if (!a.b_mn) {
+    rc |= make_map(&p->tmBh, d->B_hi, d->K, d->N, d->ldb, TC_BK, bn);
+    rc |= make_map(&p->tmBl, a.x3 ? d->B_lo : d->B_hi, d->K, d->N, d->ldb, TC_BK, bn);
+  } else {
+    rc |= make_map(&p->tmBh, d->B_hi, d->N, d->K, d->ldb, 64, TC_BK);
+    rc |= make_map(&p->tmBl, a.x3 ? d->B_lo : d->B_hi, d->N, d->K, d->ldb, 64, TC_BK);
+  }
+  if (rc) { delete p; return -1; }
+  *plan_out = p;
+  return 0;
+}
+
+extern "C" int dlrm_b200_gemm_tc_plan_info(void* plan, int* tile_n, int* stages, int* splits, int* ctas) {
+  using namespace dlrm;
+  if (!plan) return set_error("gemm_tc_plan_info: NULL plan");
+  TcPlan* p = static_cast<TcPlan*>(plan);
+  if (tile_n) *tile_n = p->bn;
+  if (stages) *stages = p->stages;
+  if (splits) *splits = p->splits;
+  if (ctas) *ctas = (int)(p->grid.x * p->grid.y * p->grid.z);
+  return 0;
+}
+
+extern "C" int dlrm_b200_gemm_tc_run(void* plan, void* stream) {
+  using namespace dlrm;
+  if (!plan) return set_error("gemm_tc_run: NULL plan");
+  TcPlan* p = static_cast<TcPlan*>(plan);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (p->bn == 128) return launch_tc<128>(*p, st);
+  if (p->bn == 64) return launch_tc<64>(*p, st);
+  return launch_tc<32>(*p, st);
+}
+
+extern "C" int dlrm_b200_gemm_tc_plan_destroy(void* plan) {
+  delete static_cast<dlrm::TcPlan*>(plan);
+  return 0;
+}

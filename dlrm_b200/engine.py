@@ -88,7 +88,14 @@ class Engine:
         self.sigmoid_bot, self.sigmoid_top = int(sigmoid_bot), int(sigmoid_top)
         self.loss_kind = _LOSS[loss]
         self.loss_threshold = float(loss_threshold)
-        self.gemm = GEMM_SIMT_FP32 if gemm == "simt" else gemm
+        if gemm not in ("simt", "tc", "tc_bf16"):
+            raise ValueError("gemm must be simt | tc (bf16x3 split, fp32-grade) | tc_bf16")
+        self.gemm_mode = gemm
+        self.gemm = GEMM_SIMT_FP32          # back end of the fp32-pointer entry points
+        self.tc = gemm != "simt"
+        self.tc_x3 = 1 if gemm == "tc" else 0
+        self.tc_B = -1                       # batch size the tcgen05 plans were built for
+        self._pack_dirty = True
         if self.ln_bot[-1] != self.D:
             raise ValueError("bottom MLP output %d != sparse feature size %d" % (self.ln_bot[-1], self.D))
         if op == "dot":
@@ -176,7 +183,12 @@ class Engine:
                 self.dense_state = torch.zeros_like(self.dense)
 
     # ------------------------------------------------------------------ parameters
+    def mark_params_changed(self):
+        """Call after writing master weights from outside (the bf16 operand copies are stale)."""
+        self._pack_dirty = True
+
     def load_params(self, params: dict):
+        self._pack_dirty = True
         """params = dict(emb=[W_k], bot=[(W,b)...], top=[(W,b)...], v_W_l=None|[...]) of numpy /
         torch arrays (the layout of the oracle and of the reference's state_dict)."""
         with torch.no_grad():
@@ -195,6 +207,7 @@ class Engine:
     def init_params(self, seed: int = 0):
         """Same distributions as create_emb / create_mlp (dlrm_s_pytorch.py:221-228, :280-284),
         drawn on the device (26 x 1e6 x 128 takes 150 s with the reference's numpy init)."""
+        self._pack_dirty = True
         g = torch.Generator(device=self.device)
         g.manual_seed(seed)
         with torch.no_grad():
@@ -285,6 +298,8 @@ class Engine:
         B = sp.batch
         if B > self.max_batch:
             self._alloc_activations(B)
+        if self.tc:
+            return self._tc_forward(X, sp)
         FD = self.F * self.D
         outs, lds = self._bot_outs(B)
         self.mlp_forward("bot", X, X.stride(0), B, outs, lds)
@@ -388,6 +403,8 @@ class Engine:
         dense_grad and the per-bag embedding grads in dT[:, 1:, :]."""
         B = sp.batch
         FD = self.F * self.D
+        if self.tc:
+            return self._tc_backward(X, sp, target)
         self.loss_and_grad(target, B)
         top_ld = [t.shape[1] for t in self.top_act]
         xin, ldx = self._top_in()
@@ -441,8 +458,250 @@ class Engine:
         clr = lr / (1.0 + (self.opt_step - 1.0) * lr_decay) if optimizer == "rwsadagrad" else lr
         if self.T:
             self.emb_update(sp, self.dT.view(-1)[self.D:], self.F * self.D, self.D, optimizer, clr)
-        self.dense_step(optimizer, clr)
+        if self.tc:
+            self._dense_update_pack(_OPT[optimizer], clr)
+        else:
+            self.dense_step(optimizer, clr)
         return self.loss_buf
+
+
+
+    # ================================================================== tcgen05 path
+    # Layers whose output width is >= 16 run on tensor cores (all bottom layers, the top layers
+    # up to the final 256 -> 1 layer, which stays on the fp32 CUDA-core kernels).  Every fp32
+    # activation / gradient / weight is kept as a (hi, lo) bf16 pair, activations carry a
+    # constant-1 column and weights a bias column, so the bias add and the bias gradient come
+    # out of the GEMMs themselves.
+    def _tc_n(self, which: str) -> int:
+        ln = self.ln_bot if which == "bot" else self.ln_top
+        n = 0
+        for i in range(len(ln) - 1):
+            if ln[i + 1] >= 16:
+                n += 1
+            else:
+                break
+        if which == "bot" and n != len(ln) - 1:
+            return 0
+        return n
+
+    def _tc_setup(self, B: int):
+        dev, bf = self.device, torch.bfloat16
+        r8 = lambda v: (v + 7) // 8 * 8
+        self.tc_B = B
+        self.ntc = {"bot": self._tc_n("bot"), "top": self._tc_n("top")}
+        self.tc_in, self.tc_gz, self.tc_W = {}, {}, {}
+        self.tc_plans = {"fwd": {}, "dgrad": {}, "wgrad": {}}
+        x3 = self.tc_x3
+        P = self.dense_numel
+        # split-K factors for the wgrads -> number of gradient slabs
+        self.tc_splits = {}
+        smax = 1
+        for which in ("bot", "top"):
+            ln = self.ln_bot if which == "bot" else self.ln_top
+            for i in range(self.ntc[which]):
+                tiles = ((ln[i + 1] + 127) // 128) * ((ln[i] + 1 + 127) // 128)
+                sk = max(1, min(8, (120 + tiles - 1) // tiles, (B + 63) // 64))
+                self.tc_splits[(which, i)] = sk
+                smax = max(smax, sk)
+        if self.dense_grad.numel() < smax * P:
+            self.dense_grad = torch.zeros(smax * P, dtype=torch.float32, device=dev)
+            self.dW, self.db = {"bot": [], "top": []}, {"bot": [], "top": []}
+            for name, i, kind, o, shape in self.dense_slices:
+                n = int(np.prod(shape))
+                (self.dW if kind == "W" else self.db)[name].append(self.dense_grad[o:o + n].view(shape))
+        self._dense_off = {}
+        for name, i, kind, o, shape in self.dense_slices:
+            self._dense_off[(name, i, kind)] = o
+        for which in ("bot", "top"):
+            ln = self.ln_bot if which == "bot" else self.ln_top
+            ntc = self.ntc[which]
+            ins, gzs, Ws = [], [], []
+            for i in range(ntc):
+                K, N = ln[i], ln[i + 1]
+                Kp, Np = r8(K + 1), r8(N)
+                h = torch.zeros((B, Kp), dtype=bf, device=dev)
+                l = torch.zeros((B, Kp), dtype=bf, device=dev)
+                h[:, K] = 1.0  # constant-1 column: bias folded into the GEMM
+                ins.append((h, l, Kp))
+                gzs.append((torch.zeros((B, Np), dtype=bf, device=dev), torch.zeros((B, Np), dtype=bf, device=dev), Np))
+                Ws.append((torch.zeros((N, Kp), dtype=bf, device=dev), torch.zeros((N, Kp), dtype=bf, device=dev), Kp))
+            self.tc_in[which], self.tc_gz[which], self.tc_W[which] = ins, gzs, Ws
+        FD = self.F * self.D
+        GP = _lib.GemmTcPlan
+        for which in ("bot", "top"):
+            ln = self.ln_bot if which == "bot" else self.ln_top
+            ntc = self.ntc[which]
+            nl = len(ln) - 1
+            for i in range(ntc):
+                K, N = ln[i], ln[i + 1]
+                ih, il, Kp = self.tc_in[which][i]
+                wh, wl, _ = self.tc_W[which][i]
+                gh, gl, Np = self.tc_gz[which][i]
+                # ---- forward: Y = act([X | 1] [W | b]^T)
+                kw = dict(A_hi=ih.data_ptr(), A_lo=il.data_ptr(), lda=Kp, a_mn_major=0,
+                          B_hi=wh.data_ptr(), B_lo=wl.data_ptr(), ldb=Kp, b_mn_major=0,
+                          M=B, N=N, K=K + 1, mode_x3=x3, split_k=1, act=self._act(which, i))
+                if i + 1 < ntc:
+                    oh, ol, Kp2 = self.tc_in[which][i + 1]
+                    kw.update(out_hi=oh.data_ptr(), out_lo=ol.data_ptr(), ld_out=Kp2)
+                if which == "bot" and i == nl - 1:
+                    kw.update(out_f32=self.Tbuf.data_ptr(), ld_f32=FD)
+                elif which == "top" and (i == ntc - 1):
+                    kw.update(out_f32=self.top_act[i].data_ptr(), ld_f32=self.top_act[i].shape[1])
+                self.tc_plans["fwd"][(which, i)] = GP(**kw)
+                # ---- wgrad: [dW | db] = gz^T [X | 1]   (both operands read MN-major, split-K slabs)
+                oW = self._dense_off[(which, i, "W")]
+                ob = self._dense_off[(which, i, "b")]
+                self.tc_plans["wgrad"][(which, i)] = GP(
+                    A_hi=gh.data_ptr(), A_lo=gl.data_ptr(), lda=Np, a_mn_major=1,
+                    B_hi=ih.data_ptr(), B_lo=il.data_ptr(), ldb=Kp, b_mn_major=1,
+                    M=N, N=K + 1, K=B, mode_x3=x3, split_k=self.tc_splits[(which, i)],
+                    out_f32=self.dense_grad.data_ptr() + oW * 4, ld_f32=K, slab_stride=P,
+                    out_col=self.dense_grad.data_ptr() + ob * 4, col_index=K, col_slab_stride=P)
+                # ---- dgrad: gz_prev = (gz W) * act'(input activation)
+                if i > 0:
+                    ph, pl, Np_prev = self.tc_gz[which][i - 1]
+                    self.tc_plans["dgrad"][(which, i)] = GP(
+                        A_hi=gh.data_ptr(), A_lo=gl.data_ptr(), lda=Np, a_mn_major=0,
+                        B_hi=wh.data_ptr(), B_lo=wl.data_ptr(), ldb=Kp, b_mn_major=1,
+                        M=B, N=K, K=N, mode_x3=x3, split_k=1,
+                        mask_act=self._act(which, i - 1), mask_hi=ih.data_ptr(), mask_lo=il.data_ptr(), ldmask=Kp,
+                        out_hi=ph.data_ptr(), out_lo=pl.data_ptr(), ld_out=Np_prev)
+                elif which == "top" and self.op == "dot":
+                    self.tc_plans["dgrad"][(which, 0)] = GP(
+                        A_hi=gh.data_ptr(), A_lo=gl.data_ptr(), lda=Np, a_mn_major=0,
+                        B_hi=wh.data_ptr(), B_lo=wl.data_ptr(), ldb=Kp, b_mn_major=1,
+                        M=B, N=K, K=N, mode_x3=x3, split_k=1,
+                        out_f32=self.dR.data_ptr(), ld_f32=self.ldr)
+        self._pack_dirty = True
+
+    def _split(self, x: torch.Tensor, ldx: int, M: int, N: int, hl):
+        h, l, ld = hl
+        _lib.check(self.lib.dlrm_b200_split_bf16(x.data_ptr(), ldx, M, N, h.data_ptr(), l.data_ptr(), ld,
+                                                 _stream()), "split_bf16")
+        self.n_launch += 1
+
+    def _dense_update_pack(self, opt_code: int, lr: float, eps: float = 1e-10):
+        """optimizer step on every dense layer + bf16 operand refresh; opt_code -1 = refresh only."""
+        layers = []
+        P = self.dense_numel
+        for which in ("bot", "top"):
+            ln = self.ln_bot if which == "bot" else self.ln_top
+            for i in range(len(ln) - 1):
+                d = _lib.DenseLayer()
+                oW, ob = self._dense_off[(which, i, "W")], self._dense_off[(which, i, "b")]
+                d.W = self.dense.data_ptr() + oW * 4
+                d.b = self.dense.data_ptr() + ob * 4
+                if self.dense_state is not None:
+                    d.sW = self.dense_state.data_ptr() + oW * 4
+                    d.sb = self.dense_state.data_ptr() + ob * 4
+                d.dW = self.dense_grad.data_ptr() + oW * 4
+                d.db = self.dense_grad.data_ptr() + ob * 4
+                d.slab_stride = P
+                d.N, d.K = ln[i + 1], ln[i]
+                if i < self.ntc[which]:
+                    wh, wl, Kp = self.tc_W[which][i]
+                    d.pack_hi, d.pack_lo, d.ld_pack = wh.data_ptr(), wl.data_ptr(), Kp
+                    d.num_slabs = self.tc_splits[(which, i)] if opt_code >= 0 else 1
+                else:
+                    d.num_slabs = 1
+                layers.append(d)
+        for c0 in range(0, len(layers), 16):
+            chunk = layers[c0:c0 + 16]
+            arr = (_lib.DenseLayer * len(chunk))(*chunk)
+            _lib.check(self.lib.dlrm_b200_dense_update_pack(arr, len(chunk), opt_code, lr, eps, _stream()),
+                       "dense_update_pack")
+            self.n_launch += 1
+
+    def _tc_prepare(self, B: int):
+        if self.tc_B != B:
+            self._tc_setup(B)
+        if self._pack_dirty:
+            self._dense_update_pack(-1, 0.0)
+            self._pack_dirty = False
+
+    def _tc_mlp_forward(self, which: str, B: int):
+        ln = self.ln_bot if which == "bot" else self.ln_top
+        s = _stream()
+        ntc = self.ntc[which]
+        for i in range(ntc):
+            self.tc_plans["fwd"][(which, i)].run(s)
+            self.n_launch += 1
+        # fp32 CUDA-core suffix (e.g. the final 256 -> 1 layer)
+        for i in range(ntc, len(ln) - 1):
+            K, N = ln[i], ln[i + 1]
+            x = self.top_act[i - 1]
+            _lib.check(self.lib.dlrm_b200_linear_fwd(x.data_ptr(), x.shape[1], self.W[which][i].data_ptr(), K,
+                                                     self.b[which][i].data_ptr(), self.top_act[i].data_ptr(),
+                                                     self.top_act[i].shape[1], B, N, K, self._act(which, i),
+                                                     GEMM_SIMT_FP32, s), "linear_fwd")
+            self.n_launch += 1
+
+    def _tc_forward(self, X: torch.Tensor, sp: SparseInput) -> torch.Tensor:
+        B = sp.batch
+        self._tc_prepare(B)
+        if self.ntc["bot"] == 0 or self.ntc["top"] == 0 or self.op != "dot":
+            raise RuntimeError("gemm='tc' needs op='dot' and MLP layers of width >= 16; use gemm='simt'")
+        FD = self.F * self.D
+        self._split(X, X.stride(0), B, self.ln_bot[0], self.tc_in["bot"][0])
+        self._tc_mlp_forward("bot", B)
+        if self.T:
+            ev = self._gather_events
+            if ev is not None:
+                ev[0].record()
+            self.emb_forward(sp, self.Tbuf.view(-1)[self.D:], FD, self.D)
+            if ev is not None:
+                ev[1].record()
+        _lib.check(self.lib.dlrm_b200_interact_fwd(self.Tbuf.data_ptr(), FD, self.Rbuf.data_ptr(), self.ldr, B,
+                                                   self.F, self.D, int(self.itself), _stream()), "interact_fwd")
+        self.n_launch += 1
+        self._split(self.Rbuf, self.ldr, B, self.num_int, self.tc_in["top"][0])
+        self._tc_mlp_forward("top", B)
+        p = self.top_act[-1][:B]
+        if 0.0 < self.loss_threshold < 1.0:
+            return torch.clamp(p, self.loss_threshold, 1.0 - self.loss_threshold)
+        return p
+
+    def _tc_mlp_backward(self, which: str, B: int):
+        s = _stream()
+        for i in reversed(range(self.ntc[which])):
+            self.tc_plans["wgrad"][(which, i)].run(s)
+            self.n_launch += 1
+            pl = self.tc_plans["dgrad"].get((which, i))
+            if pl is not None:
+                pl.run(s)
+                self.n_launch += 1
+
+    def _tc_backward(self, X: torch.Tensor, sp: SparseInput, target: torch.Tensor):
+        B = sp.batch
+        FD = self.F * self.D
+        s = _stream()
+        self.loss_and_grad(target, B)
+        nt, ntc = len(self.ln_top) - 1, self.ntc["top"]
+        top_ld = [t.shape[1] for t in self.top_act]
+        # fp32 suffix of the top MLP
+        for i in reversed(range(ntc, nt)):
+            K, N = self.ln_top[i], self.ln_top[i + 1]
+            xin = self.top_act[i - 1]
+            _lib.check(self.lib.dlrm_b200_linear_wgrad(self.top_gz[i].data_ptr(), top_ld[i], xin.data_ptr(),
+                                                       xin.shape[1], self.dW["top"][i].data_ptr(), K,
+                                                       self.db["top"][i].data_ptr(), B, N, K, GEMM_SIMT_FP32, s),
+                       "linear_wgrad")
+            _lib.check(self.lib.dlrm_b200_linear_dgrad(self.top_gz[i].data_ptr(), top_ld[i],
+                                                       self.W["top"][i].data_ptr(), K, xin.data_ptr(),
+                                                       xin.shape[1], self._act("top", i - 1),
+                                                       self.top_gz[i - 1].data_ptr(), top_ld[i - 1], B, N, K,
+                                                       GEMM_SIMT_FP32, s), "linear_dgrad")
+            self.n_launch += 3
+        self._split(self.top_gz[ntc - 1], top_ld[ntc - 1], B, self.ln_top[ntc], self.tc_gz["top"][ntc - 1])
+        self._tc_mlp_backward("top", B)
+        bot_last_act = self._act("bot", len(self.ln_bot) - 2)
+        _lib.check(self.lib.dlrm_b200_interact_bwd(self.Tbuf.data_ptr(), FD, self.dR.data_ptr(), self.ldr,
+                                                   self.dT.data_ptr(), FD, B, self.F, self.D, int(self.itself),
+                                                   bot_last_act, s), "interact_bwd")
+        self.n_launch += 1
+        self._split(self.dT, FD, B, self.D, self.tc_gz["bot"][-1])
+        self._tc_mlp_backward("bot", B)
 
 
 def sparse_from_reference(lS_o, lS_i, device) -> SparseInput:

@@ -162,6 +162,55 @@ int dlrm_b200_loss_fwd_bwd(const float* p, const float* target, const float* los
 int dlrm_b200_dense_update(float* param, const float* grad, float* state /*NULL for SGD*/,
                            int64_t n, int optimizer, float lr, float eps, void* stream);
 
+
+/* ------------------------------------------------------------------------------------------
+ * tcgen05 GEMM back end of apply_mlp and its autograd (aten::addmm, dlrm_s_pytorch.py:399-405):
+ *   D[M,N] = sum_k A(m,k) * B(n,k),  bf16 operands staged by TMA, fp32 accumulation in TMEM.
+ * Operands are (hi, lo) bf16 pairs of fp32 values (hi = bf16(x), lo = bf16(x - hi)); mode_x3
+ * computes hi*hi + hi*lo + lo*hi (fp32-grade), otherwise hi*hi only.  An operand is K-major
+ * ([rows, K], ld = row stride) or MN-major ([K, rows]); ld in elements, multiple of 8.
+ * The bias is folded into the GEMM: activations carry a constant-1 column, weights a bias column.
+ * Epilogue (all optional): act(); multiply by act'(y), y = mask_hi + mask_lo [M, ldmask];
+ * fp32 store (split-K: one slab per split, reduced by dense_update_pack); one column diverted to
+ * out_col (bias gradient); (hi, lo) bf16 stores in normal [M, ld_out] and transposed [N, ld_outT]
+ * layout.  A plan holds the TMA descriptors: create once per buffer set, run every step.
+ * ------------------------------------------------------------------------------------------ */
+typedef struct {
+  const void* A_hi; const void* A_lo; int64_t lda; int a_mn_major;
+  const void* B_hi; const void* B_lo; int64_t ldb; int b_mn_major;
+  int64_t M, N, K;
+  int mode_x3;
+  int split_k;      /* >= 1 */
+  int tile_n;       /* 0 = auto, or 32 / 64 / 128 */
+  int act;          /* DLRM_ACT_* applied to the accumulator */
+  int mask_act;     /* DLRM_ACT_*: multiply by act'(y) */
+  const void* mask_hi; const void* mask_lo; int64_t ldmask;
+  float* out_f32; int64_t ld_f32; int64_t slab_stride;
+  void* out_hi; void* out_lo; int64_t ld_out;
+  void* outT_hi; void* outT_lo; int64_t ld_outT;
+  float* out_col; int64_t col_index; int64_t col_slab_stride;
+} dlrm_gemm_tc_desc_t;
+
+int dlrm_b200_gemm_tc_plan_create(const dlrm_gemm_tc_desc_t* desc /*[host]*/, void** plan);
+int dlrm_b200_gemm_tc_plan_info(void* plan, int* tile_n, int* stages, int* splits, int* ctas);
+int dlrm_b200_gemm_tc_run(void* plan, void* stream);
+int dlrm_b200_gemm_tc_plan_destroy(void* plan);
+
+/* fp32 [M,N] (row stride ldx) -> (hi, lo) bf16 [M, ld_out]; lo may be NULL */
+int dlrm_b200_split_bf16(const float* X, int64_t ldx, int64_t M, int64_t N, void* hi, void* lo,
+                         int64_t ld_out, void* stream);
+
+/* Dense optimizer step fused with the split-K slab reduction of dW/db and the refresh of the
+ * [N, K+1] = [W | bias] (hi, lo) operand copies.  optimizer = DLRM_OPT_* or -1 (pack only). */
+typedef struct {
+  float* W; float* b; float* sW; float* sb;
+  const float* dW; const float* db;
+  void* pack_hi; void* pack_lo;
+  int64_t slab_stride; int64_t N; int64_t K; int64_t ld_pack; int64_t num_slabs;
+} dlrm_dense_layer_t;
+int dlrm_b200_dense_update_pack(const dlrm_dense_layer_t* layers /*[host]*/, int num_layers, int optimizer,
+                                float lr, float eps, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
