@@ -181,7 +181,7 @@ def bytes_fwd_gather(nnz, T, B, D):
 
 def ours(args):
     from dlrm_b200.data import DeviceBatch, make_batch
-    from dlrm_b200.engine import Engine
+    from dlrm_b200.engine import Engine, GraphedTrainStep
 
     n = args.gpus
     if n > 1:
@@ -206,23 +206,31 @@ def ours(args):
         devb.append(db)
     torch.cuda.synchronize()
     lr = 0.01
-    gather_ev = []
+    # two static staging buffers, each with its own captured graph of the whole step
+    stage = [DeviceBatch(host[0].layout, dev) for _ in range(2)]
+    for st in stage:
+        st.load(host[0], non_blocking=False)
+    use_graph = not args.no_graph
+    steps_g = [GraphedTrainStep(eng, st, lr, "rwsadagrad", train=train) for st in stage] if use_graph else None
 
-    def step(db, timed=False):
+    def run_on(st_i):
+        if use_graph:
+            return steps_g[st_i].replay()
+        st = stage[st_i]
         if train:
-            if timed:
-                # events around the gather on the launching stream (roofline.achieved)
-                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                eng._gather_events = (e0, e1)
-                gather_ev.append((e0, e1, db.nnz))
-            eng.train_step(db.X, db.sparse, db.target, lr, "rwsadagrad")
-            eng._gather_events = None
-        else:
-            eng.forward(db.X, db.sparse)
+            return eng.train_step(st.X, st.sparse, st.target, lr, "rwsadagrad")
+        return eng.forward(st.X, st.sparse)
 
-    # ---- device-resident value
+    def step_resident(i):
+        # inputs already resident in HBM: device-to-device copy of the packed batch into the
+        # graph's static buffer (2.7 MB), then the step
+        src = devb[i % args.ring]
+        nbytes = src.layout.used(src.nnz)
+        stage[0].buf[:nbytes].copy_(src.buf[:nbytes], non_blocking=True)
+        run_on(0)
+
     for w in range(args.warmup):
-        step(devb[w % args.ring])
+        step_resident(w)
     torch.cuda.synchronize()
     sampler = ClockSampler(0)
     sampler.start()
@@ -233,38 +241,16 @@ def ours(args):
     launches0 = eng.n_launch
     ev0.record()
     for s in range(args.steps):
-        step(devb[(args.warmup + s) % args.ring], timed=True)
+        step_resident(args.warmup + s)
     ev1.record()
-    launches = eng.n_launch - launches0
     torch.cuda.synchronize()
     t1 = time.time()
+    launches = eng.n_launch - launches0
     clocks = sampler.stop(t0, t1)
     ms = ev0.elapsed_time(ev1) / args.steps
     value = B / (ms * 1e-3)
 
-    # ---- gather roofline (events recorded inside the timed region)
-    peaks = {}
-    try:
-        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as fh:
-            peaks = json.load(fh)
-    except Exception:
-        pass
-    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
-    peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s"
-    roof = None
-    if gather_ev:
-        tg = np.array([a.elapsed_time(b) for a, b, _ in gather_ev]) * 1e-3
-        by = np.array([bytes_fwd_gather(nz, T, B, D) for _, _, nz in gather_ev], dtype=np.float64)
-        ach = float(by.sum() / tg.sum() / 1e9)
-        roof = {"kernel": "emb_fwd_vec_kernel (multi-table EmbeddingBag gather)", "bound": "hbm",
-                "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak,
-                "traffic": None, "peak_source": peak_src, "avg_launch_us": float(tg.mean() * 1e6),
-                "algorithmic_bytes_per_launch": float(by.mean())}
-    else:
-        roof = measure_gather_alone(eng, devb, args, hbm_peak, peak_src, T, B, D)
-
-    # ---- e2e: host buffers, H2D of the packed batch + D2H of the loss inside the timed region
-    stage = [DeviceBatch(host[0].layout, dev) for _ in range(2)]
+    # ---- e2e: host buffers; H2D of the packed batch + D2H of the loss inside the timed region
     copy_stream = torch.cuda.Stream()
     loss_host = torch.zeros(1).pin_memory()
     main = torch.cuda.current_stream()
@@ -288,12 +274,8 @@ def ours(args):
                     h2d += stage[nxt].load(host[(base + s + 1) % args.ring])
                     ready[nxt].record(copy_stream)
             main.wait_event(ready[cur])
-            if train:
-                loss = eng.train_step(stage[cur].X, stage[cur].sparse, stage[cur].target, lr, "rwsadagrad")
-                loss_host.copy_(loss, non_blocking=True)
-            else:
-                p = eng.forward(stage[cur].X, stage[cur].sparse)
-                loss_host.copy_(p[:1, 0], non_blocking=True)
+            out = run_on(cur)
+            loss_host.copy_(out.view(-1)[:1], non_blocking=True)
             freed[cur].record(main)
         main.synchronize()
 
@@ -307,18 +289,61 @@ def ours(args):
     ms_e2e = ev0.elapsed_time(ev1) / args.steps
     e2e = {"value": B / (ms_e2e * 1e-3), "unit": "samples/s", "h2d_bytes_per_step": int(h2d / args.steps),
            "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e,
-           "note": "packed pinned batch -> one cudaMemcpyAsync on a copy stream (double-buffered), "
-                   "loss read back every step"}
+           "note": "packed pinned batch -> one cudaMemcpyAsync on a copy stream (double-buffered) -> "
+                   "one CUDA-graph launch per step; loss read back every step"}
+
+    # ---- rooflines of the HBM-bound kernels, timed with CUDA events on the launching stream
+    peaks = {}
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as fh:
+            peaks = json.load(fh)
+    except Exception:
+        pass
+    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s"
+    roof = measure_gather_alone(eng, devb, args, hbm_peak, peak_src, T, B, D)
+    roof_upd = measure_update_alone(eng, devb, args, hbm_peak, T, B, D) if train else None
 
     cb = cpu_baseline(train, budget_s=args.cpu_budget) if not args.no_cpu else None
     line = {
         "metric": metric_name(train), "value": value, "unit": "samples/s", "n_gpus": 1, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "fp32", "data": "synthetic", "config": config_dict(args, 1),
-        "roofline": roof, "cpu_baseline": cb, "e2e": e2e,
-        "gpu_launches": int(launches), "clocks": clocks,
+        "vs_baseline": None,
+        "dtype": {"simt": "fp32", "tc": "fp32 (bf16x3 split on tcgen05, fp32 accumulate)", "tc_bf16": "bf16"}[args.gemm],
+        "data": "synthetic", "config": config_dict(args, 1),
+        "roofline": roof, "roofline_update": roof_upd, "cpu_baseline": cb, "e2e": e2e,
+        "gpu_launches": int(launches), "cuda_graph": bool(use_graph), "clocks": clocks,
     }
     print(json.dumps(line))
+
+
+def measure_update_alone(eng, devb, args, hbm_peak, T, B, D):
+    """Training-mode gather (+link) and the fused coalesce + row-wise Adagrad update, timed alone."""
+    FD = eng.F * eng.D
+    out = eng.Tbuf.view(-1)[eng.D:]
+    eng.dT.normal_()
+    eng.head.zero_()
+    ev = []
+    for s in range(args.steps + 3):
+        db = devb[s % len(devb)]
+        e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+        e0.record()
+        eng.emb_forward(db.sparse, out, FD, eng.D, link=True)
+        e1.record()
+        eng.emb_update(db.sparse, eng.dT.view(-1)[eng.D:], FD, eng.D, "rwsadagrad", 1e-6)
+        e2.record()
+        if s >= 3:
+            ev.append((e0, e1, e2, db.nnz))
+    torch.cuda.synchronize()
+    tg = np.array([a.elapsed_time(b) for a, b, _, _ in ev]) * 1e-3
+    tu = np.array([b.elapsed_time(c) for _, b, c, _ in ev]) * 1e-3
+    nnz = np.array([z for _, _, _, z in ev], dtype=np.float64)
+    by_u = nnz * (D * 4 * 2 + 8) + T * B * D * 4 + nnz * 8   # SURVEY §8(d) bytes_bwd
+    ach = float(by_u.sum() / tu.sum() / 1e9)
+    return {"kernel": "emb_update_kernel (coalesce + row-wise Adagrad, in place)", "bound": "hbm",
+            "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak, "traffic": None,
+            "avg_launch_us": float(tu.mean() * 1e6), "algorithmic_bytes_per_launch": float(by_u.mean()),
+            "train_gather_plus_link_us": float(tg.mean() * 1e6)}
 
 
 def measure_gather_alone(eng, devb, args, hbm_peak, peak_src, T, B, D):
@@ -351,7 +376,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="cfg2", choices=["cfg2", "cfg1"])
     ap.add_argument("--ring", type=int, default=16)
-    ap.add_argument("--gemm", default="simt")
+    ap.add_argument("--gemm", default="tc", choices=["tc", "tc_bf16", "simt"])
+    ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--cpu-budget", type=float, default=15.0)
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()

@@ -52,7 +52,9 @@ _lib = None
 # every symbol include/dlrm_b200.h declares (tests check the .so exports all of them)
 SYMBOLS = [
     "dlrm_b200_abi_version", "dlrm_b200_last_error", "dlrm_b200_device_info",
-    "dlrm_b200_emb_bag_fwd", "dlrm_b200_emb_bwd_link", "dlrm_b200_emb_bwd_update",
+    "dlrm_b200_emb_bag_fwd", "dlrm_b200_emb_bag_fwd_train", "dlrm_b200_emb_bwd_link",
+    "dlrm_b200_emb_bwd_update", "dlrm_b200_head_scratch_bytes", "dlrm_b200_head_fused",
+    "dlrm_b200_interact_fwd_ex", "dlrm_b200_interact_bwd_ex",
     "dlrm_b200_linear_fwd", "dlrm_b200_linear_dgrad", "dlrm_b200_linear_wgrad",
     "dlrm_b200_interact_fwd", "dlrm_b200_interact_bwd", "dlrm_b200_loss_fwd_bwd",
     "dlrm_b200_dense_update",
@@ -68,6 +70,13 @@ def _declare(lib):
     lib.dlrm_b200_set_tunable.argtypes = [i32, i32]
     lib.dlrm_b200_device_info.argtypes = [i32, C.POINTER(i32), C.POINTER(i32), C.POINTER(i32)]
     lib.dlrm_b200_emb_bag_fwd.argtypes = [C.POINTER(EmbFwdTable), i32, i32, i64, i32, i32, vp, i64, i64, vp]
+    lib.dlrm_b200_emb_bag_fwd_train.argtypes = [C.POINTER(EmbFwdTable), C.POINTER(EmbBwdTable), i32, i32, i64, i32,
+                                                i32, vp, vp, i64, i64, vp]
+    lib.dlrm_b200_head_scratch_bytes.argtypes = [i64, i64]
+    lib.dlrm_b200_head_fused.argtypes = [vp, i64, vp, vp, vp, vp, i64, i64, i32, i32, i32, f32, vp, vp, vp, vp, vp,
+                                         vp, i64, vp, vp, i64, vp, vp]
+    lib.dlrm_b200_interact_fwd_ex.argtypes = [vp, i64, vp, i64, vp, vp, i64, i64, i32, i32, i32, vp]
+    lib.dlrm_b200_interact_bwd_ex.argtypes = [vp, i64, vp, i64, vp, i64, i64, i32, i32, i32, i32, vp, vp, i64, vp]
     lib.dlrm_b200_emb_bwd_link.argtypes = [C.POINTER(EmbBwdTable), i32, i64, i32, i32, vp, vp]
     lib.dlrm_b200_emb_bwd_update.argtypes = [C.POINTER(EmbBwdTable), i32, i32, i64, i32, i32, vp, vp,
                                              i64, i64, i32, f32, f32, vp]
@@ -86,7 +95,9 @@ def _declare(lib):
     lib.dlrm_b200_dense_update_pack.argtypes = [C.POINTER(DenseLayer), i32, i32, f32, f32, vp]
     for name in SYMBOLS:
         fn = getattr(lib, name)
-        if name != "dlrm_b200_last_error":
+        if name == "dlrm_b200_head_scratch_bytes":
+            fn.restype = i64
+        elif name != "dlrm_b200_last_error":
             fn.restype = i32
 
 

@@ -141,93 +141,110 @@ __global__ void __launch_bounds__(256) emb_update_kernel(const __grid_constant__
       my_head = tb.head[my_r];
       my_next = P.link[my_pos].x;
     }
-    unsigned owners = __ballot_sync(0xffffffffu, j < end && my_head == (int)(my_pos + 1));
-    while (owners) {
-      const int src = __ffs(owners) - 1;
-      owners &= owners - 1;
-      const long long r = __shfl_sync(0xffffffffu, my_r, src);
-      int nxt = __shfl_sync(0xffffffffu, my_next, src);
-      float* wrow = tb.w + r * D;
-      // issue the weight-row read first: it is the long-latency (HBM) access
-      Pack<W> w[NV];
+    const unsigned owners_all = __ballot_sync(0xffffffffu, j < end && my_head == (int)(my_pos + 1));
+    const int n = (int)min(32LL, end - j0);
+    constexpr int PF = NV == 1 ? 4 : (NV == 2 ? 2 : 1);  // weight rows kept in flight per warp
+    for (int u0 = 0; u0 < n; u0 += PF) {
+      // issue the long-latency (HBM) weight-row and momentum reads of up to PF owned rows first
+      Pack<W> wpf[PF][NV];
+      float mpf[PF];
 #pragma unroll
-      for (int v = 0; v < NV; ++v)
-        if (col_ok[v]) w[v] = ld_pack<W>(wrow + lane * W + v * 32 * W);
-      float m_old = 0.f;
-      if (P.optimizer == DLRM_OPT_RWSADAGRAD) m_old = tb.mom[r];
-
-      Pack<W> g[NV];
-      if (nxt == 0) {
+      for (int u = 0; u < PF; ++u) {
+        const int src = u0 + u;
+        const long long r = __shfl_sync(0xffffffffu, my_r, src & 31);
+        if (src < n && ((owners_all >> src) & 1u)) {
+          const float* wrow = tb.w + r * D;
 #pragma unroll
-        for (int v = 0; v < NV; ++v) g[v] = g_self[v];
-      } else {
-        // duplicates: gather members (self first), in chunks of 32, sorted by position
-#pragma unroll
-        for (int v = 0; v < NV; ++v)
-#pragma unroll
-          for (int e = 0; e < W; ++e) g[v].x[e] = 0.f;
-        int cnt = 1;
-        int mpos = (lane == 0) ? (int)(tb.pair_base + j0 + src) : 0x7fffffff;
-        int mbag = (int)b;
-        while (true) {
-          if (nxt != 0 && cnt < 32) {
-            const int2 e = P.link[nxt - 1];
-            if (lane == cnt) { mpos = nxt - 1; mbag = e.y; }
-            ++cnt;
-            nxt = e.x;
-            if (nxt != 0 && cnt < 32) continue;
-          }
-          // rank of my member among the chunk (positions are unique)
-          int rank = 0;
-          for (int i = 0; i < cnt; ++i) rank += (__shfl_sync(0xffffffffu, mpos, i) < mpos) ? 1 : 0;
-          for (int q = 0; q < cnt; ++q) {
-            const unsigned who = __ballot_sync(0xffffffffu, lane < cnt && rank == q);
-            const int bag = __shfl_sync(0xffffffffu, mbag, __ffs(who) - 1);
-#pragma unroll
-            for (int v = 0; v < NV; ++v) {
-              if (col_ok[v]) {
-                const Pack<W> t = ld_pack<W>(dYk + (long long)bag * P.dy_stride_sample + lane * W + v * 32 * W);
-#pragma unroll
-                for (int e = 0; e < W; ++e) g[v].x[e] += t.x[e];
-              }
-            }
-          }
-          if (nxt == 0) break;
-          cnt = 0;
-          mpos = 0x7fffffff;
+          for (int v = 0; v < NV; ++v)
+            if (col_ok[v]) wpf[u][v] = ld_pack<W>(wrow + lane * W + v * 32 * W);
+          mpf[u] = (P.optimizer == DLRM_OPT_RWSADAGRAD) ? tb.mom[r] : 0.f;
         }
       }
+#pragma unroll
+      for (int u = 0; u < PF; ++u) {
+        const int src = u0 + u;
+        const long long r = __shfl_sync(0xffffffffu, my_r, src & 31);
+        int nxt = __shfl_sync(0xffffffffu, my_next, src & 31);
+        if (!(src < n && ((owners_all >> src) & 1u))) continue;
+        float* wrow = tb.w + r * D;
+        Pack<W> w[NV];
+#pragma unroll
+        for (int v = 0; v < NV; ++v) w[v] = wpf[u][v];
+        const float m_old = mpf[u];
 
-      if (P.optimizer == DLRM_OPT_RWSADAGRAD) {
-        float sq = 0.f;
+        Pack<W> g[NV];
+        if (nxt == 0) {
 #pragma unroll
-        for (int v = 0; v < NV; ++v)
-          if (col_ok[v])
+          for (int v = 0; v < NV; ++v) g[v] = g_self[v];
+        } else {
+          // duplicates: gather members (self first), in chunks of 32, sorted by position
 #pragma unroll
-            for (int e = 0; e < W; ++e) sq = fmaf(g[v].x[e], g[v].x[e], sq);
-        sq = warp_sum(sq);
-        const float m_new = m_old + sq * inv_d;
-        const float stdv = sqrtf(m_new) + P.eps;
-        const float nlr = -P.lr;
+          for (int v = 0; v < NV; ++v)
 #pragma unroll
-        for (int v = 0; v < NV; ++v)
-          if (col_ok[v]) {
+            for (int e = 0; e < W; ++e) g[v].x[e] = 0.f;
+          int cnt = 1;
+          int mpos = (lane == 0) ? (int)(tb.pair_base + j0 + src) : 0x7fffffff;
+          int mbag = (int)b;
+          while (true) {
+            if (nxt != 0 && cnt < 32) {
+              const int2 e = P.link[nxt - 1];
+              if (lane == cnt) { mpos = nxt - 1; mbag = e.y; }
+              ++cnt;
+              nxt = e.x;
+              if (nxt != 0 && cnt < 32) continue;
+            }
+            // rank of my member among the chunk (positions are unique)
+            int rank = 0;
+            for (int i = 0; i < cnt; ++i) rank += (__shfl_sync(0xffffffffu, mpos, i) < mpos) ? 1 : 0;
+            for (int q = 0; q < cnt; ++q) {
+              const unsigned who = __ballot_sync(0xffffffffu, lane < cnt && rank == q);
+              const int bag = __shfl_sync(0xffffffffu, mbag, __ffs(who) - 1);
 #pragma unroll
-            for (int e = 0; e < W; ++e) w[v].x[e] = fmaf(nlr, g[v].x[e] / stdv, w[v].x[e]);
-            st_pack<W>(wrow + lane * W + v * 32 * W, w[v]);
+              for (int v = 0; v < NV; ++v) {
+                if (col_ok[v]) {
+                  const Pack<W> t = ld_pack<W>(dYk + (long long)bag * P.dy_stride_sample + lane * W + v * 32 * W);
+#pragma unroll
+                  for (int e = 0; e < W; ++e) g[v].x[e] += t.x[e];
+                }
+              }
+            }
+            if (nxt == 0) break;
+            cnt = 0;
+            mpos = 0x7fffffff;
           }
-        if (lane == 0) tb.mom[r] = m_new;
-      } else {
-        const float nlr = -P.lr;
+        }
+
+        if (P.optimizer == DLRM_OPT_RWSADAGRAD) {
+          float sq = 0.f;
 #pragma unroll
-        for (int v = 0; v < NV; ++v)
-          if (col_ok[v]) {
+          for (int v = 0; v < NV; ++v)
+            if (col_ok[v])
 #pragma unroll
-            for (int e = 0; e < W; ++e) w[v].x[e] = fmaf(nlr, g[v].x[e], w[v].x[e]);
-            st_pack<W>(wrow + lane * W + v * 32 * W, w[v]);
-          }
+              for (int e = 0; e < W; ++e) sq = fmaf(g[v].x[e], g[v].x[e], sq);
+          sq = warp_sum(sq);
+          const float m_new = m_old + sq * inv_d;
+          const float stdv = sqrtf(m_new) + P.eps;
+          const float nlr = -P.lr;
+#pragma unroll
+          for (int v = 0; v < NV; ++v)
+            if (col_ok[v]) {
+#pragma unroll
+              for (int e = 0; e < W; ++e) w[v].x[e] = fmaf(nlr, g[v].x[e] / stdv, w[v].x[e]);
+              st_pack<W>(wrow + lane * W + v * 32 * W, w[v]);
+            }
+          if (lane == 0) tb.mom[r] = m_new;
+        } else {
+          const float nlr = -P.lr;
+#pragma unroll
+          for (int v = 0; v < NV; ++v)
+            if (col_ok[v]) {
+#pragma unroll
+              for (int e = 0; e < W; ++e) w[v].x[e] = fmaf(nlr, g[v].x[e], w[v].x[e]);
+              st_pack<W>(wrow + lane * W + v * 32 * W, w[v]);
+            }
+        }
+        if (lane == 0) tb.head[r] = 0;
       }
-      if (lane == 0) tb.head[r] = 0;
     }
   }
 }

@@ -19,6 +19,8 @@ struct EmbFwdTable {
   const void* off;
   const float* rw;
   long long nnz;
+  int* head;            // training: per-row list heads of this table (see emb_bwd.cu), else null
+  long long pair_base;  // training: first slot of this table in link[]
 };
 
 struct EmbFwdParams {
@@ -30,7 +32,17 @@ struct EmbFwdParams {
   int dim;
   int include_last;
   int bags_per_group;
+  int2* link;  // training: link[pos] = {previous head of the row, bag}
 };
+
+// Fused "link" step of the sort-free coalesce (emb_bwd.cu): thread the occurrence at position j
+// of this table onto the per-row list while its index is already in a register.
+__device__ __forceinline__ void link_occurrence(const EmbFwdTable& tb, int2* link, long long j,
+                                                long long row, long long bag) {
+  const long long pos = tb.pair_base + j;
+  const int prev = atomicExch(tb.head + row, (int)(pos + 1));
+  link[pos] = make_int2(prev, (int)bag);
+}
 
 template <typename idx_t>
 __device__ __forceinline__ long long bag_end(const idx_t* off, long long b, long long batch,
@@ -39,8 +51,8 @@ __device__ __forceinline__ long long bag_end(const idx_t* off, long long b, long
 }
 
 // G lanes per bag, NV float4 per lane (dim = 4*G*NV when exact; columns >= dim are masked)
-template <int G, int NV, int U, typename idx_t, bool WEIGHTED>
-__global__ void __launch_bounds__(256) emb_fwd_vec_kernel(const __grid_constant__ EmbFwdParams P) {
+template <int G, int NV, int U, typename idx_t, bool WEIGHTED, bool LINK>
+__global__ void __launch_bounds__(256, (G == 32 && NV == 1) ? 4 : 1) emb_fwd_vec_kernel(const __grid_constant__ EmbFwdParams P) {
   const EmbFwdTable& tb = P.t[blockIdx.y];
   const idx_t* __restrict__ idx = static_cast<const idx_t*>(tb.idx);
   const idx_t* __restrict__ off = static_cast<const idx_t*>(tb.off);
@@ -60,32 +72,39 @@ __global__ void __launch_bounds__(256) emb_fwd_vec_kernel(const __grid_constant_
 
   // bag boundaries of this group's run of bags: one coalesced load, then shuffles.
   // (S <= G is enforced by the host so lane gl can hold boundary gl.)
-  long long my_bound = 0;
+  // positions inside one call fit 31 bits (host-checked: nnz < 2^31); rows stay 64-bit
+  int my_bound = 0;
   if (gl <= nb) {
     const long long b = b0 + gl;
-    my_bound = (b < P.batch) ? (long long)off[b] : 0;
-    if (gl == nb) my_bound = bag_end<idx_t>(off, b - 1, P.batch, tb.nnz, P.include_last);
+    my_bound = (b < P.batch) ? (int)off[b] : 0;
+    if (gl == nb) my_bound = (int)bag_end<idx_t>(off, b - 1, P.batch, tb.nnz, P.include_last);
   }
-  long long start = __shfl_sync(gmask, my_bound, 0, G);
-  long long end = __shfl_sync(gmask, my_bound, 1, G);
+  int start = __shfl_sync(gmask, my_bound, 0, G);
+  int end = __shfl_sync(gmask, my_bound, 1, G);
   // first index chunk of bag 0
   long long my_row = (start + gl < end) ? (long long)idx[start + gl] : 0;
+  if (LINK && start + gl < end) link_occurrence(tb, P.link, start + gl, my_row, b0);
 
   for (int s = 0; s < nb; ++s) {
     // prefetch boundaries + first index chunk of the next bag
-    long long nstart = 0, nend = 0, next_row = 0;
+    int nstart = 0, nend = 0;
+    long long next_row = 0;
     if (s + 1 < nb) {
       nstart = end;
       nend = __shfl_sync(gmask, my_bound, s + 2, G);
       next_row = (nstart + gl < nend) ? (long long)idx[nstart + gl] : 0;
+      if (LINK && nstart + gl < nend) link_occurrence(tb, P.link, nstart + gl, next_row, b0 + s + 1);
     }
     float4 acc[NV];
 #pragma unroll
     for (int v = 0; v < NV; ++v) acc[v] = make_float4(0.f, 0.f, 0.f, 0.f);
 
-    for (long long j0 = start; j0 < end; j0 += G) {
-      if (j0 != start) my_row = (j0 + gl < end) ? (long long)idx[j0 + gl] : 0;
-      const int n = (int)min((long long)G, end - j0);
+    for (int j0 = start; j0 < end; j0 += G) {
+      if (j0 != start) {
+        my_row = (j0 + gl < end) ? (long long)idx[j0 + gl] : 0;
+        if (LINK && j0 + gl < end) link_occurrence(tb, P.link, j0 + gl, my_row, b0 + s);
+      }
+      const int n = min(G, end - j0);
       for (int jj = 0; jj < n; jj += U) {
         float4 val[U][NV];
         float wgt[U];
@@ -134,7 +153,7 @@ __global__ void __launch_bounds__(256) emb_fwd_vec_kernel(const __grid_constant_
 }
 
 // any dim / any alignment: one thread per output element, sequential over the bag
-template <typename idx_t, bool WEIGHTED>
+template <typename idx_t, bool WEIGHTED, bool LINK>
 __global__ void emb_fwd_scalar_kernel(const __grid_constant__ EmbFwdParams P) {
   const EmbFwdTable& tb = P.t[blockIdx.y];
   const idx_t* __restrict__ idx = static_cast<const idx_t*>(tb.idx);
@@ -149,36 +168,37 @@ __global__ void emb_fwd_scalar_kernel(const __grid_constant__ EmbFwdParams P) {
   float acc = 0.f;
   for (long long j = start; j < end; ++j) {
     const long long r = idx[j];
+    if (LINK && d == 0) link_occurrence(tb, P.link, j, r, b);
     const float x = tb.w[r * D + d];
     acc = WEIGHTED ? fmaf(tb.rw[r], x, acc) : acc + x;
   }
   P.out[b * P.stride_sample + (long long)blockIdx.y * P.stride_table + d] = acc;
 }
 
-template <int G, int NV, int U, typename idx_t, bool WEIGHTED>
+template <int G, int NV, int U, typename idx_t, bool WEIGHTED, bool LINK>
 static int launch_vec(const EmbFwdParams& P, int num_tables, cudaStream_t st) {
   const int block = 256;
   const long long groups_per_block = (long long)(block / 32) * (32 / G);
   const long long groups = (P.batch + P.bags_per_group - 1) / P.bags_per_group;
   dim3 grid((unsigned)((groups + groups_per_block - 1) / groups_per_block), (unsigned)num_tables);
-  emb_fwd_vec_kernel<G, NV, U, idx_t, WEIGHTED><<<grid, block, 0, st>>>(P);
+  emb_fwd_vec_kernel<G, NV, U, idx_t, WEIGHTED, LINK><<<grid, block, 0, st>>>(P);
   DLRM_CHECK_LAUNCH("emb_fwd_vec_kernel");
   return 0;
 }
 
-template <typename idx_t, bool WEIGHTED>
+template <typename idx_t, bool WEIGHTED, bool LINK>
 static int dispatch(const EmbFwdParams& Pin, int num_tables, bool vec_ok, cudaStream_t st) {
   EmbFwdParams P = Pin;
   const int D = P.dim;
   if (vec_ok) {
     const int u8 = get_tunable(TUNE_EMB_UNROLL) != 4;
     int S = get_tunable(TUNE_EMB_BAGS_PER_GROUP);
-    if (S <= 0) S = 4;
+    if (S <= 0) S = 8;  // measured on B200 (profiles/): 8 bags per group, 8 rows in flight
 #define VEC(G, NV)                                                                   \
   do {                                                                               \
     P.bags_per_group = S < (G) ? S : (G)-1;                                          \
-    if ((G) >= 8 && u8) return launch_vec<G, NV, 8, idx_t, WEIGHTED>(P, num_tables, st); \
-    return launch_vec<G, NV, ((G) >= 4 ? 4 : (G)), idx_t, WEIGHTED>(P, num_tables, st);  \
+    if ((G) >= 8 && u8) return launch_vec<G, NV, 8, idx_t, WEIGHTED, LINK>(P, num_tables, st); \
+    return launch_vec<G, NV, ((G) >= 4 ? 4 : (G)), idx_t, WEIGHTED, LINK>(P, num_tables, st);  \
   } while (0)
     if (D == 16) VEC(4, 1);  // dim 4 / 8: scalar kernel (a group must hold S+1 bag bounds)
     if (D == 32) VEC(8, 1);
@@ -191,17 +211,17 @@ static int dispatch(const EmbFwdParams& Pin, int num_tables, bool vec_ok, cudaSt
   const int block = 256;
   const long long n = P.batch * D;
   dim3 grid((unsigned)((n + block - 1) / block), (unsigned)num_tables);
-  emb_fwd_scalar_kernel<idx_t, WEIGHTED><<<grid, block, 0, st>>>(P);
+  emb_fwd_scalar_kernel<idx_t, WEIGHTED, LINK><<<grid, block, 0, st>>>(P);
   DLRM_CHECK_LAUNCH("emb_fwd_scalar_kernel");
   return 0;
 }
 
 }  // namespace dlrm
 
-extern "C" int dlrm_b200_emb_bag_fwd(const dlrm_emb_fwd_table_t* tables, int num_tables, int dim,
-                                     int64_t batch, int idx_bytes, int include_last, float* out,
-                                     int64_t out_stride_sample, int64_t out_stride_table,
-                                     void* stream) {
+static int emb_fwd_impl(const dlrm_emb_fwd_table_t* tables, const dlrm_emb_bwd_table_t* train,
+                        int32_t* link, int num_tables, int dim, int64_t batch, int idx_bytes,
+                        int include_last, float* out, int64_t out_stride_sample,
+                        int64_t out_stride_table, void* stream) {
   using namespace dlrm;
   if (num_tables < 0 || num_tables > DLRM_B200_MAX_TABLES_PER_CALL)
     return set_error("emb_bag_fwd: num_tables=%d out of range [0,%d]", num_tables,
@@ -211,6 +231,7 @@ extern "C" int dlrm_b200_emb_bag_fwd(const dlrm_emb_fwd_table_t* tables, int num
   if (batch == 0 || num_tables == 0) return 0;
   if (batch < 0 || batch * (int64_t)dim > (int64_t)0x7fffffff * 256)
     return set_error("emb_bag_fwd: batch=%lld too large", (long long)batch);
+  if (train && !link) return set_error("emb_bag_fwd_train: link is NULL");
   EmbFwdParams P;
   bool weighted = false, any_unweighted = false;
   bool vec_ok = (dim % 4 == 0) && dim <= 512 && aligned16(out) && out_stride_sample % 4 == 0 &&
@@ -221,8 +242,14 @@ extern "C" int dlrm_b200_emb_bag_fwd(const dlrm_emb_fwd_table_t* tables, int num
     P.t[k].off = tables[k].offsets;
     P.t[k].rw = tables[k].row_weights;
     P.t[k].nnz = tables[k].nnz;
+    P.t[k].head = train ? train[k].head : nullptr;
+    P.t[k].pair_base = train ? train[k].pair_base : 0;
     if (!tables[k].weight || !tables[k].offsets || (!tables[k].indices && tables[k].nnz > 0))
       return set_error("emb_bag_fwd: table %d has a NULL pointer", k);
+    if (tables[k].nnz > 0x7ffffffeLL) return set_error("emb_bag_fwd: table %d: nnz >= 2^31 per call", k);
+    if (train && !train[k].head) return set_error("emb_bag_fwd_train: table %d head is NULL", k);
+    if (train && train[k].pair_base + tables[k].nnz > 0x7ffffffeLL)
+      return set_error("emb_bag_fwd_train: more than 2^31-2 index occurrences");
     if (tables[k].row_weights) weighted = true; else any_unweighted = true;
     vec_ok = vec_ok && aligned16(tables[k].weight);
   }
@@ -235,10 +262,34 @@ extern "C" int dlrm_b200_emb_bag_fwd(const dlrm_emb_fwd_table_t* tables, int num
   P.dim = dim;
   P.include_last = include_last;
   P.bags_per_group = 1;
+  P.link = reinterpret_cast<int2*>(link);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  if (idx_bytes == 8)
-    return weighted ? dispatch<long long, true>(P, num_tables, vec_ok, st)
-                    : dispatch<long long, false>(P, num_tables, vec_ok, st);
-  return weighted ? dispatch<int, true>(P, num_tables, vec_ok, st)
-                  : dispatch<int, false>(P, num_tables, vec_ok, st);
+#define DISPATCH(IDX)                                                                          \
+  do {                                                                                         \
+    if (train) return weighted ? dispatch<IDX, true, true>(P, num_tables, vec_ok, st)          \
+                               : dispatch<IDX, false, true>(P, num_tables, vec_ok, st);        \
+    return weighted ? dispatch<IDX, true, false>(P, num_tables, vec_ok, st)                    \
+                    : dispatch<IDX, false, false>(P, num_tables, vec_ok, st);                  \
+  } while (0)
+  if (idx_bytes == 8) DISPATCH(long long);
+  DISPATCH(int);
+#undef DISPATCH
+}
+
+extern "C" int dlrm_b200_emb_bag_fwd(const dlrm_emb_fwd_table_t* tables, int num_tables, int dim,
+                                     int64_t batch, int idx_bytes, int include_last, float* out,
+                                     int64_t out_stride_sample, int64_t out_stride_table,
+                                     void* stream) {
+  return emb_fwd_impl(tables, nullptr, nullptr, num_tables, dim, batch, idx_bytes, include_last, out,
+                      out_stride_sample, out_stride_table, stream);
+}
+
+extern "C" int dlrm_b200_emb_bag_fwd_train(const dlrm_emb_fwd_table_t* tables,
+                                           const dlrm_emb_bwd_table_t* train, int num_tables, int dim,
+                                           int64_t batch, int idx_bytes, int include_last, int32_t* next,
+                                           float* out, int64_t out_stride_sample,
+                                           int64_t out_stride_table, void* stream) {
+  if (!train) return dlrm::set_error("emb_bag_fwd_train: train descriptors are NULL");
+  return emb_fwd_impl(tables, train, next, num_tables, dim, batch, idx_bytes, include_last, out,
+                      out_stride_sample, out_stride_table, stream);
 }

@@ -3,6 +3,8 @@
 // the operand T[b] = [x; ly_0; ...; ly_{T-1}] is read IN PLACE from the buffer the bottom MLP and
 // the gather wrote, the strict-lower-triangle flatten happens in the epilogue, and x is copied
 // into R[:, 0:D] on the way.
+#include <cuda_bf16.h>
+
 #include "common.cuh"
 
 namespace dlrm {
@@ -16,7 +18,7 @@ __global__ void __launch_bounds__(192) interact_fwd_kernel(const float* __restri
                                                            float* __restrict__ R, long long ldr,
                                                            long long batch, int F, int D, int itself,
                                                            int spb) {
-  extern __shared__ float smem[];
+  extern __shared__ __align__(128) float smem[];
   const int nb = (F + 2) / 3;
   const int Fp = nb * 3;
   const int LD = D + 1;
@@ -77,6 +79,111 @@ __global__ void __launch_bounds__(192) interact_fwd_kernel(const float* __restri
 }
 
 // ------------------------------------------------------------------------------------------
+// forward v2 (dim % 4 == 0): the F x D operand of each sample is one contiguous block of T, so
+// it is brought into shared memory by ONE bulk-async copy (cp.async.bulk + mbarrier complete_tx,
+// the 1-D TMA path) instead of per-thread loads; rows stay unpadded and every lane walks the
+// feature dimension rotated by its lane id, which keeps the 32 lanes on 32 different banks.
+// Optionally writes R as the (hi, lo) bf16 operand pair of the first top-MLP GEMM.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(192) interact_fwd2_kernel(const float* __restrict__ T, long long ldt,
+                                                            float* __restrict__ R, long long ldr,
+                                                            __nv_bfloat16* __restrict__ Rh,
+                                                            __nv_bfloat16* __restrict__ Rl, long long ldrb,
+                                                            long long batch, int F, int D, int itself,
+                                                            int spb) {
+  extern __shared__ __align__(128) float smem[];
+  const int nb = (F + 2) / 3;
+  const int Fp = nb * 3;
+  const int tps = nb * (nb + 1) / 2;
+  const int npairs = itself ? F * (F + 1) / 2 : F * (F - 1) / 2;
+  const int per_sample = Fp * D + ((npairs + 3) & ~3);
+  unsigned long long* bar = reinterpret_cast<unsigned long long*>(smem + (size_t)spb * per_sample);
+  const long long s0 = (long long)blockIdx.x * spb;
+  const int ns = (int)min((long long)spb, batch - s0);
+  const unsigned bar_a = (unsigned)__cvta_generic_to_shared(bar);
+  if (threadIdx.x == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar_a));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    const unsigned bytes = (unsigned)(F * D * 4);
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_a), "r"(bytes * ns) : "memory");
+    for (int s = 0; s < ns; ++s) {
+      const unsigned dst = (unsigned)__cvta_generic_to_shared(smem + (size_t)s * per_sample);
+      const float* src = T + (s0 + s) * ldt;
+      asm volatile(
+          "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+          "l"(src), "r"(bytes), "r"(bar_a)
+          : "memory");
+    }
+  }
+  // zero the padding rows F..Fp-1 while the copy is in flight
+  for (int e = threadIdx.x; e < ns * (Fp - F) * D; e += blockDim.x) {
+    const int s = e / ((Fp - F) * D);
+    const int rem = e - s * (Fp - F) * D;
+    smem[(size_t)s * per_sample + F * D + rem] = 0.f;
+  }
+  __syncthreads();  // barrier init visible to all threads + padding written
+  {
+    unsigned ok = 0;
+    int tries = 0;
+    while (true) {
+      asm volatile(
+          "{\n\t.reg .pred P1;\n\tmbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2;\n\tselp.u32 %0, 1, 0, P1;\n\t}"
+          : "=r"(ok)
+          : "r"(bar_a), "r"(0u)
+          : "memory");
+      if (ok) break;
+      if (++tries > (1 << 22)) __trap();
+    }
+  }
+  const int lane = threadIdx.x & 31;
+  for (int item = threadIdx.x; item < ns * tps; item += blockDim.x) {
+    const int s = item / tps;
+    const int q = item - s * tps;
+    int a = (int)((sqrtf(8.f * q + 1.f) - 1.f) * 0.5f);
+    while ((a + 1) * (a + 2) / 2 <= q) ++a;
+    while (a * (a + 1) / 2 > q) --a;
+    const int c = q - a * (a + 1) / 2;
+    const float* Ts = smem + (size_t)s * per_sample;
+    const float* ra = Ts + (3 * a) * D;
+    const float* rc = Ts + (3 * c) * D;
+    float z[3][3] = {{0.f, 0.f, 0.f}, {0.f, 0.f, 0.f}, {0.f, 0.f, 0.f}};
+    int d = lane % D;
+    for (int it = 0; it < D; ++it) {
+      const float a0 = ra[d], a1 = ra[D + d], a2 = ra[2 * D + d];
+      const float c0 = rc[d], c1 = rc[D + d], c2 = rc[2 * D + d];
+      z[0][0] = fmaf(a0, c0, z[0][0]); z[0][1] = fmaf(a0, c1, z[0][1]); z[0][2] = fmaf(a0, c2, z[0][2]);
+      z[1][0] = fmaf(a1, c0, z[1][0]); z[1][1] = fmaf(a1, c1, z[1][1]); z[1][2] = fmaf(a1, c2, z[1][2]);
+      z[2][0] = fmaf(a2, c0, z[2][0]); z[2][1] = fmaf(a2, c1, z[2][1]); z[2][2] = fmaf(a2, c2, z[2][2]);
+      if (++d == D) d = 0;
+    }
+    float* Zs = smem + (size_t)s * per_sample + Fp * D;
+#pragma unroll
+    for (int x = 0; x < 3; ++x)
+#pragma unroll
+      for (int y = 0; y < 3; ++y) {
+        const int i = 3 * a + x, j = 3 * c + y;
+        if (i < F && (j < i || (itself && j == i))) {
+          const int p = itself ? i * (i + 1) / 2 + j : i * (i - 1) / 2 + j;
+          Zs[p] = z[x][y];
+        }
+      }
+  }
+  __syncthreads();
+  const int ncols = D + npairs;
+  for (int e = threadIdx.x; e < ns * ncols; e += blockDim.x) {
+    const int s = e / ncols, cidx = e - s * ncols;
+    const float v = cidx < D ? smem[(size_t)s * per_sample + cidx]
+                             : smem[(size_t)s * per_sample + Fp * D + (cidx - D)];
+    if (R) R[(s0 + s) * ldr + cidx] = v;
+    if (Rh) {
+      const __nv_bfloat16 hb = __float2bfloat16_rn(v);
+      Rh[(s0 + s) * ldrb + cidx] = hb;
+      if (Rl) Rl[(s0 + s) * ldrb + cidx] = __float2bfloat16_rn(v - __bfloat162float(hb));
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
 // backward: dT[i][d] = sum_j S[i][j] T[j][d] (+ dR[d] for i == 0),  S = dZ + dZ^T.
 // One thread owns a column d of one sample: T[:, d] lives in registers, S rows are read as
 // broadcast float4 from shared memory.
@@ -86,8 +193,10 @@ __global__ void __launch_bounds__(128) interact_bwd_kernel(const float* __restri
                                                            const float* __restrict__ dR, long long lddr,
                                                            float* __restrict__ dT, long long lddt,
                                                            long long batch, int F, int D, int itself,
-                                                           int mask0, int spb) {
-  extern __shared__ __align__(16) float smem[];
+                                                           int mask0, int spb,
+                                                           __nv_bfloat16* __restrict__ g0h,
+                                                           __nv_bfloat16* __restrict__ g0l, long long ldg0) {
+  extern __shared__ __align__(128) float smem[];
   const int F4 = (F + 3) & ~3;
   const long long s0 = (long long)blockIdx.x * spb;
   const int ns = (int)min((long long)spb, batch - s0);
@@ -132,21 +241,50 @@ __global__ void __launch_bounds__(128) interact_bwd_kernel(const float* __restri
       if (i == 0 && mask0 == DLRM_ACT_RELU) acc = (t[0] > 0.f) ? acc : 0.f;
       if (i == 0 && mask0 == DLRM_ACT_SIGMOID) acc *= (1.0f - t[0]) * t[0];
       out[(long long)i * D] = acc;
+      if (i == 0 && g0h) {  // feature 0 = gradient into the bottom MLP: also as a (hi, lo) bf16 pair
+        const __nv_bfloat16 hb = __float2bfloat16_rn(acc);
+        g0h[(s0 + s) * ldg0 + d] = hb;
+        if (g0l) g0l[(s0 + s) * ldg0 + d] = __float2bfloat16_rn(acc - __bfloat162float(hb));
+      }
     }
   }
 }
 
 }  // namespace dlrm
 
-extern "C" int dlrm_b200_interact_fwd(const float* T, int64_t ldt, float* R, int64_t ldr,
-                                      int64_t batch, int num_features, int dim, int itself,
-                                      void* stream) {
+extern "C" int dlrm_b200_interact_fwd_ex(const float* T, int64_t ldt, float* R, int64_t ldr, void* R_hi,
+                                         void* R_lo, int64_t ld_rb, int64_t batch, int num_features,
+                                         int dim, int itself, void* stream) {
   using namespace dlrm;
   if (batch == 0) return 0;
   if (num_features < 1 || dim < 1) return set_error("interact_fwd: F=%d D=%d", num_features, dim);
+  if (!T || (!R && !R_hi)) return set_error("interact_fwd: NULL pointer");
   const int F = num_features, D = dim;
   const int nb = (F + 2) / 3, Fp = nb * 3, tps = nb * (nb + 1) / 2;
   const int npairs = itself ? F * (F + 1) / 2 : F * (F - 1) / 2;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const bool bulk = (D % 4 == 0) && (ldt % 4 == 0) && aligned16(T);
+  if (bulk) {
+    const size_t per_sample = ((size_t)Fp * D + ((npairs + 3) & ~3)) * sizeof(float);
+    int spb = 192 / tps;
+    if (spb < 1) spb = 1;
+    while (spb > 1 && spb * per_sample + 16 > 100 * 1024) --spb;
+    const size_t smem = spb * per_sample + 16;
+    if (smem <= 200 * 1024) {
+      static thread_local bool configured = false;
+      if (smem > 48 * 1024 && !configured) {
+        DLRM_CUDA(cudaFuncSetAttribute(interact_fwd2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        configured = true;
+      }
+      const long long grid = (batch + spb - 1) / spb;
+      interact_fwd2_kernel<<<(unsigned)grid, 192, smem, st>>>(T, ldt, R, ldr, static_cast<__nv_bfloat16*>(R_hi),
+                                                              static_cast<__nv_bfloat16*>(R_lo), ld_rb, batch, F, D,
+                                                              itself, spb);
+      DLRM_CHECK_LAUNCH("interact_fwd2_kernel");
+      return 0;
+    }
+  }
+  if (R_hi) return set_error("interact_fwd: bf16 output needs dim %% 4 == 0 and aligned T");
   const size_t per_sample = ((size_t)Fp * (D + 1) + npairs) * sizeof(float);
   if (per_sample > 200 * 1024)
     return set_error("interact_fwd: F=%d D=%d needs %zu B of shared memory per sample (max 200 KB)",
@@ -162,15 +300,21 @@ extern "C" int dlrm_b200_interact_fwd(const float* T, int64_t ldt, float* R, int
     configured = 200 * 1024;
   }
   const long long grid = (batch + spb - 1) / spb;
-  interact_fwd_kernel<<<(unsigned)grid, 192, smem, static_cast<cudaStream_t>(stream)>>>(
-      T, ldt, R, ldr, batch, F, D, itself, spb);
+  interact_fwd_kernel<<<(unsigned)grid, 192, smem, st>>>(T, ldt, R, ldr, batch, F, D, itself, spb);
   DLRM_CHECK_LAUNCH("interact_fwd_kernel");
   return 0;
 }
 
-extern "C" int dlrm_b200_interact_bwd(const float* T, int64_t ldt, const float* dR, int64_t lddr,
-                                      float* dT, int64_t lddt, int64_t batch, int num_features,
-                                      int dim, int itself, int mask_feature0, void* stream) {
+extern "C" int dlrm_b200_interact_fwd(const float* T, int64_t ldt, float* R, int64_t ldr,
+                                      int64_t batch, int num_features, int dim, int itself,
+                                      void* stream) {
+  return dlrm_b200_interact_fwd_ex(T, ldt, R, ldr, nullptr, nullptr, 0, batch, num_features, dim, itself, stream);
+}
+
+extern "C" int dlrm_b200_interact_bwd_ex(const float* T, int64_t ldt, const float* dR, int64_t lddr,
+                                         float* dT, int64_t lddt, int64_t batch, int num_features,
+                                         int dim, int itself, int mask_feature0, void* g0_hi, void* g0_lo,
+                                         int64_t ld_g0, void* stream) {
   using namespace dlrm;
   if (batch == 0) return 0;
   const int F = num_features, D = dim;
@@ -183,12 +327,21 @@ extern "C" int dlrm_b200_interact_bwd(const float* T, int64_t ldt, const float* 
   if (smem > 48 * 1024) return set_error("interact_bwd: shared memory %zu too large", smem);
   const long long grid = (batch + spb - 1) / spb;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  __nv_bfloat16* gh = static_cast<__nv_bfloat16*>(g0_hi);
+  __nv_bfloat16* gl = static_cast<__nv_bfloat16*>(g0_lo);
   if (F <= 8)
-    interact_bwd_kernel<8><<<(unsigned)grid, 128, smem, st>>>(T, ldt, dR, lddr, dT, lddt, batch, F, D, itself, mask_feature0, spb);
+    interact_bwd_kernel<8><<<(unsigned)grid, 128, smem, st>>>(T, ldt, dR, lddr, dT, lddt, batch, F, D, itself, mask_feature0, spb, gh, gl, ld_g0);
   else if (F <= 32)
-    interact_bwd_kernel<32><<<(unsigned)grid, 128, smem, st>>>(T, ldt, dR, lddr, dT, lddt, batch, F, D, itself, mask_feature0, spb);
+    interact_bwd_kernel<32><<<(unsigned)grid, 128, smem, st>>>(T, ldt, dR, lddr, dT, lddt, batch, F, D, itself, mask_feature0, spb, gh, gl, ld_g0);
   else
-    interact_bwd_kernel<64><<<(unsigned)grid, 128, smem, st>>>(T, ldt, dR, lddr, dT, lddt, batch, F, D, itself, mask_feature0, spb);
+    interact_bwd_kernel<64><<<(unsigned)grid, 128, smem, st>>>(T, ldt, dR, lddr, dT, lddt, batch, F, D, itself, mask_feature0, spb, gh, gl, ld_g0);
   DLRM_CHECK_LAUNCH("interact_bwd_kernel");
   return 0;
+}
+
+extern "C" int dlrm_b200_interact_bwd(const float* T, int64_t ldt, const float* dR, int64_t lddr,
+                                      float* dT, int64_t lddt, int64_t batch, int num_features,
+                                      int dim, int itself, int mask_feature0, void* stream) {
+  return dlrm_b200_interact_bwd_ex(T, ldt, dR, lddr, dT, lddt, batch, num_features, dim, itself,
+                                   mask_feature0, nullptr, nullptr, 0, stream);
 }

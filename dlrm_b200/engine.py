@@ -259,21 +259,34 @@ class Engine:
         sig = self.sigmoid_bot if which == "bot" else self.sigmoid_top
         return ACT_SIGMOID if i == sig else ACT_RELU
 
-    def emb_forward(self, sp: SparseInput, out: torch.Tensor, stride_sample: int, stride_table: int):
+    def emb_forward(self, sp: SparseInput, out: torch.Tensor, stride_sample: int, stride_table: int,
+                    link: bool = False):
+        """One launch per <= 64 tables.  link=True (training) also threads every index occurrence
+        onto its per-row list (step 1 of the sort-free coalesce) inside the same kernel."""
         chk = _lib.check
+        if link:
+            total = sp.nnz_total if sp.include_last else sum(int(i.numel()) for i in sp.indices)
+            self._ensure_link(total)
         for c0 in range(0, self.T, _lib.MAX_TABLES):
             ks = list(range(c0, min(self.T, c0 + _lib.MAX_TABLES)))
             desc = self._fwd_desc(sp, ks)
-            chk(self.lib.dlrm_b200_emb_bag_fwd(desc, len(ks), self.D, sp.batch, sp.idx_bytes,
-                                               int(sp.include_last),
-                                               out.data_ptr() + c0 * stride_table * 4, stride_sample,
-                                               stride_table, _stream()), "emb_bag_fwd")
+            optr = out.data_ptr() + c0 * stride_table * 4
+            if link:
+                bdesc, _ = self._bwd_desc_chunk(sp, ks)
+                chk(self.lib.dlrm_b200_emb_bag_fwd_train(desc, bdesc, len(ks), self.D, sp.batch, sp.idx_bytes,
+                                                         int(sp.include_last), self.link.data_ptr(), optr,
+                                                         stride_sample, stride_table, _stream()),
+                    "emb_bag_fwd_train")
+            else:
+                chk(self.lib.dlrm_b200_emb_bag_fwd(desc, len(ks), self.D, sp.batch, sp.idx_bytes,
+                                                   int(sp.include_last), optr, stride_sample, stride_table,
+                                                   _stream()), "emb_bag_fwd")
             self.n_launch += 1
 
     def mlp_forward(self, which: str, x: torch.Tensor, ldx: int, B: int, outs: List[torch.Tensor],
-                    lds: List[int]):
+                    lds: List[int], upto: Optional[int] = None):
         ln = self.ln_bot if which == "bot" else self.ln_top
-        for i in range(len(ln) - 1):
+        for i in range(len(ln) - 1 if upto is None else upto):
             K, N = ln[i], ln[i + 1]
             _lib.check(self.lib.dlrm_b200_linear_fwd(x.data_ptr(), ldx, self.W[which][i].data_ptr(), K,
                                                      self.b[which][i].data_ptr(), outs[i].data_ptr(),
@@ -292,14 +305,48 @@ class Engine:
             return self.Rbuf, self.ldr
         return self.Tbuf, self.F * self.D
 
-    def forward(self, X: torch.Tensor, sp: SparseInput) -> torch.Tensor:
+    # ---- fused head (last top layer with a single output; csrc/head.cu)
+    @property
+    def has_head(self) -> bool:
+        return self.ln_top[-1] == 1 and len(self.ln_top) >= 3
+
+    def _head(self, B: int, target: Optional[torch.Tensor], train: bool):
+        """p (+ loss, gz, dW/db of the last layer and the gradient w.r.t. its input)."""
+        nt = len(self.ln_top) - 1
+        K = self.ln_top[nt - 1]
+        h = self.top_act[nt - 2]
+        need = int(self.lib.dlrm_b200_head_scratch_bytes(B, K))
+        if getattr(self, "head_scratch", None) is None or self.head_scratch.numel() < need:
+            self.head_scratch = torch.zeros(need, dtype=torch.uint8, device=self.device)
+        gprev = gh = gl = None
+        ldg = ldb = 0
+        if train:
+            if self.tc and (nt - 2) < self.ntc["top"]:
+                gh_t, gl_t, ldb = self.tc_gz["top"][nt - 2]
+                gh, gl = gh_t.data_ptr(), gl_t.data_ptr()
+            else:
+                gprev, ldg = self.top_gz[nt - 2].data_ptr(), self.top_gz[nt - 2].shape[1]
+        _lib.check(self.lib.dlrm_b200_head_fused(
+            h.data_ptr(), h.shape[1], self.W["top"][nt - 1].data_ptr(), self.b["top"][nt - 1].data_ptr(),
+            _ptr(target), _ptr(self.loss_ws), B, K, self._act("top", nt - 1), self._act("top", nt - 2),
+            self.loss_kind, self.loss_threshold, self.top_act[nt - 1].data_ptr(),
+            self.loss_buf.data_ptr() if target is not None else None,
+            self.top_gz[nt - 1].data_ptr() if target is not None else None,
+            self.dW["top"][nt - 1].data_ptr() if train else None,
+            self.db["top"][nt - 1].data_ptr() if train else None,
+            gprev, ldg, gh, gl, ldb, self.head_scratch.data_ptr(), _stream()), "head_fused")
+        self.n_launch += 1
+
+    def forward(self, X: torch.Tensor, sp: SparseInput, *, link: bool = False, skip_head: bool = False) -> torch.Tensor:
         """sequential_forward.  X [B, m_den] fp32 on the device.  Returns p [B, n_out] (a view of an
-        engine buffer, valid until the next call); clamped iff 0 < loss_threshold < 1."""
+        engine buffer, valid until the next call); clamped iff 0 < loss_threshold < 1.
+        link=True: training forward (gather also builds the per-row occurrence lists);
+        skip_head=True: leave the final 1-output layer to the fused head in backward()."""
         B = sp.batch
         if B > self.max_batch:
             self._alloc_activations(B)
         if self.tc:
-            return self._tc_forward(X, sp)
+            return self._tc_forward(X, sp, link, skip_head)
         FD = self.F * self.D
         outs, lds = self._bot_outs(B)
         self.mlp_forward("bot", X, X.stride(0), B, outs, lds)
@@ -307,7 +354,7 @@ class Engine:
             ev = self._gather_events
             if ev is not None:
                 ev[0].record()
-            self.emb_forward(sp, self.Tbuf.view(-1)[self.D:], FD, self.D)
+            self.emb_forward(sp, self.Tbuf.view(-1)[self.D:], FD, self.D, link)
             if ev is not None:
                 ev[1].record()
         if self.op == "dot":
@@ -316,11 +363,31 @@ class Engine:
                                                        _stream()), "interact_fwd")
             self.n_launch += 1
         xin, ldx = self._top_in()
-        self.mlp_forward("top", xin, ldx, B, self.top_act, [t.shape[1] for t in self.top_act])
+        self.mlp_forward("top", xin, ldx, B, self.top_act, [t.shape[1] for t in self.top_act],
+                         upto=(len(self.ln_top) - 2) if self.has_head else None)
+        if self.has_head and not skip_head:
+            self._head(B, None, False)
         p = self.top_act[-1][:B]
         if 0.0 < self.loss_threshold < 1.0:
             return torch.clamp(p, self.loss_threshold, 1.0 - self.loss_threshold)
         return p
+
+    def prepare(self, sp: SparseInput, train: bool = True):
+        """Allocate every lazily-created buffer / tcgen05 plan for this batch shape (no kernels that
+        change parameters): required before CUDA-graph capture."""
+        B = sp.batch
+        if B > self.max_batch:
+            self._alloc_activations(B)
+        if train and self.T:
+            self._ensure_link(sp.nnz_total if sp.include_last else sum(int(i.numel()) for i in sp.indices))
+        if self.has_head:
+            nt = len(self.ln_top) - 1
+            need = int(self.lib.dlrm_b200_head_scratch_bytes(B, self.ln_top[nt - 1]))
+            if getattr(self, "head_scratch", None) is None or self.head_scratch.numel() < need:
+                self.head_scratch = torch.zeros(need, dtype=torch.uint8, device=self.device)
+        if self.tc:
+            self._tc_prepare(B)
+        torch.cuda.synchronize()
 
     def emb_link(self, sp: SparseInput):
         """Thread this batch's (table,row) occurrences onto per-row lists.  Indices only: may be
@@ -362,7 +429,10 @@ class Engine:
         layer and (if dx is given) the gradient w.r.t. the stack input, times in_act'(x_in)."""
         ln = self.ln_bot if which == "bot" else self.ln_top
         s = _stream()
-        for i in reversed(range(len(ln) - 1)):
+        nl = len(ln) - 1
+        if which == "top" and self.has_head:
+            nl -= 1  # the fused head already produced that layer's gradients
+        for i in reversed(range(nl)):
             K, N = ln[i], ln[i + 1]
             xin, ldxi = (x_in, ldx) if i == 0 else (acts[i - 1], act_ld[i - 1])
             _lib.check(self.lib.dlrm_b200_linear_wgrad(gz[i].data_ptr(), gz_ld[i], xin.data_ptr(), ldxi,
@@ -405,7 +475,10 @@ class Engine:
         FD = self.F * self.D
         if self.tc:
             return self._tc_backward(X, sp, target)
-        self.loss_and_grad(target, B)
+        if self.has_head:
+            self._head(B, target, True)   # p, loss, gz, dW/db of the last layer, gz of the layer below
+        else:
+            self.loss_and_grad(target, B)
         top_ld = [t.shape[1] for t in self.top_act]
         xin, ldx = self._top_in()
         bot_last_act = self._act("bot", len(self.ln_bot) - 2)
@@ -450,9 +523,7 @@ class Engine:
         """forward + loss + backward + optimizer.step().  Returns the loss (1-element device
         tensor, not synchronised)."""
         self.ensure_optimizer_state(optimizer)
-        if not link_done and self.T:
-            self.emb_link(sp)
-        self.forward(X, sp)
+        self.forward(X, sp, link=not link_done, skip_head=True)
         self.backward(X, sp, target)
         self.opt_step += 1
         clr = lr / (1.0 + (self.opt_step - 1.0) * lr_decay) if optimizer == "rwsadagrad" else lr
@@ -620,15 +691,20 @@ class Engine:
             self._dense_update_pack(-1, 0.0)
             self._pack_dirty = False
 
-    def _tc_mlp_forward(self, which: str, B: int):
+    def _tc_mlp_forward(self, which: str, B: int, skip_head: bool = False):
         ln = self.ln_bot if which == "bot" else self.ln_top
         s = _stream()
         ntc = self.ntc[which]
         for i in range(ntc):
             self.tc_plans["fwd"][(which, i)].run(s)
             self.n_launch += 1
-        # fp32 CUDA-core suffix (e.g. the final 256 -> 1 layer)
-        for i in range(ntc, len(ln) - 1):
+        nl = len(ln) - 1
+        if which == "top" and self.has_head:
+            nl -= 1
+            if not skip_head:
+                self._head(B, None, False)
+        # fp32 CUDA-core suffix (layers narrower than 16 outputs)
+        for i in range(ntc, nl):
             K, N = ln[i], ln[i + 1]
             x = self.top_act[i - 1]
             _lib.check(self.lib.dlrm_b200_linear_fwd(x.data_ptr(), x.shape[1], self.W[which][i].data_ptr(), K,
@@ -637,7 +713,7 @@ class Engine:
                                                      GEMM_SIMT_FP32, s), "linear_fwd")
             self.n_launch += 1
 
-    def _tc_forward(self, X: torch.Tensor, sp: SparseInput) -> torch.Tensor:
+    def _tc_forward(self, X: torch.Tensor, sp: SparseInput, link: bool = False, skip_head: bool = False) -> torch.Tensor:
         B = sp.batch
         self._tc_prepare(B)
         if self.ntc["bot"] == 0 or self.ntc["top"] == 0 or self.op != "dot":
@@ -649,14 +725,22 @@ class Engine:
             ev = self._gather_events
             if ev is not None:
                 ev[0].record()
-            self.emb_forward(sp, self.Tbuf.view(-1)[self.D:], FD, self.D)
+            self.emb_forward(sp, self.Tbuf.view(-1)[self.D:], FD, self.D, link)
             if ev is not None:
                 ev[1].record()
-        _lib.check(self.lib.dlrm_b200_interact_fwd(self.Tbuf.data_ptr(), FD, self.Rbuf.data_ptr(), self.ldr, B,
-                                                   self.F, self.D, int(self.itself), _stream()), "interact_fwd")
-        self.n_launch += 1
-        self._split(self.Rbuf, self.ldr, B, self.num_int, self.tc_in["top"][0])
-        self._tc_mlp_forward("top", B)
+        rh, rl, ldrb = self.tc_in["top"][0]
+        if self.D % 4 == 0:
+            # R goes straight to the (hi, lo) operand pair of the first top-MLP GEMM
+            _lib.check(self.lib.dlrm_b200_interact_fwd_ex(self.Tbuf.data_ptr(), FD, None, self.ldr, rh.data_ptr(),
+                                                          rl.data_ptr(), ldrb, B, self.F, self.D, int(self.itself),
+                                                          _stream()), "interact_fwd_ex")
+            self.n_launch += 1
+        else:
+            _lib.check(self.lib.dlrm_b200_interact_fwd(self.Tbuf.data_ptr(), FD, self.Rbuf.data_ptr(), self.ldr, B,
+                                                       self.F, self.D, int(self.itself), _stream()), "interact_fwd")
+            self.n_launch += 1
+            self._split(self.Rbuf, self.ldr, B, self.num_int, self.tc_in["top"][0])
+        self._tc_mlp_forward("top", B, skip_head)
         p = self.top_act[-1][:B]
         if 0.0 < self.loss_threshold < 1.0:
             return torch.clamp(p, self.loss_threshold, 1.0 - self.loss_threshold)
@@ -676,9 +760,15 @@ class Engine:
         B = sp.batch
         FD = self.F * self.D
         s = _stream()
-        self.loss_and_grad(target, B)
         nt, ntc = len(self.ln_top) - 1, self.ntc["top"]
         top_ld = [t.shape[1] for t in self.top_act]
+        head_to_tc = False
+        if self.has_head:
+            self._head(B, target, True)
+            head_to_tc = (nt - 2) < ntc   # head wrote the bf16 gradient pair of layer nt-2 directly
+            nt -= 1
+        else:
+            self.loss_and_grad(target, B)
         # fp32 suffix of the top MLP
         for i in reversed(range(ntc, nt)):
             K, N = self.ln_top[i], self.ln_top[i + 1]
@@ -693,15 +783,58 @@ class Engine:
                                                        self.top_gz[i - 1].data_ptr(), top_ld[i - 1], B, N, K,
                                                        GEMM_SIMT_FP32, s), "linear_dgrad")
             self.n_launch += 3
-        self._split(self.top_gz[ntc - 1], top_ld[ntc - 1], B, self.ln_top[ntc], self.tc_gz["top"][ntc - 1])
+        if not head_to_tc:
+            self._split(self.top_gz[ntc - 1], top_ld[ntc - 1], B, self.ln_top[ntc], self.tc_gz["top"][ntc - 1])
         self._tc_mlp_backward("top", B)
         bot_last_act = self._act("bot", len(self.ln_bot) - 2)
-        _lib.check(self.lib.dlrm_b200_interact_bwd(self.Tbuf.data_ptr(), FD, self.dR.data_ptr(), self.ldr,
-                                                   self.dT.data_ptr(), FD, B, self.F, self.D, int(self.itself),
-                                                   bot_last_act, s), "interact_bwd")
+        g0h, g0l, ldg0 = self.tc_gz["bot"][-1]
+        _lib.check(self.lib.dlrm_b200_interact_bwd_ex(self.Tbuf.data_ptr(), FD, self.dR.data_ptr(), self.ldr,
+                                                      self.dT.data_ptr(), FD, B, self.F, self.D, int(self.itself),
+                                                      bot_last_act, g0h.data_ptr(), g0l.data_ptr(), ldg0, s),
+                   "interact_bwd_ex")
         self.n_launch += 1
-        self._split(self.dT, FD, B, self.D, self.tc_gz["bot"][-1])
         self._tc_mlp_backward("bot", B)
+
+
+class GraphedTrainStep:
+    """One training step (forward, loss, backward, fused embedding + dense optimizer) captured
+    into a CUDA graph over a static packed device batch: per step the host issues one H2D (or D2D)
+    copy of the packed inputs and one graph launch instead of ~35 kernel launches.  The learning
+    rate is baked into the graph (re-capture to change it)."""
+
+    def __init__(self, eng: "Engine", stage, lr: float, optimizer: str = "rwsadagrad", warmup: int = 3,
+                 train: bool = True):
+        self.eng, self.stage, self.train = eng, stage, train
+        self.lr, self.optimizer = lr, optimizer
+        eng.ensure_optimizer_state(optimizer)
+        if warmup > 0:
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                for _ in range(warmup):   # allocates every lazily-created buffer / plan outside capture
+                    self._eager()
+            torch.cuda.current_stream().wait_stream(side)
+        else:
+            eng.prepare(stage.sparse, train)  # allocate lazily-created buffers without running a step
+        torch.cuda.synchronize()
+        n0 = eng.n_launch
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self.out = self._eager()
+        self.kernels_per_replay = eng.n_launch - n0
+
+    def _eager(self):
+        st = self.stage
+        if self.train:
+            return self.eng.train_step(st.X, st.sparse, st.target, self.lr, self.optimizer)
+        return self.eng.forward(st.X, st.sparse)
+
+    def replay(self):
+        self.graph.replay()
+        self.eng.n_launch += self.kernels_per_replay
+        if self.train:
+            self.eng.opt_step += 1
+        return self.out
 
 
 def sparse_from_reference(lS_o, lS_i, device) -> SparseInput:

@@ -97,6 +97,14 @@ typedef struct {
   int64_t pair_base;    /* first slot of this table in next[] / (sum of nnz of earlier tables) */
 } dlrm_emb_bwd_table_t;
 
+/* Training forward: the gather of dlrm_b200_emb_bag_fwd AND step 1 (link) in the same launch --
+ * the index of every occurrence is already in a register, so linking costs one atomicExch. */
+int dlrm_b200_emb_bag_fwd_train(const dlrm_emb_fwd_table_t* tables /*[host]*/,
+                                const dlrm_emb_bwd_table_t* train /*[host]*/, int num_tables, int dim,
+                                int64_t batch, int idx_bytes, int include_last, int32_t* next,
+                                float* out, int64_t out_stride_sample, int64_t out_stride_table,
+                                void* stream);
+
 int dlrm_b200_emb_bwd_link(const dlrm_emb_bwd_table_t* tables /*[host]*/, int num_tables,
                            int64_t batch, int idx_bytes, int include_last,
                            int32_t* next /*[total nnz]*/, void* stream);
@@ -138,6 +146,15 @@ int dlrm_b200_linear_wgrad(const float* dY, int64_t lddy, const float* X, int64_
  * ------------------------------------------------------------------------------------------ */
 int dlrm_b200_interact_fwd(const float* T, int64_t ldt, float* R, int64_t ldr, int64_t batch,
                            int num_features, int dim, int itself, void* stream);
+/* _ex variants: additionally emit the (hi, lo) bf16 operand pair consumed by the tcgen05 GEMMs
+ * (R for the first top-MLP layer; feature 0 of dT for the bottom MLP's backward).  R may be NULL
+ * when only the bf16 pair is wanted. */
+int dlrm_b200_interact_fwd_ex(const float* T, int64_t ldt, float* R, int64_t ldr, void* R_hi, void* R_lo,
+                              int64_t ld_rb, int64_t batch, int num_features, int dim, int itself,
+                              void* stream);
+int dlrm_b200_interact_bwd_ex(const float* T, int64_t ldt, const float* dR, int64_t lddr, float* dT,
+                              int64_t lddt, int64_t batch, int num_features, int dim, int itself,
+                              int mask_feature0, void* g0_hi, void* g0_lo, int64_t ld_g0, void* stream);
 int dlrm_b200_interact_bwd(const float* T, int64_t ldt, const float* dR, int64_t lddr,
                            float* dT, int64_t lddt, int64_t batch, int num_features, int dim,
                            int itself, int mask_feature0, void* stream);
@@ -159,6 +176,21 @@ int dlrm_b200_loss_fwd_bwd(const float* p, const float* target, const float* los
  *   SGD:        p -= lr * g
  *   RWSAdagrad dense branch (optim/rwsadagrad.py:145-148): s += g*g; p -= lr * g / (sqrt(s)+eps)
  * ------------------------------------------------------------------------------------------ */
+/* ------------------------------------------------------------------------------------------
+ * Fused head for a top MLP whose last layer has one output: Linear(K->1) + act + clamp + loss
+ * + d(loss) + wgrad/bias-grad/dgrad of that layer in ONE launch (see csrc/head.cu).
+ * target == NULL: inference (p only).  dW == NULL: loss (+ gz) only.  gprev (fp32) and/or
+ * gprev_hi/lo (bf16 pair) receive gz * w * act_prev'(h).  scratch: dlrm_b200_head_scratch_bytes()
+ * bytes, zero-initialised once.
+ * ------------------------------------------------------------------------------------------ */
+int64_t dlrm_b200_head_scratch_bytes(int64_t batch, int64_t K);
+int dlrm_b200_head_fused(const float* h, int64_t ldh, const float* w, const float* bias,
+                         const float* target, const float* loss_ws, int64_t batch, int64_t K,
+                         int act_last, int act_prev, int loss_kind, float loss_threshold,
+                         float* p, float* loss_out, float* gz, float* dW, float* db,
+                         float* gprev, int64_t ld_gprev, void* gprev_hi, void* gprev_lo,
+                         int64_t ld_gprev_bf16, void* scratch, void* stream);
+
 int dlrm_b200_dense_update(float* param, const float* grad, float* state /*NULL for SGD*/,
                            int64_t n, int optimizer, float lr, float eps, void* stream);
 

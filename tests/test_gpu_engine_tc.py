@@ -66,14 +66,17 @@ def test_tc_backward_vs_reference(name):
             nW, nb = ln[i + 1] * ln[i], ln[i + 1]
             dW = sum(e.dense_grad[s * P + oW:s * P + oW + nW] for s in range(ns)).view(ln[i + 1], ln[i])
             db = sum(e.dense_grad[s * P + ob:s * P + ob + nb] for s in range(ns))
-            np.testing.assert_allclose(dW.cpu().numpy(), g[f"g_{nm}W{i}"], rtol=1e-3, atol=1e-6)
-            np.testing.assert_allclose(db.cpu().numpy(), g[f"g_{nm}b{i}"], rtol=1e-3, atol=1e-6)
+            for got, want in ((dW, g[f"g_{nm}W{i}"]), (db, g[f"g_{nm}b{i}"])):
+                # bf16x3: error relative to the gradient scale of the tensor (sums of products)
+                sc = float(np.abs(want).max()) + 1e-12
+                assert np.abs(got.cpu().numpy() - want).max() <= 3e-5 * sc + 1e-9, (nm, i)
     dT = e.dT[:g.B].cpu().numpy()
     _, off, idx, _ = g.batch(0)
     for k in range(g.T):
         if g.has(f"g_emb{k}_rows"):
             rows, vals = O.coalesce(*O.sparse_grad(idx[k], off[k], dT[:, 1 + k, :]))
-            np.testing.assert_allclose(vals, g[f"g_emb{k}_vals"], rtol=1e-3, atol=1e-6)
+            sc = float(np.abs(g[f"g_emb{k}_vals"]).max()) + 1e-12
+            assert np.abs(vals - g[f"g_emb{k}_vals"]).max() <= 3e-5 * sc + 1e-9
 
 
 @pytest.mark.parametrize("opt", ["sgd", "rwsadagrad"])
@@ -95,3 +98,39 @@ def test_tc_train_steps_vs_reference(name, opt):
         for i in range(len(e.W[nm])):
             _robust_close(e.b[nm][i].cpu().numpy(), g[f"{opt}_{nm}b{i}"], 2e-6 if tight else 2e-5,
                           2e-5 if tight else 2.5 * lr, f"{nm}b{i}")
+
+
+@pytest.mark.parametrize("gemm", ["simt", "tc"])
+def test_cuda_graph_step_equals_eager(gemm):
+    """GraphedTrainStep (packed static batch, whole step in one CUDA graph) == eager train_step."""
+    from dlrm_b200.data import DeviceBatch, make_batch
+    from dlrm_b200.engine import Engine, GraphedTrainStep
+
+    rng = np.random.default_rng(3)
+    D, ln_emb, ln_bot = 128, [3000, 500, 40], [13, 64, 128]
+    ln_top = [D + 4 * 3 // 2, 64, 32, 1]
+    B = 192
+    params = O.random_params(rng, D, ln_emb, ln_bot, ln_top)
+    hbs = [make_batch(np.random.default_rng(10 + i), ln_emb, B, 13, 10) for i in range(4)]
+    res = []
+    for mode in ("eager", "graph"):
+        e = Engine(D, ln_emb, ln_bot, ln_top, loss="bce", sigmoid_top=len(ln_top) - 2, device=DEV, max_batch=B,
+                   gemm=gemm)
+        e.load_params(params)
+        st = DeviceBatch(hbs[0].layout, DEV)
+        st.load(hbs[0], non_blocking=False)
+        losses = []
+        if mode == "graph":
+            gs = GraphedTrainStep(e, st, 0.01, "sgd", warmup=0)   # warmup=0: identical update count
+            # capture itself does not execute; replay for every batch
+            for hb in hbs:
+                st.load(hb, non_blocking=False)
+                losses.append(float(gs.replay().item()))
+        else:
+            for hb in hbs:
+                st.load(hb, non_blocking=False)
+                losses.append(float(e.train_step(st.X, st.sparse, st.target, 0.01, "sgd").item()))
+        res.append((losses, e.dense.clone(), e.tables.clone()))
+    np.testing.assert_allclose(res[0][0], res[1][0], rtol=0, atol=1e-6)
+    assert torch.allclose(res[0][1], res[1][1], rtol=0, atol=1e-6)
+    assert torch.allclose(res[0][2], res[1][2], rtol=0, atol=1e-6)
