@@ -108,83 +108,107 @@ __device__ __forceinline__ void st_pack(float* p, const Pack<W>& r) {
   }
 }
 
+// Occurrence-centric: a warp takes 32 consecutive index positions (all tables share one global
+// position space: reference format = per-table arrays + pair_base, packed format = one array),
+// reads index / link / head with coalesced + gathered loads, and processes the rows it owns with
+// up to PF weight rows AND their dY rows in flight.  The bag of an occurrence comes from link[],
+// so the offsets are not needed (packed format reads only the per-table bounds).
 template <int W, int NV, typename idx_t>
-__global__ void __launch_bounds__(256) emb_update_kernel(const __grid_constant__ EmbBwdParams P) {
-  const EmbBwdTable& tb = P.t[blockIdx.y];
-  const idx_t* __restrict__ idx = static_cast<const idx_t*>(tb.idx);
-  const idx_t* __restrict__ off = static_cast<const idx_t*>(tb.off);
+__global__ void __launch_bounds__(256, NV == 1 ? 3 : 1) emb_update_kernel(const __grid_constant__ EmbBwdParams P,
+                                                                          int num_tables, long long total_hint) {
+  __shared__ long long bound[DLRM_B200_MAX_TABLES_PER_CALL + 1];
+  if ((int)threadIdx.x <= num_tables) {
+    const int k = threadIdx.x;
+    long long v;
+    if (k < num_tables) {
+      v = P.include_last ? (long long)static_cast<const idx_t*>(P.t[k].off)[0] : P.t[k].pair_base;
+    } else {
+      v = P.include_last ? (long long)static_cast<const idx_t*>(P.t[num_tables - 1].off)[P.batch] : total_hint;
+    }
+    bound[k] = v;
+  }
+  __syncthreads();
   const int D = P.dim;
   const int lane = threadIdx.x & 31;
-  const long long b = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (b >= P.batch) return;
-  const long long start = off[b];
-  const long long end = bag_end2<idx_t>(off, b, P.batch, tb.nnz, P.include_last);
-  if (start >= end) return;
-  const float* dYk = P.dY + (long long)blockIdx.y * P.dy_stride_table;
-
+  const long long first = bound[0], total = bound[num_tables];
+  const long long warp0 = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const long long wstride = (long long)gridDim.x * (blockDim.x >> 5);
   bool col_ok[NV];
-  Pack<W> g_self[NV];
 #pragma unroll
-  for (int v = 0; v < NV; ++v) {
-    col_ok[v] = lane * W + v * 32 * W < D;
-    if (col_ok[v]) g_self[v] = ld_pack<W>(dYk + b * P.dy_stride_sample + lane * W + v * 32 * W);
-  }
+  for (int v = 0; v < NV; ++v) col_ok[v] = lane * W + v * 32 * W < D;
   const float inv_d = 1.0f / (float)D;
+  constexpr int PF = NV == 1 ? 4 : 1;
 
-  for (long long j0 = start; j0 < end; j0 += 32) {
-    const long long j = j0 + lane;
-    long long my_r = 0;
-    int my_head = 0, my_next = 0;
-    const long long my_pos = tb.pair_base + j;
-    if (j < end) {
-      my_r = idx[j];
-      my_head = tb.head[my_r];
-      my_next = P.link[my_pos].x;
+  for (long long base = first + warp0 * 32; base < total; base += wstride * 32) {
+    const long long pos = base + lane;
+    const bool valid = pos < total;
+    // table of this position: largest k with bound[k] <= pos (empty tables share a bound)
+    int k = 0;
+    {
+      int lo = 0, hi = num_tables - 1;
+      while (lo < hi) {
+        const int mid = (lo + hi + 1) >> 1;
+        if (bound[mid] <= pos) lo = mid; else hi = mid - 1;
+      }
+      k = lo;
     }
-    const unsigned owners_all = __ballot_sync(0xffffffffu, j < end && my_head == (int)(my_pos + 1));
-    const int n = (int)min(32LL, end - j0);
-    constexpr int PF = NV == 1 ? 4 : (NV == 2 ? 2 : 1);  // weight rows kept in flight per warp
-    for (int u0 = 0; u0 < n; u0 += PF) {
-      // issue the long-latency (HBM) weight-row and momentum reads of up to PF owned rows first
-      Pack<W> wpf[PF][NV];
+    long long my_r = 0;
+    int my_head = 0;
+    int2 my_link = make_int2(0, 0);
+    if (valid) {
+      const EmbBwdTable& tb = P.t[k];
+      my_r = static_cast<const idx_t*>(tb.idx)[pos - tb.pair_base];
+      my_link = P.link[pos];
+      my_head = tb.head[my_r];
+    }
+    const unsigned owners = __ballot_sync(0xffffffffu, valid && my_head == (int)(pos + 1));
+    for (int u0 = 0; u0 < 32; u0 += PF) {
+      if (((owners >> u0) & ((1u << PF) - 1u)) == 0u) continue;
+      Pack<W> wpf[PF][NV], gpf[PF][NV];
       float mpf[PF];
 #pragma unroll
       for (int u = 0; u < PF; ++u) {
         const int src = u0 + u;
-        const long long r = __shfl_sync(0xffffffffu, my_r, src & 31);
-        if (src < n && ((owners_all >> src) & 1u)) {
+        const long long r = __shfl_sync(0xffffffffu, my_r, src);
+        const int ku = __shfl_sync(0xffffffffu, k, src);
+        const int bag = __shfl_sync(0xffffffffu, my_link.y, src);
+        if ((owners >> src) & 1u) {
+          const EmbBwdTable& tb = P.t[ku];
           const float* wrow = tb.w + r * D;
+          const float* grow = P.dY + (long long)ku * P.dy_stride_table + (long long)bag * P.dy_stride_sample;
 #pragma unroll
           for (int v = 0; v < NV; ++v)
-            if (col_ok[v]) wpf[u][v] = ld_pack<W>(wrow + lane * W + v * 32 * W);
+            if (col_ok[v]) {
+              wpf[u][v] = ld_pack<W>(wrow + lane * W + v * 32 * W);
+              gpf[u][v] = ld_pack<W>(grow + lane * W + v * 32 * W);
+            }
           mpf[u] = (P.optimizer == DLRM_OPT_RWSADAGRAD) ? tb.mom[r] : 0.f;
         }
       }
 #pragma unroll
       for (int u = 0; u < PF; ++u) {
         const int src = u0 + u;
-        const long long r = __shfl_sync(0xffffffffu, my_r, src & 31);
-        int nxt = __shfl_sync(0xffffffffu, my_next, src & 31);
-        if (!(src < n && ((owners_all >> src) & 1u))) continue;
+        const long long r = __shfl_sync(0xffffffffu, my_r, src);
+        const int ku = __shfl_sync(0xffffffffu, k, src);
+        int nxt = __shfl_sync(0xffffffffu, my_link.x, src);
+        const int self_bag = __shfl_sync(0xffffffffu, my_link.y, src);
+        if (!((owners >> src) & 1u)) continue;
+        const EmbBwdTable& tb = P.t[ku];
         float* wrow = tb.w + r * D;
-        Pack<W> w[NV];
+        const float* dYk = P.dY + (long long)ku * P.dy_stride_table;
+        Pack<W> w[NV], g[NV];
 #pragma unroll
-        for (int v = 0; v < NV; ++v) w[v] = wpf[u][v];
+        for (int v = 0; v < NV; ++v) { w[v] = wpf[u][v]; g[v] = gpf[u][v]; }
         const float m_old = mpf[u];
-
-        Pack<W> g[NV];
-        if (nxt == 0) {
-#pragma unroll
-          for (int v = 0; v < NV; ++v) g[v] = g_self[v];
-        } else {
+        if (nxt != 0) {
           // duplicates: gather members (self first), in chunks of 32, sorted by position
 #pragma unroll
           for (int v = 0; v < NV; ++v)
 #pragma unroll
             for (int e = 0; e < W; ++e) g[v].x[e] = 0.f;
           int cnt = 1;
-          int mpos = (lane == 0) ? (int)(tb.pair_base + j0 + src) : 0x7fffffff;
-          int mbag = (int)b;
+          int mpos = (lane == 0) ? (int)(base + src) : 0x7fffffff;
+          int mbag = self_bag;
           while (true) {
             if (nxt != 0 && cnt < 32) {
               const int2 e = P.link[nxt - 1];
@@ -193,8 +217,7 @@ __global__ void __launch_bounds__(256) emb_update_kernel(const __grid_constant__
               nxt = e.x;
               if (nxt != 0 && cnt < 32) continue;
             }
-            // rank of my member among the chunk (positions are unique)
-            int rank = 0;
+            int rank = 0;  // positions are unique -> ranks are a permutation
             for (int i = 0; i < cnt; ++i) rank += (__shfl_sync(0xffffffffu, mpos, i) < mpos) ? 1 : 0;
             for (int q = 0; q < cnt; ++q) {
               const unsigned who = __ballot_sync(0xffffffffu, lane < cnt && rank == q);
@@ -213,7 +236,6 @@ __global__ void __launch_bounds__(256) emb_update_kernel(const __grid_constant__
             mpos = 0x7fffffff;
           }
         }
-
         if (P.optimizer == DLRM_OPT_RWSADAGRAD) {
           float sq = 0.f;
 #pragma unroll
@@ -330,14 +352,29 @@ extern "C" int dlrm_b200_emb_bwd_update(const dlrm_emb_bwd_table_t* tables, int 
   P.lr = lr;
   P.eps = eps;
   const int block = 256;
-  dim3 grid((unsigned)((batch + (block / 32) - 1) / (block / 32)), (unsigned)num_tables);
+  long long total = 0;
+  for (int k = 0; k < num_tables; ++k) total += tables[k].nnz;   // reference format: exact; packed: capacity
+  if (include_last) {
+    total = 0;
+    for (int k = 0; k < num_tables; ++k) total = tables[k].nnz > total ? tables[k].nnz : total;
+  }
+  if (total == 0) return 0;
+  int dev = 0, sms = 0;
+  DLRM_CUDA(cudaGetDevice(&dev));
+  DLRM_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  long long gridx = (total / 32 + block / 32) / (block / 32);
+  if (gridx > (long long)sms * 3) gridx = (long long)sms * 3;
+  if (gridx < 1) gridx = 1;
+  const long long total_hint = include_last ? 0 : (tables[num_tables - 1].pair_base + tables[num_tables - 1].nnz);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-#define UPD(Wd, NV)                                                                    \
-  do {                                                                                 \
-    if (idx_bytes == 8) emb_update_kernel<Wd, NV, long long><<<grid, block, 0, st>>>(P); \
-    else emb_update_kernel<Wd, NV, int><<<grid, block, 0, st>>>(P);                     \
-    DLRM_CHECK_LAUNCH("emb_update_kernel");                                            \
-    return 0;                                                                          \
+#define UPD(Wd, NV)                                                                                        \
+  do {                                                                                                     \
+    if (idx_bytes == 8)                                                                                    \
+      emb_update_kernel<Wd, NV, long long><<<(unsigned)gridx, block, 0, st>>>(P, num_tables, total_hint);  \
+    else                                                                                                   \
+      emb_update_kernel<Wd, NV, int><<<(unsigned)gridx, block, 0, st>>>(P, num_tables, total_hint);        \
+    DLRM_CHECK_LAUNCH("emb_update_kernel");                                                                \
+    return 0;                                                                                              \
   } while (0)
   if (vec) {
     if (dim <= 128) UPD(4, 1);

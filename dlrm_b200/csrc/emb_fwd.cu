@@ -50,105 +50,118 @@ __device__ __forceinline__ long long bag_end(const idx_t* off, long long b, long
   return (include_last || b + 1 < batch) ? (long long)off[b + 1] : nnz;
 }
 
-// G lanes per bag, NV float4 per lane (dim = 4*G*NV when exact; columns >= dim are masked)
+// G lanes per bag, NV float4 per lane (dim = 4*G*NV when exact; columns >= dim are masked).
+// Persistent: the grid is sized to one resident wave (SMs x blocks/SM) and every lane group strides
+// over work items of S consecutive bags, so there is no partial second wave of CTAs.
 template <int G, int NV, int U, typename idx_t, bool WEIGHTED, bool LINK>
-__global__ void __launch_bounds__(256, (G == 32 && NV == 1) ? 4 : 1) emb_fwd_vec_kernel(const __grid_constant__ EmbFwdParams P) {
-  const EmbFwdTable& tb = P.t[blockIdx.y];
-  const idx_t* __restrict__ idx = static_cast<const idx_t*>(tb.idx);
-  const idx_t* __restrict__ off = static_cast<const idx_t*>(tb.off);
-  const float* __restrict__ W = tb.w;
+__global__ void __launch_bounds__(256, (G == 32 && NV == 1) ? 3 : 1) emb_fwd_vec_kernel(
+    const __grid_constant__ EmbFwdParams P, int num_tables) {
   const int D = P.dim;
   constexpr int GROUPS_PER_WARP = 32 / G;
   const int lane = threadIdx.x & 31;
   const int gl = lane % G;   // lane inside the group
   const int grp = lane / G;  // group inside the warp
   const unsigned gmask = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << (grp * G));
-  const long long group_id =
-      ((long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * GROUPS_PER_WARP + grp;
   const int S = P.bags_per_group;
-  const long long b0 = group_id * S;
-  if (b0 >= P.batch) return;
-  const int nb = (int)min((long long)S, P.batch - b0);
+  const long long items_per_table = (P.batch + S - 1) / S;
+  const long long total_items = items_per_table * num_tables;
+  const long long group0 =
+      ((long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * GROUPS_PER_WARP + grp;
+  const long long group_stride = (long long)gridDim.x * (blockDim.x >> 5) * GROUPS_PER_WARP;
 
-  // bag boundaries of this group's run of bags: one coalesced load, then shuffles.
-  // (S <= G is enforced by the host so lane gl can hold boundary gl.)
-  // positions inside one call fit 31 bits (host-checked: nnz < 2^31); rows stay 64-bit
-  int my_bound = 0;
-  if (gl <= nb) {
-    const long long b = b0 + gl;
-    my_bound = (b < P.batch) ? (int)off[b] : 0;
-    if (gl == nb) my_bound = (int)bag_end<idx_t>(off, b - 1, P.batch, tb.nnz, P.include_last);
-  }
-  int start = __shfl_sync(gmask, my_bound, 0, G);
-  int end = __shfl_sync(gmask, my_bound, 1, G);
-  // first index chunk of bag 0
-  long long my_row = (start + gl < end) ? (long long)idx[start + gl] : 0;
-  if (LINK && start + gl < end) link_occurrence(tb, P.link, start + gl, my_row, b0);
+  for (long long item = group0; item < total_items; item += group_stride) {
+    const int table = (int)(item / items_per_table);
+    const EmbFwdTable& tb = P.t[table];
+    const idx_t* __restrict__ idx = static_cast<const idx_t*>(tb.idx);
+    const idx_t* __restrict__ off = static_cast<const idx_t*>(tb.off);
+    const float* __restrict__ W = tb.w;
+    const long long b0 = (item - (long long)table * items_per_table) * S;
+    const int nb = (int)min((long long)S, P.batch - b0);
 
-  for (int s = 0; s < nb; ++s) {
-    // prefetch boundaries + first index chunk of the next bag
-    int nstart = 0, nend = 0;
-    long long next_row = 0;
-    if (s + 1 < nb) {
-      nstart = end;
-      nend = __shfl_sync(gmask, my_bound, s + 2, G);
-      next_row = (nstart + gl < nend) ? (long long)idx[nstart + gl] : 0;
-      if (LINK && nstart + gl < nend) link_occurrence(tb, P.link, nstart + gl, next_row, b0 + s + 1);
+    // bag boundaries of this run of bags: one coalesced load, then shuffles (S < G, host-enforced).
+    // positions inside one call fit 31 bits (host-checked: nnz < 2^31); rows stay 64-bit
+    int my_bound = 0;
+    if (gl <= nb) {
+      const long long b = b0 + gl;
+      my_bound = (b < P.batch) ? (int)off[b] : 0;
+      if (gl == nb) my_bound = (int)bag_end<idx_t>(off, b - 1, P.batch, tb.nnz, P.include_last);
     }
-    float4 acc[NV];
-#pragma unroll
-    for (int v = 0; v < NV; ++v) acc[v] = make_float4(0.f, 0.f, 0.f, 0.f);
+    int start = __shfl_sync(gmask, my_bound, 0, G);
+    int end = __shfl_sync(gmask, my_bound, 1, G);
+    // first index chunk of bag 0 (+ fused link: the atomic's result is only stored after the rows)
+    long long my_row = (start + gl < end) ? (long long)idx[start + gl] : 0;
+    int my_prev = 0;
+    if (LINK && start + gl < end) my_prev = atomicExch(tb.head + my_row, (int)(tb.pair_base + start + gl + 1));
 
-    for (int j0 = start; j0 < end; j0 += G) {
-      if (j0 != start) {
-        my_row = (j0 + gl < end) ? (long long)idx[j0 + gl] : 0;
-        if (LINK && j0 + gl < end) link_occurrence(tb, P.link, j0 + gl, my_row, b0 + s);
+    for (int s = 0; s < nb; ++s) {
+      // prefetch boundaries + first index chunk of the next bag
+      int nstart = 0, nend = 0, next_prev = 0;
+      long long next_row = 0;
+      if (s + 1 < nb) {
+        nstart = end;
+        nend = __shfl_sync(gmask, my_bound, s + 2, G);
+        next_row = (nstart + gl < nend) ? (long long)idx[nstart + gl] : 0;
+        if (LINK && nstart + gl < nend)
+          next_prev = atomicExch(tb.head + next_row, (int)(tb.pair_base + nstart + gl + 1));
       }
-      const int n = min(G, end - j0);
-      for (int jj = 0; jj < n; jj += U) {
-        float4 val[U][NV];
-        float wgt[U];
+      float4 acc[NV];
 #pragma unroll
-        for (int u = 0; u < U; ++u) {
-          const long long r = __shfl_sync(gmask, my_row, jj + u, G);  // jj+u < G always (U | G or guarded)
-          if (jj + u < n) {
-            const float* rp = W + r * D + gl * 4;
-#pragma unroll
-            for (int v = 0; v < NV; ++v) {
-              if (gl * 4 + v * G * 4 < D) val[u][v] = ldg_stream_f4(rp + v * G * 4);
-            }
-            if (WEIGHTED) wgt[u] = __ldg(tb.rw + r);
-          }
+      for (int v = 0; v < NV; ++v) acc[v] = make_float4(0.f, 0.f, 0.f, 0.f);
+
+      for (int j0 = start; j0 < end; j0 += G) {
+        if (j0 != start) {
+          my_row = (j0 + gl < end) ? (long long)idx[j0 + gl] : 0;
+          if (LINK && j0 + gl < end) my_prev = atomicExch(tb.head + my_row, (int)(tb.pair_base + j0 + gl + 1));
         }
+        const int n = min(G, end - j0);
+        for (int jj = 0; jj < n; jj += U) {
+          float4 val[U][NV];
+          float wgt[U];
 #pragma unroll
-        for (int u = 0; u < U; ++u) {
-          if (jj + u < n) {
+          for (int u = 0; u < U; ++u) {
+            const long long r = __shfl_sync(gmask, my_row, jj + u, G);  // jj+u < G always (U | G)
+            if (jj + u < n) {
+              const float* rp = W + r * D + gl * 4;
 #pragma unroll
-            for (int v = 0; v < NV; ++v) {
-              if (WEIGHTED) {
-                acc[v].x = fmaf(wgt[u], val[u][v].x, acc[v].x);
-                acc[v].y = fmaf(wgt[u], val[u][v].y, acc[v].y);
-                acc[v].z = fmaf(wgt[u], val[u][v].z, acc[v].z);
-                acc[v].w = fmaf(wgt[u], val[u][v].w, acc[v].w);
-              } else {
-                acc[v].x += val[u][v].x;
-                acc[v].y += val[u][v].y;
-                acc[v].z += val[u][v].z;
-                acc[v].w += val[u][v].w;
+              for (int v = 0; v < NV; ++v) {
+                if (gl * 4 + v * G * 4 < D) val[u][v] = ldg_stream_f4(rp + v * G * 4);
+              }
+              if (WEIGHTED) wgt[u] = __ldg(tb.rw + r);
+            }
+          }
+#pragma unroll
+          for (int u = 0; u < U; ++u) {
+            if (jj + u < n) {
+#pragma unroll
+              for (int v = 0; v < NV; ++v) {
+                if (WEIGHTED) {
+                  acc[v].x = fmaf(wgt[u], val[u][v].x, acc[v].x);
+                  acc[v].y = fmaf(wgt[u], val[u][v].y, acc[v].y);
+                  acc[v].z = fmaf(wgt[u], val[u][v].z, acc[v].z);
+                  acc[v].w = fmaf(wgt[u], val[u][v].w, acc[v].w);
+                } else {
+                  acc[v].x += val[u][v].x;
+                  acc[v].y += val[u][v].y;
+                  acc[v].z += val[u][v].z;
+                  acc[v].w += val[u][v].w;
+                }
               }
             }
           }
         }
+        if (LINK && j0 + gl < end)
+          P.link[tb.pair_base + j0 + gl] = make_int2(my_prev, (int)(b0 + s));
       }
-    }
-    float* op = P.out + (b0 + s) * P.stride_sample + (long long)blockIdx.y * P.stride_table + gl * 4;
+      float* op = P.out + (b0 + s) * P.stride_sample + (long long)table * P.stride_table + gl * 4;
 #pragma unroll
-    for (int v = 0; v < NV; ++v) {
-      if (gl * 4 + v * G * 4 < D) *reinterpret_cast<float4*>(op + v * G * 4) = acc[v];
+      for (int v = 0; v < NV; ++v) {
+        if (gl * 4 + v * G * 4 < D) *reinterpret_cast<float4*>(op + v * G * 4) = acc[v];
+      }
+      start = nstart;
+      end = nend;
+      my_row = next_row;
+      my_prev = next_prev;
     }
-    start = nstart;
-    end = nend;
-    my_row = next_row;
   }
 }
 
@@ -178,10 +191,20 @@ __global__ void emb_fwd_scalar_kernel(const __grid_constant__ EmbFwdParams P) {
 template <int G, int NV, int U, typename idx_t, bool WEIGHTED, bool LINK>
 static int launch_vec(const EmbFwdParams& P, int num_tables, cudaStream_t st) {
   const int block = 256;
+  static int resident = 0;  // CTAs in one full wave on this device, for this instantiation
+  if (!resident) {
+    int dev = 0, sms = 0, per_sm = 0;
+    DLRM_CUDA(cudaGetDevice(&dev));
+    DLRM_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    DLRM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(
+        &per_sm, emb_fwd_vec_kernel<G, NV, U, idx_t, WEIGHTED, LINK>, block, 0));
+    resident = sms * (per_sm > 0 ? per_sm : 1);
+  }
   const long long groups_per_block = (long long)(block / 32) * (32 / G);
-  const long long groups = (P.batch + P.bags_per_group - 1) / P.bags_per_group;
-  dim3 grid((unsigned)((groups + groups_per_block - 1) / groups_per_block), (unsigned)num_tables);
-  emb_fwd_vec_kernel<G, NV, U, idx_t, WEIGHTED, LINK><<<grid, block, 0, st>>>(P);
+  const long long items = ((P.batch + P.bags_per_group - 1) / P.bags_per_group) * num_tables;
+  long long grid = (items + groups_per_block - 1) / groups_per_block;
+  if (grid > resident) grid = resident;
+  emb_fwd_vec_kernel<G, NV, U, idx_t, WEIGHTED, LINK><<<(unsigned)grid, block, 0, st>>>(P, num_tables);
   DLRM_CHECK_LAUNCH("emb_fwd_vec_kernel");
   return 0;
 }
@@ -193,7 +216,7 @@ static int dispatch(const EmbFwdParams& Pin, int num_tables, bool vec_ok, cudaSt
   if (vec_ok) {
     const int u8 = get_tunable(TUNE_EMB_UNROLL) != 4;
     int S = get_tunable(TUNE_EMB_BAGS_PER_GROUP);
-    if (S <= 0) S = 8;  // measured on B200 (profiles/): 8 bags per group, 8 rows in flight
+    if (S <= 0) S = 4;  // bags per work item of the persistent loop
 #define VEC(G, NV)                                                                   \
   do {                                                                               \
     P.bags_per_group = S < (G) ? S : (G)-1;                                          \

@@ -269,16 +269,40 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
       for (int j = 0; j < 32; ++j) v[j] = apply_act_tc(__uint_as_float(r[j]), g.act);
       const bool full = nb + 32 <= g.N;
       if (g.mask_act != DLRM_ACT_NONE && m_ok) {
+        if (full && (g.ldmask & 7) == 0) {
+          // 32 bf16 of this row = 4 x 16-byte loads (hi), + 4 (lo) for sigmoid'
+          __align__(16) __nv_bfloat16 yh[32], yl[32];
+          const uint4* ph = reinterpret_cast<const uint4*>(g.mask_hi + m * g.ldmask + nb);
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          if (full || nb + j < g.N) {
-            const long long o = m * g.ldmask + nb + j;
-            float y = __bfloat162float(g.mask_hi[o]);
-            if (g.mask_act == DLRM_ACT_RELU) {
-              v[j] = y > 0.f ? v[j] : 0.f;
-            } else {
-              if (g.mask_lo) y += __bfloat162float(g.mask_lo[o]);
+          for (int q = 0; q < 4; ++q) reinterpret_cast<uint4*>(yh)[q] = ph[q];
+          if (g.mask_act == DLRM_ACT_RELU) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = __bfloat162float(yh[j]) > 0.f ? v[j] : 0.f;
+          } else {
+            if (g.mask_lo) {
+              const uint4* pl = reinterpret_cast<const uint4*>(g.mask_lo + m * g.ldmask + nb);
+#pragma unroll
+              for (int q = 0; q < 4; ++q) reinterpret_cast<uint4*>(yl)[q] = pl[q];
+            }
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              float y = __bfloat162float(yh[j]);
+              if (g.mask_lo) y += __bfloat162float(yl[j]);
               v[j] *= (1.0f - y) * y;
+            }
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            if (full || nb + j < g.N) {
+              const long long o = m * g.ldmask + nb + j;
+              float y = __bfloat162float(g.mask_hi[o]);
+              if (g.mask_act == DLRM_ACT_RELU) {
+                v[j] = y > 0.f ? v[j] : 0.f;
+              } else {
+                if (g.mask_lo) y += __bfloat162float(g.mask_lo[o]);
+                v[j] *= (1.0f - y) * y;
+              }
             }
           }
         }

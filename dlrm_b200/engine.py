@@ -143,6 +143,11 @@ class Engine:
             self.loss_ws = torch.as_tensor(loss_ws, dtype=torch.float32, device=dev)
         self.opt_step = 0
         self.n_launch = 0            # kernels launched by this engine (bench: gpu_launches)
+        # side streams: the gather runs beside the bottom MLP, the weight-gradient GEMMs and the
+        # embedding update beside the dgrad chain (independent work; parallel branches in the graph)
+        self.multi_stream = True
+        self.s_emb = torch.cuda.Stream(device=self.device)
+        self.s_wg = torch.cuda.Stream(device=self.device)
         self._gather_events = None   # optional (start, end) CUDA events recorded around the gather
         self._alloc_activations(int(max_batch))
 
@@ -468,13 +473,14 @@ class Engine:
         self.n_launch += 1
         return self.loss_buf
 
-    def backward(self, X: torch.Tensor, sp: SparseInput, target: torch.Tensor):
+    def backward(self, X: torch.Tensor, sp: SparseInput, target: torch.Tensor, update=None):
         """Everything between the loss and the parameter gradients.  Leaves dense grads in
-        dense_grad and the per-bag embedding grads in dT[:, 1:, :]."""
+        dense_grad and the per-bag embedding grads in dT[:, 1:, :].  update=(optimizer, clr) also
+        applies the fused embedding update (on a side stream on the tensor-core path)."""
         B = sp.batch
         FD = self.F * self.D
         if self.tc:
-            return self._tc_backward(X, sp, target)
+            return self._tc_backward(X, sp, target, update)
         if self.has_head:
             self._head(B, target, True)   # p, loss, gz, dW/db of the last layer, gz of the layer below
         else:
@@ -524,11 +530,14 @@ class Engine:
         tensor, not synchronised)."""
         self.ensure_optimizer_state(optimizer)
         self.forward(X, sp, link=not link_done, skip_head=True)
-        self.backward(X, sp, target)
         self.opt_step += 1
         clr = lr / (1.0 + (self.opt_step - 1.0) * lr_decay) if optimizer == "rwsadagrad" else lr
-        if self.T:
-            self.emb_update(sp, self.dT.view(-1)[self.D:], self.F * self.D, self.D, optimizer, clr)
+        if self.tc:
+            self.backward(X, sp, target, update=(optimizer, clr))
+        else:
+            self.backward(X, sp, target)
+            if self.T:
+                self.emb_update(sp, self.dT.view(-1)[self.D:], self.F * self.D, self.D, optimizer, clr)
         if self.tc:
             self._dense_update_pack(_OPT[optimizer], clr)
         else:
@@ -543,6 +552,17 @@ class Engine:
     # activation / gradient / weight is kept as a (hi, lo) bf16 pair, activations carry a
     # constant-1 column and weights a bias column, so the bias add and the bias gradient come
     # out of the GEMMs themselves.
+    def _fork(self, side):
+        """side stream starts after everything enqueued so far on the current stream."""
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream())
+        side.wait_event(ev)
+
+    def _join(self, side):
+        ev = torch.cuda.Event()
+        ev.record(side)
+        torch.cuda.current_stream().wait_event(ev)
+
     def _tc_n(self, which: str) -> int:
         ln = self.ln_bot if which == "bot" else self.ln_top
         n = 0
@@ -719,9 +739,16 @@ class Engine:
         if self.ntc["bot"] == 0 or self.ntc["top"] == 0 or self.op != "dot":
             raise RuntimeError("gemm='tc' needs op='dot' and MLP layers of width >= 16; use gemm='simt'")
         FD = self.F * self.D
+        ms = self.multi_stream and self.T > 0
+        if ms:   # gather (+ link) beside the bottom MLP
+            self._fork(self.s_emb)
+            with torch.cuda.stream(self.s_emb):
+                self.emb_forward(sp, self.Tbuf.view(-1)[self.D:], FD, self.D, link)
         self._split(X, X.stride(0), B, self.ln_bot[0], self.tc_in["bot"][0])
         self._tc_mlp_forward("bot", B)
-        if self.T:
+        if ms:
+            self._join(self.s_emb)
+        elif self.T:
             ev = self._gather_events
             if ev is not None:
                 ev[0].record()
@@ -747,16 +774,22 @@ class Engine:
         return p
 
     def _tc_mlp_backward(self, which: str, B: int):
-        s = _stream()
+        """gz of the last tensor-core layer is ready on the current stream.  dgrads stay on it (the
+        critical chain); every wgrad only feeds the final dense update and goes to the side stream."""
         for i in reversed(range(self.ntc[which])):
-            self.tc_plans["wgrad"][(which, i)].run(s)
+            if self.multi_stream:
+                self._fork(self.s_wg)   # gz_i was produced by the previous launch on this stream
+                with torch.cuda.stream(self.s_wg):
+                    self.tc_plans["wgrad"][(which, i)].run(_stream())
+            else:
+                self.tc_plans["wgrad"][(which, i)].run(_stream())
             self.n_launch += 1
             pl = self.tc_plans["dgrad"].get((which, i))
             if pl is not None:
-                pl.run(s)
+                pl.run(_stream())
                 self.n_launch += 1
 
-    def _tc_backward(self, X: torch.Tensor, sp: SparseInput, target: torch.Tensor):
+    def _tc_backward(self, X: torch.Tensor, sp: SparseInput, target: torch.Tensor, update=None):
         B = sp.batch
         FD = self.F * self.D
         s = _stream()
@@ -793,7 +826,20 @@ class Engine:
                                                       bot_last_act, g0h.data_ptr(), g0l.data_ptr(), ldg0, s),
                    "interact_bwd_ex")
         self.n_launch += 1
+        if update is not None and self.T:
+            # fused coalesce + sparse optimizer beside the bottom-MLP backward
+            opt, clr = update
+            if self.multi_stream:
+                self._fork(self.s_emb)
+                with torch.cuda.stream(self.s_emb):
+                    self.emb_update(sp, self.dT.view(-1)[self.D:], FD, self.D, opt, clr)
+            else:
+                self.emb_update(sp, self.dT.view(-1)[self.D:], FD, self.D, opt, clr)
         self._tc_mlp_backward("bot", B)
+        if self.multi_stream:
+            self._join(self.s_wg)
+            if update is not None and self.T:
+                self._join(self.s_emb)
 
 
 class GraphedTrainStep:
