@@ -71,7 +71,31 @@ __global__ void __launch_bounds__(256) dense_update_kernel(float* __restrict__ p
   }
 }
 
+__global__ void __launch_bounds__(256) act_bwd_kernel(const float* __restrict__ gy,
+                                                      const float* __restrict__ y,
+                                                      float* __restrict__ gz, long long n, int act,
+                                                      float thr) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float g = gy[i];
+  const float yi = y[i];
+  if (thr > 0.f && thr < 1.f && !(yi >= thr && yi <= 1.0f - thr)) g = 0.f;  // clamp backward
+  if (act == DLRM_ACT_SIGMOID) g *= (1.0f - yi) * yi;
+  else if (act == DLRM_ACT_RELU) g = yi > 0.f ? g : 0.f;
+  gz[i] = g;
+}
+
 }  // namespace dlrm
+
+extern "C" int dlrm_b200_act_bwd(const float* gy, const float* y, float* gz, int64_t n, int act,
+                                 float clamp_threshold, void* stream) {
+  using namespace dlrm;
+  if (n <= 0) return 0;
+  if (!gy || !y || !gz) return set_error("act_bwd: NULL pointer");
+  act_bwd_kernel<<<(unsigned)((n + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(gy, y, gz, n, act, clamp_threshold);
+  DLRM_CHECK_LAUNCH("act_bwd_kernel");
+  return 0;
+}
 
 extern "C" int dlrm_b200_loss_fwd_bwd(const float* p, const float* target, const float* loss_ws,
                                       int64_t n, int loss_kind, float loss_threshold, int last_act,

@@ -47,6 +47,10 @@ __global__ void __launch_bounds__(256) dense_update_pack_kernel(const __grid_con
     const float* gp = is_b ? L.db : L.dW;
     float g = gp[o];
     for (int s = 1; s < L.nslabs; ++s) g += gp[o + s * L.slab_stride];  // fixed order: deterministic
+    if (P.optimizer == -2) {  // fold the slabs only (the caller all-reduces slab 0 next)
+      const_cast<float*>(gp)[o] = g;
+      continue;
+    }
     float* pp = is_b ? L.b : L.W;
     float p = pp[o];
     if (P.optimizer == DLRM_OPT_RWSADAGRAD) {
@@ -91,7 +95,8 @@ extern "C" int dlrm_b200_dense_update_pack(const dlrm_dense_layer_t* layers, int
   for (int i = 0; i < num_layers; ++i) {
     const dlrm_dense_layer_t& s = layers[i];
     if (!s.W || !s.b) return set_error("dense_update_pack: layer %d NULL master", i);
-    if (optimizer >= 0 && (!s.dW || !s.db)) return set_error("dense_update_pack: layer %d NULL grad", i);
+    if ((optimizer >= 0 || optimizer == -2) && (!s.dW || !s.db))
+      return set_error("dense_update_pack: layer %d NULL grad", i);
     if (optimizer == DLRM_OPT_RWSADAGRAD && (!s.sW || !s.sb))
       return set_error("dense_update_pack: layer %d NULL Adagrad state", i);
     DenseLayer& d = P.l[i];

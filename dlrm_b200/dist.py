@@ -1,0 +1,299 @@
+"""One-process-per-GPU DLRM: table-wise sharded embeddings + data-parallel MLPs.
+
+Replaces `DLRM_Net.distributed_forward` (dlrm_s_pytorch.py:528-585) and `extend_distributed.py`
+(`get_my_slice` :47-51, `get_split_lengths` :54-62, `alltoall` :541-576 and its autograd pair
+`All2All_Req/Wait` :389-486, DDP of the MLPs :1329-1336):
+
+  * tables are split into contiguous slices over the ranks exactly like `get_my_slice`;
+  * every rank pools ITS tables for the GLOBAL batch (one gather launch), the pooled vectors are
+    exchanged so that every rank ends up with ALL tables for ITS batch slice, inside the
+    interaction operand T (forward), and the per-bag gradients travel the opposite way (backward)
+    into the fused coalesce + row-wise-Adagrad update of the owning rank;
+  * the MLPs are replicated; their gradients are averaged with one NCCL all-reduce (DDP semantics:
+    mean over ranks of the local-mean-loss gradients; embedding gradients are NOT averaged -- the
+    reference's all-to-all backward simply routes them, `extend_distributed.py:467-486`).
+
+Exchange back ends
+  "nccl" : `all_to_all_single` on packed send/recv buffers (the reference's collective).
+  "p2p"  : the gather kernel stores each pooled row directly into the owner rank's T buffer
+           through peer-mapped memory (NVLink stores) and the update kernel reads the dY rows
+           from the peers' dT buffers -- no staging buffers, no separate collective.
+
+Launch: `torchrun --nproc-per-node N ...` (env RANK/LOCAL_RANK/WORLD_SIZE/MASTER_*).
+"""
+from __future__ import annotations
+
+import json
+import os
+import time
+from typing import List, Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+
+# ---------------------------------------------------------------------------- host-side layout logic
+def table_slices(n_tables: int, world: int) -> List[Tuple[int, int]]:
+    """Contiguous [start, end) table slice of every rank (extend_distributed.get_my_slice)."""
+    k, m = divmod(n_tables, world)
+    return [(r * k + min(r, m), (r + 1) * k + min(r + 1, m)) for r in range(world)]
+
+
+def a2a_splits(n_tables: int, world: int, rank: int, local_batch: int, dim: int):
+    """(send_splits, recv_splits) in ELEMENTS for the forward exchange of pooled vectors.
+
+    send buffer of rank r : [world][local_batch][T_r][dim]   (sample-major: block d goes to rank d)
+    recv buffer of rank r : [world][local_batch][T_s][dim]   (block s came from rank s)
+    The backward exchange uses the same numbers with the roles swapped."""
+    sl = table_slices(n_tables, world)
+    t_mine = sl[rank][1] - sl[rank][0]
+    send = [local_batch * t_mine * dim] * world
+    recv = [local_batch * (e - s) * dim for s, e in sl]
+    return send, recv
+
+
+def scatter_recv_into_T(recv: torch.Tensor, Tbuf: torch.Tensor, n_tables: int, world: int,
+                        local_batch: int, dim: int):
+    """recv [sum_s B*T_s*D] -> Tbuf[:B, 1 + start_s : 1 + end_s, :] for every source rank s."""
+    o = 0
+    for s, e in table_slices(n_tables, world):
+        n = local_batch * (e - s) * dim
+        if e > s:
+            Tbuf[:local_batch, 1 + s:1 + e, :].copy_(recv[o:o + n].view(local_batch, e - s, dim))
+        o += n
+
+
+def pack_dT_into_send(dT: torch.Tensor, gsend: torch.Tensor, n_tables: int, world: int,
+                      local_batch: int, dim: int):
+    """dT[:B, 1 + start_d : 1 + end_d, :] -> gsend block d (gradients of rank d's tables)."""
+    o = 0
+    for s, e in table_slices(n_tables, world):
+        n = local_batch * (e - s) * dim
+        if e > s:
+            gsend[o:o + n].view(local_batch, e - s, dim).copy_(dT[:local_batch, 1 + s:1 + e, :])
+        o += n
+
+
+def init_distributed(backend: Optional[str] = None):
+    """Process-group bring-up from the torchrun environment (extend_distributed.init_distributed)."""
+    if dist.is_initialized():
+        return dist.get_rank(), dist.get_world_size()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", str(rank)))
+    os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+    os.environ.setdefault("MASTER_PORT", "29500")
+    if backend is None:
+        backend = "nccl" if torch.cuda.is_available() else "gloo"
+    if backend == "nccl":
+        torch.cuda.set_device(local)
+        dist.init_process_group(backend, rank=rank, world_size=world, device_id=torch.device("cuda", local))
+    else:
+        dist.init_process_group(backend, rank=rank, world_size=world)
+    return rank, world
+
+
+# ---------------------------------------------------------------------------- the sharded engine
+class DistEngine:
+    def __init__(self, m_spa: int, ln_emb: Sequence[int], ln_bot: Sequence[int], ln_top: Sequence[int], *,
+                 local_batch: int, device=None, gemm: str = "tc", loss: str = "bce", exchange: str = "nccl",
+                 **kw):
+        from .engine import Engine
+
+        if gemm == "simt":
+            raise SystemExit("ERROR: dlrm_b200.dist runs on the tensor-core path (gemm='tc' or 'tc_bf16')")
+        self.rank, self.world = dist.get_rank(), dist.get_world_size()
+        self.Tg = len(ln_emb)
+        if self.Tg < self.world:
+            raise SystemExit("ERROR: only (%d) sparse features for (%d) devices, table partitions will fail"
+                             % (self.Tg, self.world))
+        self.D = int(m_spa)
+        self.B = int(local_batch)
+        self.Bg = self.B * self.world
+        self.slices = table_slices(self.Tg, self.world)
+        self.t0, self.t1 = self.slices[self.rank]
+        self.Tl = self.t1 - self.t0
+        self.exchange = exchange
+        if device is None:
+            device = "cuda:%d" % torch.cuda.current_device()
+        self.device = torch.device(device)
+        self.eng = Engine(m_spa, list(ln_emb[self.t0:self.t1]), ln_bot, ln_top, n_features=self.Tg + 1,
+                          loss=loss, device=device, max_batch=self.B, gemm=gemm,
+                          sigmoid_top=len(ln_top) - 2, **kw)
+        e = self.eng
+        f32 = torch.float32
+        self.send_splits, self.recv_splits = a2a_splits(self.Tg, self.world, self.rank, self.B, self.D)
+        self.send = torch.zeros(self.Bg * self.Tl * self.D, dtype=f32, device=self.device)
+        self.recv = torch.zeros(sum(self.recv_splits), dtype=f32, device=self.device)
+        self.gsend = torch.zeros(sum(self.recv_splits), dtype=f32, device=self.device)
+        self.grecv = torch.zeros(self.Bg * self.Tl * self.D, dtype=f32, device=self.device)
+        e.gather_fn, e.update_fn, e.dense_sync_fn = self._gather, self._update, self._dense_sync
+        self.a2a_bytes = 0
+
+    # -- forward: pool local tables for the global batch, exchange, land in T
+    def _gather(self, sp, link):
+        e = self.eng
+        e.emb_forward(sp, self.send, self.Tl * self.D, self.D, link)
+        dist.all_to_all_single(self.recv, self.send, self.recv_splits, self.send_splits)
+        scatter_recv_into_T(self.recv, e.Tbuf, self.Tg, self.world, self.B, self.D)
+
+    # -- backward: route per-bag gradients to the table owners, fused coalesce + optimizer there
+    def _update(self, sp, optimizer, clr):
+        e = self.eng
+        pack_dT_into_send(e.dT, self.gsend, self.Tg, self.world, self.B, self.D)
+        dist.all_to_all_single(self.grecv, self.gsend, self.send_splits, self.recv_splits)
+        e.emb_update(sp, self.grecv, self.Tl * self.D, self.D, optimizer, clr)
+
+    def _dense_sync(self):
+        dist.all_reduce(self.eng.dense_grad[:self.eng.dense_numel], op=dist.ReduceOp.AVG)
+
+    def sync_dense_params_from_rank0(self):
+        """DDP broadcasts rank 0's MLP weights at wrap time (SURVEY A: reference quirk)."""
+        dist.broadcast(self.eng.dense, src=0)
+        self.eng.mark_params_changed()
+
+    def forward(self, X_local, sp_global_local_tables):
+        return self.eng.forward(X_local, sp_global_local_tables)
+
+    def train_step(self, X_local, sp_global_local_tables, target_local, lr, optimizer="rwsadagrad"):
+        return self.eng.train_step(X_local, sp_global_local_tables, target_local, lr, optimizer)
+
+
+# ---------------------------------------------------------------------------- synthetic sharded batches
+def make_sharded_batch(step_seed: int, ln_emb: Sequence[int], rank: int, world: int, local_batch: int,
+                       m_den: int = 13, lmax: int = 10, pin: bool = True):
+    """Rank-local view of one GLOBAL synthetic batch: indices of the rank's tables for all
+    world*local_batch samples (packed format) + the rank's slice of dense features and targets.
+    Every table / slice has its own seed, so all ranks agree on the global batch."""
+    from .data import HostBatch, PackedLayout, fill_batch
+
+    t0, t1 = table_slices(len(ln_emb), world)[rank]
+    rows = list(ln_emb[t0:t1])
+    Bg = local_batch * world
+    cap = int(Bg * sum(min(int(r), lmax) for r in rows))
+    hb = HostBatch(PackedLayout(Bg, len(rows), m_den, cap), pin)
+    fill_batch(hb, np.random.default_rng([step_seed, 7, rank]), rows, lmax)
+    rng = np.random.default_rng([step_seed, 11])
+    Xg = rng.random((Bg, m_den), dtype=np.float32)
+    Tg = np.round(rng.random((Bg, 1), dtype=np.float32))
+    sl = slice(rank * local_batch, (rank + 1) * local_batch)
+    X = torch.from_numpy(Xg[sl].copy())
+    T = torch.from_numpy(Tg[sl].copy())
+    if pin and torch.cuda.is_available():
+        X, T = X.pin_memory(), T.pin_memory()
+    return hb, X, T
+
+
+# ---------------------------------------------------------------------------- bench entry (bench.py --gpus N)
+def bench_main(args, CFG, metric_name, config_dict, ClockSampler):
+    from .data import DeviceBatch
+
+    rank, world = init_distributed("nccl")
+    local = int(os.environ.get("LOCAL_RANK", str(rank)))
+    dev = "cuda:%d" % local
+    torch.cuda.set_device(local)
+    train = args.workload != "cfg1"
+    D, T, B = CFG["m_spa"], CFG["T"], CFG["B"]
+    ln_emb = [CFG["rows"]] * T
+    ln_top = [D + (T + 1) * T // 2] + CFG["top_tail"]
+    de = DistEngine(D, ln_emb, CFG["ln_bot"], ln_top, local_batch=B, device=dev, gemm=args.gemm,
+                    exchange=getattr(args, "exchange", "nccl"))
+    de.eng.init_params(100 + rank)
+    de.sync_dense_params_from_rank0()
+    de.eng.ensure_optimizer_state("rwsadagrad")
+    ring = []
+    for i in range(args.ring):
+        hb, X, Tt = make_sharded_batch(1000 + i, ln_emb, rank, world, B, 13, CFG["lmax"])
+        db = DeviceBatch(hb.layout, dev)
+        db.load(hb, non_blocking=False)
+        ring.append((hb, db, X, X.to(dev), Tt, Tt.to(dev)))
+    lr = 0.01
+
+    def step(i):
+        hb, db, Xh, Xd, Th, Td = ring[i % args.ring]
+        if train:
+            return de.train_step(Xd, db.sparse, Td, lr, "rwsadagrad")
+        return de.forward(Xd, db.sparse)
+
+    for w in range(args.warmup):
+        step(w)
+    torch.cuda.synchronize()
+    dist.barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.25)
+    dist.barrier()
+    torch.cuda.synchronize()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0 = time.time()
+    n0 = de.eng.n_launch
+    ev0.record()
+    for s in range(args.steps):
+        step(args.warmup + s)
+    ev1.record()
+    torch.cuda.synchronize()
+    dist.barrier()
+    t1 = time.time()
+    launches = de.eng.n_launch - n0
+    ms = torch.tensor([ev0.elapsed_time(ev1) / args.steps], device=dev)
+    dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms = float(ms.item())
+
+    # e2e: host batches (packed sparse part + dense slice) copied every step, loss read back
+    stage = DeviceBatch(ring[0][0].layout, dev)
+    Xs = torch.empty((B, 13), device=dev)
+    Ts = torch.empty((B, 1), device=dev)
+    loss_host = torch.zeros(1).pin_memory()
+    h2d = 0
+
+    def e2e_step(i):
+        nonlocal h2d
+        hb, db, Xh, Xd, Th, Td = ring[i % args.ring]
+        h2d += stage.load(hb)
+        Xs.copy_(Xh, non_blocking=True)
+        Ts.copy_(Th, non_blocking=True)
+        h2d += Xh.numel() * 4 + Th.numel() * 4
+        if train:
+            out = de.train_step(Xs, stage.sparse, Ts, lr, "rwsadagrad")
+        else:
+            out = de.forward(Xs, stage.sparse)
+        loss_host.copy_(out.view(-1)[:1], non_blocking=True)
+
+    for w in range(3):
+        e2e_step(w)
+    h2d = 0
+    torch.cuda.synchronize()
+    dist.barrier()
+    ev0.record()
+    for s in range(args.steps):
+        e2e_step(s)
+    ev1.record()
+    torch.cuda.synchronize()
+    dist.barrier()
+    ms2 = torch.tensor([ev0.elapsed_time(ev1) / args.steps], device=dev)
+    dist.all_reduce(ms2, op=dist.ReduceOp.MAX)
+    ms2 = float(ms2.item())
+    if rank == 0:
+        clocks = sampler.stop(t0, t1)
+        Bg = B * world
+        line = {
+            "metric": metric_name(train), "value": Bg / (ms * 1e-3), "unit": "samples/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None,
+            "dtype": {"simt": "fp32", "tc": "fp32 (bf16x3 split on tcgen05, fp32 accumulate)",
+                      "tc_bf16": "bf16"}[args.gemm],
+            "data": "synthetic", "config": config_dict(args, world),
+            "roofline": None, "cpu_baseline": None,
+            "e2e": {"value": Bg / (ms2 * 1e-3), "unit": "samples/s", "h2d_bytes_per_step": int(h2d / args.steps),
+                    "d2h_bytes_per_step": 4, "ms_per_step": ms2,
+                    "note": "per rank: packed pinned sparse batch (its tables, global batch) + dense slice, "
+                            "H2D every step, loss read back"},
+            "gpu_launches": int(launches), "exchange": de.exchange,
+            "a2a_bytes_per_rank_per_step": int(2 * 4 * (sum(de.send_splits) - de.send_splits[rank])),
+            "clocks": clocks,
+        }
+        print(json.dumps(line), flush=True)
+    dist.barrier()
+    dist.destroy_process_group()

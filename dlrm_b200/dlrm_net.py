@@ -65,11 +65,11 @@ class _DLRMForward(torch.autograd.Function):
     """sequential_forward as one autograd node (inputs: dense_x and every parameter)."""
 
     @staticmethod
-    def forward(ctx, net, sp, dense_x, *params):
+    def forward(ctx, net, sp, train, dense_x, *params):
         eng = net._engine
-        train = torch.is_grad_enabled() and any(p.requires_grad for p in params)
-        p = eng.forward(dense_x, sp, link=train and net._fused_opt is not None)
-        ctx.net, ctx.sp, ctx.x, ctx.nparams, ctx.linked = net, sp, dense_x, len(params), train and net._fused_opt is not None
+        linked = bool(train) and net._fused_opt is not None   # training forward: gather also links
+        p = eng.forward(dense_x, sp, link=linked)
+        ctx.net, ctx.sp, ctx.x, ctx.nparams, ctx.linked = net, sp, dense_x, len(params), linked
         return p.clone()
 
     @staticmethod
@@ -77,17 +77,15 @@ class _DLRMForward(torch.autograd.Function):
         net, eng = ctx.net, ctx.net._engine
         eng.backward_from_output_grad(ctx.x, ctx.sp, gp.contiguous())
         grads: List[Optional[torch.Tensor]] = []
-        T = eng.T
         if net._fused_opt is not None:
             net._pending = (ctx.sp, ctx.linked)          # consumed by the fused optimizer's step()
-            grads += [None] * T
-        else:
-            grads += net._materialise_sparse_grads(ctx.sp)
+            return (None, None, None, None) + (None,) * ctx.nparams
+        grads += net._materialise_sparse_grads(ctx.sp)
         for name in ("bot", "top"):
             for i in range(len(eng.W[name])):
                 grads.append(eng.reduced_dW(name, i))
                 grads.append(eng.reduced_db(name, i))
-        return (None, None, None) + tuple(grads)
+        return (None, None, None, None) + tuple(grads)
 
 
 class DLRM_Net(nn.Module):
@@ -152,7 +150,12 @@ class DLRM_Net(nn.Module):
             self.loss_fn = torch.nn.BCELoss(reduction="mean")
         else:
             self.loss_fn = torch.nn.BCELoss(reduction="none")
-        self._register_load_state_dict_post_hook(lambda m, k: m._engine.mark_params_changed())
+        self.register_load_state_dict_post_hook(lambda m, k: m._engine.mark_params_changed())
+        import weakref
+
+        ref = weakref.ref(self)
+        for p in self.parameters():
+            p._dlrm_net = ref
 
     # ------------------------------------------------------------------ construction
     def create_mlp(self, ln, sigmoid_layer):
@@ -247,7 +250,9 @@ class DLRM_Net(nn.Module):
         sp = self._sparse(lS_o, lS_i)
         x = dense_x.to(eng.device, dtype=torch.float32).contiguous()
         params = list(self.parameters())
-        return _DLRMForward.apply(self, sp, x, *params)
+        if self._fused_opt is None:
+            eng.mark_params_changed()   # a torch optimizer may have written the master weights
+        return _DLRMForward.apply(self, sp, torch.is_grad_enabled(), x, *params)
 
     def parallel_forward(self, dense_x, lS_o, lS_i):
         return self.forward(dense_x, lS_o, lS_i)

@@ -69,7 +69,7 @@ class Engine:
     def __init__(self, m_spa: int, ln_emb: Sequence[int], ln_bot: Sequence[int], ln_top: Sequence[int],
                  *, op: str = "dot", itself: bool = False, sigmoid_bot: int = -1, sigmoid_top: int = -1,
                  loss: str = "bce", loss_threshold: float = 0.0, loss_ws=None, device="cuda:0",
-                 max_batch: int = 2048, gemm: str = "simt", table_rows_local: Optional[Sequence[int]] = None):
+                 max_batch: int = 2048, gemm: str = "simt", n_features: Optional[int] = None):
         if not torch.cuda.is_available():
             raise RuntimeError("dlrm_b200.Engine needs a CUDA device (B200, sm_100a); there is no CPU path")
         self.device = torch.device(device)
@@ -80,8 +80,8 @@ class Engine:
         self.ln_emb = [int(v) for v in ln_emb]
         self.ln_bot = [int(v) for v in ln_bot]
         self.ln_top = [int(v) for v in ln_top]
-        self.T = len(self.ln_emb)
-        self.F = self.T + 1
+        self.T = len(self.ln_emb)                       # tables stored on THIS device
+        self.F = int(n_features) if n_features else self.T + 1   # interaction features (global)
         self.op, self.itself = op, bool(itself)
         if op not in ("dot", "cat"):
             raise ValueError("arch_interaction_op=%s is not supported" % op)
@@ -142,6 +142,10 @@ class Engine:
         if loss_ws is not None:
             self.loss_ws = torch.as_tensor(loss_ws, dtype=torch.float32, device=dev)
         self.opt_step = 0
+        # hooks replaced by dlrm_b200.dist for table-wise sharded runs
+        self.gather_fn = None       # (sp, link) -> fills Tbuf[:, 1:, :] for the LOCAL batch
+        self.update_fn = None       # (sp, optimizer, clr) -> embedding update from dT[:, 1:, :]
+        self.dense_sync_fn = None   # () -> make dense_grad slab 0 the cross-rank mean gradient
         self.n_launch = 0            # kernels launched by this engine (bench: gpu_launches)
         # side streams: the gather runs beside the bottom MLP, the weight-gradient GEMMs and the
         # embedding update beside the dgrad chain (independent work; parallel branches in the graph)
@@ -347,7 +351,7 @@ class Engine:
         engine buffer, valid until the next call); clamped iff 0 < loss_threshold < 1.
         link=True: training forward (gather also builds the per-row occurrence lists);
         skip_head=True: leave the final 1-output layer to the fused head in backward()."""
-        B = sp.batch
+        B = X.shape[0]   # MLP / interaction batch (== sp.batch except under table-wise sharding)
         if B > self.max_batch:
             self._alloc_activations(B)
         if self.tc:
@@ -377,10 +381,10 @@ class Engine:
             return torch.clamp(p, self.loss_threshold, 1.0 - self.loss_threshold)
         return p
 
-    def prepare(self, sp: SparseInput, train: bool = True):
+    def prepare(self, sp: SparseInput, train: bool = True, batch: Optional[int] = None):
         """Allocate every lazily-created buffer / tcgen05 plan for this batch shape (no kernels that
         change parameters): required before CUDA-graph capture."""
-        B = sp.batch
+        B = batch if batch is not None else sp.batch
         if B > self.max_batch:
             self._alloc_activations(B)
         if train and self.T:
@@ -435,7 +439,7 @@ class Engine:
         ln = self.ln_bot if which == "bot" else self.ln_top
         s = _stream()
         nl = len(ln) - 1
-        if which == "top" and self.has_head:
+        if which == "top" and self.has_head and not getattr(self, "_external_gz", False):
             nl -= 1  # the fused head already produced that layer's gradients
         for i in reversed(range(nl)):
             K, N = ln[i], ln[i + 1]
@@ -477,11 +481,14 @@ class Engine:
         """Everything between the loss and the parameter gradients.  Leaves dense grads in
         dense_grad and the per-bag embedding grads in dT[:, 1:, :].  update=(optimizer, clr) also
         applies the fused embedding update (on a side stream on the tensor-core path)."""
-        B = sp.batch
+        B = X.shape[0]
         FD = self.F * self.D
         if self.tc:
             return self._tc_backward(X, sp, target, update)
-        if self.has_head:
+        ext = getattr(self, "_external_gz", False)
+        if ext:
+            pass                          # top_gz[-1] was filled by backward_from_output_grad()
+        elif self.has_head:
             self._head(B, target, True)   # p, loss, gz, dW/db of the last layer, gz of the layer below
         else:
             self.loss_and_grad(target, B)
@@ -518,6 +525,56 @@ class Engine:
         gz_ld = [t.shape[1] for t in self.bot_gz] + [FD]
         self.mlp_backward("bot", X, X.stride(0), ACT_NONE, B, acts, lds, gz, gz_ld, None, 0)
 
+    # ---- entry points used by the DLRM_Net facade (dlrm_b200/dlrm_net.py)
+    def backward_from_output_grad(self, X: torch.Tensor, sp: SparseInput, gp: torch.Tensor):
+        """Backward pass started from dE/dp computed OUTSIDE (autograd of the module's output).
+        Leaves dense grads in dense_grad (slabs) and per-bag embedding grads in dT[:, 1:, :]."""
+        B = X.shape[0]
+        nt = len(self.ln_top) - 1
+        p = self.top_act[nt - 1]
+        n = B * p.shape[1]
+        _lib.check(self.lib.dlrm_b200_act_bwd(gp.data_ptr(), p.data_ptr(), self.top_gz[nt - 1].data_ptr(), n,
+                                              self._act("top", nt - 1), self.loss_threshold, _stream()), "act_bwd")
+        self.n_launch += 1
+        self._external_gz = True
+        try:
+            self.backward(X, sp, None)
+        finally:
+            self._external_gz = False
+
+    def reduced_dW(self, which: str, i: int) -> torch.Tensor:
+        """Weight gradient of layer i with the split-K slabs folded (a new tensor)."""
+        if not self.tc or i >= self.ntc[which]:
+            return self.dW[which][i].clone()
+        P, ns = self.dense_numel, self.tc_splits[(which, i)]
+        o = self._dense_off[(which, i, "W")]
+        n = self.dW[which][i].numel()
+        return sum(self.dense_grad[s * P + o:s * P + o + n] for s in range(ns)).view_as(self.dW[which][i])
+
+    def reduced_db(self, which: str, i: int) -> torch.Tensor:
+        if not self.tc or i >= self.ntc[which]:
+            return self.db[which][i].clone()
+        P, ns = self.dense_numel, self.tc_splits[(which, i)]
+        o = self._dense_off[(which, i, "b")]
+        n = self.db[which][i].numel()
+        return sum(self.dense_grad[s * P + o:s * P + o + n] for s in range(ns)).view_as(self.db[which][i])
+
+    def mlp_only(self, which: str, x: torch.Tensor) -> torch.Tensor:
+        """apply_mlp as a stand-alone call (fp32 CUDA-core kernels; no autograd)."""
+        ln = self.ln_bot if which == "bot" else self.ln_top
+        B = x.shape[0]
+        outs = [torch.empty((B, ln[i + 1]), dtype=torch.float32, device=self.device) for i in range(len(ln) - 1)]
+        self.mlp_forward(which, x, x.stride(0), B, outs, [o.shape[1] for o in outs])
+        return outs[-1]
+
+    def interact_only(self, B: int) -> torch.Tensor:
+        """interact_features on the current contents of Tbuf[:B]; returns R [B, num_int]."""
+        FD = self.F * self.D
+        _lib.check(self.lib.dlrm_b200_interact_fwd(self.Tbuf.data_ptr(), FD, self.Rbuf.data_ptr(), self.ldr, B,
+                                                   self.F, self.D, int(self.itself), _stream()), "interact_fwd")
+        self.n_launch += 1
+        return self.Rbuf[:B, :self.num_int]
+
     def dense_step(self, optimizer: str, lr: float, eps: float = 1e-10):
         _lib.check(self.lib.dlrm_b200_dense_update(self.dense.data_ptr(), self.dense_grad.data_ptr(),
                                                    _ptr(self.dense_state), self.dense_numel, _OPT[optimizer],
@@ -539,8 +596,15 @@ class Engine:
             if self.T:
                 self.emb_update(sp, self.dT.view(-1)[self.D:], self.F * self.D, self.D, optimizer, clr)
         if self.tc:
-            self._dense_update_pack(_OPT[optimizer], clr)
+            if self.dense_sync_fn is not None:
+                self._dense_update_pack(-2, 0.0)      # fold the split-K slabs into slab 0
+                self.dense_sync_fn()                  # cross-rank mean of the dense gradients
+                self._dense_update_pack(_OPT[optimizer], clr, single_slab=True)
+            else:
+                self._dense_update_pack(_OPT[optimizer], clr)
         else:
+            if self.dense_sync_fn is not None:
+                self.dense_sync_fn()
             self.dense_step(optimizer, clr)
         return self.loss_buf
 
@@ -672,8 +736,9 @@ class Engine:
                                                  _stream()), "split_bf16")
         self.n_launch += 1
 
-    def _dense_update_pack(self, opt_code: int, lr: float, eps: float = 1e-10):
-        """optimizer step on every dense layer + bf16 operand refresh; opt_code -1 = refresh only."""
+    def _dense_update_pack(self, opt_code: int, lr: float, eps: float = 1e-10, single_slab: bool = False):
+        """optimizer step on every dense layer + bf16 operand refresh; opt_code -1 = refresh only,
+        -2 = only fold the split-K gradient slabs into slab 0."""
         layers = []
         P = self.dense_numel
         for which in ("bot", "top"):
@@ -693,7 +758,7 @@ class Engine:
                 if i < self.ntc[which]:
                     wh, wl, Kp = self.tc_W[which][i]
                     d.pack_hi, d.pack_lo, d.ld_pack = wh.data_ptr(), wl.data_ptr(), Kp
-                    d.num_slabs = self.tc_splits[(which, i)] if opt_code >= 0 else 1
+                    d.num_slabs = self.tc_splits[(which, i)] if (opt_code >= 0 or opt_code == -2) and not single_slab else 1
                 else:
                     d.num_slabs = 1
                 layers.append(d)
@@ -734,20 +799,25 @@ class Engine:
             self.n_launch += 1
 
     def _tc_forward(self, X: torch.Tensor, sp: SparseInput, link: bool = False, skip_head: bool = False) -> torch.Tensor:
-        B = sp.batch
+        B = X.shape[0]
         self._tc_prepare(B)
         if self.ntc["bot"] == 0 or self.ntc["top"] == 0 or self.op != "dot":
             raise RuntimeError("gemm='tc' needs op='dot' and MLP layers of width >= 16; use gemm='simt'")
         FD = self.F * self.D
-        ms = self.multi_stream and self.T > 0
+        ms = self.multi_stream and (self.T > 0 or self.gather_fn is not None)
         if ms:   # gather (+ link) beside the bottom MLP
             self._fork(self.s_emb)
             with torch.cuda.stream(self.s_emb):
-                self.emb_forward(sp, self.Tbuf.view(-1)[self.D:], FD, self.D, link)
+                if self.gather_fn is not None:
+                    self.gather_fn(sp, link)
+                else:
+                    self.emb_forward(sp, self.Tbuf.view(-1)[self.D:], FD, self.D, link)
         self._split(X, X.stride(0), B, self.ln_bot[0], self.tc_in["bot"][0])
         self._tc_mlp_forward("bot", B)
         if ms:
             self._join(self.s_emb)
+        elif self.gather_fn is not None:
+            self.gather_fn(sp, link)
         elif self.T:
             ev = self._gather_events
             if ev is not None:
@@ -790,13 +860,15 @@ class Engine:
                 self.n_launch += 1
 
     def _tc_backward(self, X: torch.Tensor, sp: SparseInput, target: torch.Tensor, update=None):
-        B = sp.batch
+        B = X.shape[0]
         FD = self.F * self.D
         s = _stream()
         nt, ntc = len(self.ln_top) - 1, self.ntc["top"]
         top_ld = [t.shape[1] for t in self.top_act]
         head_to_tc = False
-        if self.has_head:
+        if getattr(self, "_external_gz", False):
+            pass                          # top_gz[nt-1] given; the fp32 suffix below handles layer nt-1
+        elif self.has_head:
             self._head(B, target, True)
             head_to_tc = (nt - 2) < ntc   # head wrote the bf16 gradient pair of layer nt-2 directly
             nt -= 1
@@ -826,19 +898,22 @@ class Engine:
                                                       bot_last_act, g0h.data_ptr(), g0l.data_ptr(), ldg0, s),
                    "interact_bwd_ex")
         self.n_launch += 1
-        if update is not None and self.T:
+        has_emb = self.T > 0 or self.update_fn is not None
+        if update is not None and has_emb:
             # fused coalesce + sparse optimizer beside the bottom-MLP backward
             opt, clr = update
+            upd = (lambda: self.update_fn(sp, opt, clr)) if self.update_fn is not None else \
+                (lambda: self.emb_update(sp, self.dT.view(-1)[self.D:], FD, self.D, opt, clr))
             if self.multi_stream:
                 self._fork(self.s_emb)
                 with torch.cuda.stream(self.s_emb):
-                    self.emb_update(sp, self.dT.view(-1)[self.D:], FD, self.D, opt, clr)
+                    upd()
             else:
-                self.emb_update(sp, self.dT.view(-1)[self.D:], FD, self.D, opt, clr)
+                upd()
         self._tc_mlp_backward("bot", B)
         if self.multi_stream:
             self._join(self.s_wg)
-            if update is not None and self.T:
+            if update is not None and has_emb:
                 self._join(self.s_emb)
 
 

@@ -171,6 +171,12 @@ int dlrm_b200_loss_fwd_bwd(const float* p, const float* target, const float* los
                            int64_t n, int loss_kind, float loss_threshold, int last_act,
                            float* loss_out, float* gz, float* scratch, void* stream);
 
+/* gz = gy * [thr <= y <= 1-thr] * act'(y): entry of the backward pass when the loss is computed
+ * OUTSIDE the library (autograd of DLRM_Net.forward: `E.backward()` hands us dE/d(clamped p)).
+ * clamp_threshold outside (0,1) disables the clamp mask. */
+int dlrm_b200_act_bwd(const float* gy, const float* y, float* gz, int64_t n, int act,
+                      float clamp_threshold, void* stream);
+
 /* ------------------------------------------------------------------------------------------
  * Dense parameters of optimizer.step(): flat arenas (all bot/top W and b, contiguous).
  *   SGD:        p -= lr * g
@@ -233,7 +239,8 @@ int dlrm_b200_split_bf16(const float* X, int64_t ldx, int64_t M, int64_t N, void
                          int64_t ld_out, void* stream);
 
 /* Dense optimizer step fused with the split-K slab reduction of dW/db and the refresh of the
- * [N, K+1] = [W | bias] (hi, lo) operand copies.  optimizer = DLRM_OPT_* or -1 (pack only). */
+ * [N, K+1] = [W | bias] (hi, lo) operand copies.  optimizer = DLRM_OPT_*, -1 (pack only) or
+ * -2 (only fold the slabs into slab 0, for a cross-rank all-reduce before the update). */
 typedef struct {
   float* W; float* b; float* sW; float* sb;
   const float* dW; const float* db;

@@ -3,7 +3,7 @@
 mkdir -p gpurun_out
 T=${1:-r3}
 (timeout 300 python tests/gemm_tc_check.py gpurun_out/${T}_gemm_tc_report.txt 2>&1 | tail -5) > gpurun_out/${T}_gemm_tc.log
-(timeout 900 python -m pytest tests -q -m gpu -x 2>&1 | tail -40) > gpurun_out/${T}_pytest.log
+(timeout 900 python -m pytest tests -q -m gpu 2>&1 | tail -60) > gpurun_out/${T}_pytest.log
 (timeout 300 python __graft_entry__.py smoke 2>&1 | tail -5) > gpurun_out/${T}_smoke.log
 (timeout 300 python tools/sweep_gather.py gpurun_out/${T}_sweep.json 2>&1 | tail -30) > gpurun_out/${T}_sweep.log
 (timeout 400 python bench.py --steps 200 --warmup 20 --gemm tc --cpu-budget 10 2>&1 | tail -2) > gpurun_out/${T}_bench_tc.log
