@@ -55,6 +55,7 @@ SYMBOLS = [
     "dlrm_b200_emb_bag_fwd", "dlrm_b200_emb_bag_fwd_train", "dlrm_b200_emb_bwd_link",
     "dlrm_b200_emb_bwd_update", "dlrm_b200_head_scratch_bytes", "dlrm_b200_head_fused",
     "dlrm_b200_interact_fwd_ex", "dlrm_b200_interact_bwd_ex", "dlrm_b200_act_bwd",
+    "dlrm_b200_emb_bag_fwd_p2p", "dlrm_b200_emb_bwd_update_p2p",
     "dlrm_b200_linear_fwd", "dlrm_b200_linear_dgrad", "dlrm_b200_linear_wgrad",
     "dlrm_b200_interact_fwd", "dlrm_b200_interact_bwd", "dlrm_b200_loss_fwd_bwd",
     "dlrm_b200_dense_update",
@@ -77,6 +78,10 @@ def _declare(lib):
                                          vp, i64, vp, vp, i64, vp, vp]
     lib.dlrm_b200_interact_fwd_ex.argtypes = [vp, i64, vp, i64, vp, vp, i64, i64, i32, i32, i32, vp]
     lib.dlrm_b200_interact_bwd_ex.argtypes = [vp, i64, vp, i64, vp, i64, i64, i32, i32, i32, i32, vp, vp, i64, vp]
+    lib.dlrm_b200_emb_bag_fwd_p2p.argtypes = [C.POINTER(EmbFwdTable), C.POINTER(EmbBwdTable), i32, i32, i64, i32, i32,
+                                              vp, C.POINTER(vp), i32, i64, i64, i64, vp]
+    lib.dlrm_b200_emb_bwd_update_p2p.argtypes = [C.POINTER(EmbBwdTable), i32, i32, i64, i32, i32, vp, C.POINTER(vp),
+                                                 i32, i64, i64, i64, i32, f32, f32, vp]
     lib.dlrm_b200_act_bwd.argtypes = [vp, vp, vp, i64, i32, f32, vp]
     lib.dlrm_b200_emb_bwd_link.argtypes = [C.POINTER(EmbBwdTable), i32, i64, i32, i32, vp, vp]
     lib.dlrm_b200_emb_bwd_update.argtypes = [C.POINTER(EmbBwdTable), i32, i32, i64, i32, i32, vp, vp,

@@ -7,7 +7,7 @@ reference's style of error.  The random-data generator draws from numpy's global
 reference's order (dlrm_data_pytorch.py:899-960 and :838-846; re-seeded at batch 0 of every epoch,
 :637-638), and parameters are initialised in the reference's order, so for the same
 `--numpy-rand-seed` the inputs and initial weights are bit-identical to the reference's and the printed
-loss curve can be compared directly (tests/test_gpu_cli.py does so against a recorded reference run).
+loss curve can be compared directly (tests/test_gpu_facade.py does so against a recorded reference run).
 """
 from __future__ import annotations
 

@@ -44,7 +44,19 @@ struct EmbBwdParams {
   int optimizer;
   float lr;
   float eps;
+  // table-wise sharded runs: the dY row of global bag b is read from rank b / peer_batch through
+  // peer-mapped memory (NVLink load).  peer_batch == 0: local dY.
+  const float* peer_dY[DLRM_B200_MAX_PEERS];
+  long long peer_batch;
 };
+
+__device__ __forceinline__ const float* dy_row(const EmbBwdParams& P, long long bag) {
+  if (P.peer_batch > 0) {
+    const int src = (int)(bag / P.peer_batch);
+    return P.peer_dY[src] + (bag - src * P.peer_batch) * P.dy_stride_sample;
+  }
+  return P.dY + bag * P.dy_stride_sample;
+}
 
 template <typename idx_t>
 __device__ __forceinline__ long long bag_end2(const idx_t* off, long long b, long long batch,
@@ -175,7 +187,7 @@ __global__ void __launch_bounds__(256, NV == 1 ? 3 : 1) emb_update_kernel(const 
         if ((owners >> src) & 1u) {
           const EmbBwdTable& tb = P.t[ku];
           const float* wrow = tb.w + r * D;
-          const float* grow = P.dY + (long long)ku * P.dy_stride_table + (long long)bag * P.dy_stride_sample;
+          const float* grow = dy_row(P, bag) + (long long)ku * P.dy_stride_table;
 #pragma unroll
           for (int v = 0; v < NV; ++v)
             if (col_ok[v]) {
@@ -195,7 +207,7 @@ __global__ void __launch_bounds__(256, NV == 1 ? 3 : 1) emb_update_kernel(const 
         if (!((owners >> src) & 1u)) continue;
         const EmbBwdTable& tb = P.t[ku];
         float* wrow = tb.w + r * D;
-        const float* dYk = P.dY + (long long)ku * P.dy_stride_table;
+        const long long dyk_off = (long long)ku * P.dy_stride_table;
         Pack<W> w[NV], g[NV];
 #pragma unroll
         for (int v = 0; v < NV; ++v) { w[v] = wpf[u][v]; g[v] = gpf[u][v]; }
@@ -225,7 +237,7 @@ __global__ void __launch_bounds__(256, NV == 1 ? 3 : 1) emb_update_kernel(const 
 #pragma unroll
               for (int v = 0; v < NV; ++v) {
                 if (col_ok[v]) {
-                  const Pack<W> t = ld_pack<W>(dYk + (long long)bag * P.dy_stride_sample + lane * W + v * 32 * W);
+                  const Pack<W> t = ld_pack<W>(dy_row(P, bag) + dyk_off + lane * W + v * 32 * W);
 #pragma unroll
                   for (int e = 0; e < W; ++e) g[v].x[e] += t.x[e];
                 }
@@ -320,11 +332,11 @@ extern "C" int dlrm_b200_emb_bwd_link(const dlrm_emb_bwd_table_t* tables, int nu
   return 0;
 }
 
-extern "C" int dlrm_b200_emb_bwd_update(const dlrm_emb_bwd_table_t* tables, int num_tables, int dim,
-                                        int64_t batch, int idx_bytes, int include_last,
-                                        const int32_t* next, const float* dY,
-                                        int64_t dy_stride_sample, int64_t dy_stride_table,
-                                        int optimizer, float lr, float eps, void* stream) {
+static int emb_update_impl(const dlrm_emb_bwd_table_t* tables, int num_tables, int dim, int64_t batch,
+                           int idx_bytes, int include_last, const int32_t* next, const float* dY,
+                           int64_t dy_stride_sample, int64_t dy_stride_table, int optimizer, float lr,
+                           float eps, void* stream, const float* const* peer_dY, int world,
+                           int64_t batch_local) {
   using namespace dlrm;
   EmbBwdParams P{};
   if (int rc = fill_params(P, tables, num_tables, "emb_bwd_update")) return rc;
@@ -333,8 +345,22 @@ extern "C" int dlrm_b200_emb_bwd_update(const dlrm_emb_bwd_table_t* tables, int 
     return set_error("emb_bwd_update: optimizer=%d", optimizer);
   if (dim <= 0 || dim > 1024) return set_error("emb_bwd_update: dim=%d unsupported (1..1024)", dim);
   if (num_tables == 0 || batch == 0) return 0;
-  if (!next || !dY) return set_error("emb_bwd_update: NULL next/dY");
-  bool vec = (dim % 4 == 0) && aligned16(dY) && dy_stride_sample % 4 == 0 && dy_stride_table % 4 == 0;
+  if (!next || (!dY && !peer_dY)) return set_error("emb_bwd_update: NULL next/dY");
+  bool vec = (dim % 4 == 0) && (peer_dY || aligned16(dY)) && dy_stride_sample % 4 == 0 && dy_stride_table % 4 == 0;
+  P.peer_batch = 0;
+  for (int d = 0; d < DLRM_B200_MAX_PEERS; ++d) P.peer_dY[d] = nullptr;
+  if (peer_dY) {
+    if (world < 1 || world > DLRM_B200_MAX_PEERS || batch_local <= 0 || batch_local * world != batch)
+      return set_error("emb_bwd_update_p2p: world=%d batch_local=%lld batch=%lld", world, (long long)batch_local,
+                       (long long)batch);
+    for (int d = 0; d < world; ++d) {
+      if (!peer_dY[d]) return set_error("emb_bwd_update_p2p: peer %d pointer is NULL", d);
+      vec = vec && aligned16(peer_dY[d]);
+      P.peer_dY[d] = peer_dY[d];
+    }
+    P.peer_batch = batch_local;
+    dY = peer_dY[0];
+  }
   for (int k = 0; k < num_tables; ++k) {
     if (!tables[k].weight) return set_error("emb_bwd_update: table %d weight NULL", k);
     if (optimizer == DLRM_OPT_RWSADAGRAD && !tables[k].momentum)
@@ -389,4 +415,25 @@ extern "C" int dlrm_b200_emb_bwd_update(const dlrm_emb_bwd_table_t* tables, int 
   if (dim <= 512) UPD(1, 16);
   UPD(1, 32);
 #undef UPD
+}
+
+extern "C" int dlrm_b200_emb_bwd_update(const dlrm_emb_bwd_table_t* tables, int num_tables, int dim,
+                                        int64_t batch, int idx_bytes, int include_last,
+                                        const int32_t* next, const float* dY,
+                                        int64_t dy_stride_sample, int64_t dy_stride_table,
+                                        int optimizer, float lr, float eps, void* stream) {
+  return emb_update_impl(tables, num_tables, dim, batch, idx_bytes, include_last, next, dY, dy_stride_sample,
+                         dy_stride_table, optimizer, lr, eps, stream, nullptr, 0, 0);
+}
+
+extern "C" int dlrm_b200_emb_bwd_update_p2p(const dlrm_emb_bwd_table_t* tables, int num_tables, int dim,
+                                            int64_t batch_global, int idx_bytes, int include_last,
+                                            const int32_t* next, const float* const* peer_dY, int world,
+                                            int64_t batch_local, int64_t dy_stride_sample,
+                                            int64_t dy_stride_table, int optimizer, float lr, float eps,
+                                            void* stream) {
+  if (!peer_dY) return dlrm::set_error("emb_bwd_update_p2p: peer_dY is NULL");
+  return emb_update_impl(tables, num_tables, dim, batch_global, idx_bytes, include_last, next, nullptr,
+                         dy_stride_sample, dy_stride_table, optimizer, lr, eps, stream, peer_dY, world,
+                         batch_local);
 }

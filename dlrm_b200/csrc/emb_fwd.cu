@@ -33,7 +33,19 @@ struct EmbFwdParams {
   int include_last;
   int bags_per_group;
   int2* link;  // training: link[pos] = {previous head of the row, bag}
+  // table-wise sharded runs: bag b belongs to rank b / peer_batch and its pooled row is stored straight
+  // into that rank's buffer through peer-mapped memory (NVLink store).  peer_batch == 0: local output.
+  float* peer_out[DLRM_B200_MAX_PEERS];
+  long long peer_batch;
 };
+
+__device__ __forceinline__ float* out_row(const EmbFwdParams& P, long long b) {
+  if (P.peer_batch > 0) {
+    const int dst = (int)(b / P.peer_batch);
+    return P.peer_out[dst] + (b - dst * P.peer_batch) * P.stride_sample;
+  }
+  return P.out + b * P.stride_sample;
+}
 
 // Fused "link" step of the sort-free coalesce (emb_bwd.cu): thread the occurrence at position j
 // of this table onto the per-row list while its index is already in a register.
@@ -152,7 +164,7 @@ __global__ void __launch_bounds__(256, (G == 32 && NV == 1) ? 3 : 1) emb_fwd_vec
         if (LINK && j0 + gl < end)
           P.link[tb.pair_base + j0 + gl] = make_int2(my_prev, (int)(b0 + s));
       }
-      float* op = P.out + (b0 + s) * P.stride_sample + (long long)table * P.stride_table + gl * 4;
+      float* op = out_row(P, b0 + s) + (long long)table * P.stride_table + gl * 4;
 #pragma unroll
       for (int v = 0; v < NV; ++v) {
         if (gl * 4 + v * G * 4 < D) *reinterpret_cast<float4*>(op + v * G * 4) = acc[v];
@@ -185,7 +197,7 @@ __global__ void emb_fwd_scalar_kernel(const __grid_constant__ EmbFwdParams P) {
     const float x = tb.w[r * D + d];
     acc = WEIGHTED ? fmaf(tb.rw[r], x, acc) : acc + x;
   }
-  P.out[b * P.stride_sample + (long long)blockIdx.y * P.stride_table + d] = acc;
+  out_row(P, b)[(long long)blockIdx.y * P.stride_table + d] = acc;
 }
 
 template <int G, int NV, int U, typename idx_t, bool WEIGHTED, bool LINK>
@@ -244,7 +256,8 @@ static int dispatch(const EmbFwdParams& Pin, int num_tables, bool vec_ok, cudaSt
 static int emb_fwd_impl(const dlrm_emb_fwd_table_t* tables, const dlrm_emb_bwd_table_t* train,
                         int32_t* link, int num_tables, int dim, int64_t batch, int idx_bytes,
                         int include_last, float* out, int64_t out_stride_sample,
-                        int64_t out_stride_table, void* stream) {
+                        int64_t out_stride_table, void* stream, float* const* peer_out = nullptr,
+                        int world = 0, int64_t batch_local = 0) {
   using namespace dlrm;
   if (num_tables < 0 || num_tables > DLRM_B200_MAX_TABLES_PER_CALL)
     return set_error("emb_bag_fwd: num_tables=%d out of range [0,%d]", num_tables,
@@ -257,7 +270,7 @@ static int emb_fwd_impl(const dlrm_emb_fwd_table_t* tables, const dlrm_emb_bwd_t
   if (train && !link) return set_error("emb_bag_fwd_train: link is NULL");
   EmbFwdParams P;
   bool weighted = false, any_unweighted = false;
-  bool vec_ok = (dim % 4 == 0) && dim <= 512 && aligned16(out) && out_stride_sample % 4 == 0 &&
+  bool vec_ok = (dim % 4 == 0) && dim <= 512 && (peer_out || aligned16(out)) && out_stride_sample % 4 == 0 &&
                 out_stride_table % 4 == 0;
   for (int k = 0; k < num_tables; ++k) {
     P.t[k].w = tables[k].weight;
@@ -286,6 +299,20 @@ static int emb_fwd_impl(const dlrm_emb_fwd_table_t* tables, const dlrm_emb_bwd_t
   P.include_last = include_last;
   P.bags_per_group = 1;
   P.link = reinterpret_cast<int2*>(link);
+  P.peer_batch = 0;
+  for (int d = 0; d < DLRM_B200_MAX_PEERS; ++d) P.peer_out[d] = nullptr;
+  if (peer_out) {
+    if (world < 1 || world > DLRM_B200_MAX_PEERS || batch_local <= 0 || batch_local * world != batch)
+      return set_error("emb_bag_fwd_p2p: world=%d batch_local=%lld batch=%lld", world, (long long)batch_local,
+                       (long long)batch);
+    for (int d = 0; d < world; ++d) {
+      if (!peer_out[d]) return set_error("emb_bag_fwd_p2p: peer %d pointer is NULL", d);
+      vec_ok = vec_ok && aligned16(peer_out[d]);
+      P.peer_out[d] = peer_out[d];
+    }
+    P.peer_batch = batch_local;
+    P.out = peer_out[0];
+  }
   cudaStream_t st = static_cast<cudaStream_t>(stream);
 #define DISPATCH(IDX)                                                                          \
   do {                                                                                         \
@@ -315,4 +342,14 @@ extern "C" int dlrm_b200_emb_bag_fwd_train(const dlrm_emb_fwd_table_t* tables,
   if (!train) return dlrm::set_error("emb_bag_fwd_train: train descriptors are NULL");
   return emb_fwd_impl(tables, train, next, num_tables, dim, batch, idx_bytes, include_last, out,
                       out_stride_sample, out_stride_table, stream);
+}
+
+extern "C" int dlrm_b200_emb_bag_fwd_p2p(const dlrm_emb_fwd_table_t* tables,
+                                         const dlrm_emb_bwd_table_t* train, int num_tables, int dim,
+                                         int64_t batch_global, int idx_bytes, int include_last, int32_t* next,
+                                         float* const* peer_out, int world, int64_t batch_local,
+                                         int64_t out_stride_sample, int64_t out_stride_table, void* stream) {
+  if (!peer_out) return dlrm::set_error("emb_bag_fwd_p2p: peer_out is NULL");
+  return emb_fwd_impl(tables, train, next, num_tables, dim, batch_global, idx_bytes, include_last, nullptr,
+                      out_stride_sample, out_stride_table, stream, peer_out, world, batch_local);
 }

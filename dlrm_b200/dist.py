@@ -129,7 +129,77 @@ class DistEngine:
         self.gsend = torch.zeros(sum(self.recv_splits), dtype=f32, device=self.device)
         self.grecv = torch.zeros(self.Bg * self.Tl * self.D, dtype=f32, device=self.device)
         e.gather_fn, e.update_fn, e.dense_sync_fn = self._gather, self._update, self._dense_sync
-        self.a2a_bytes = 0
+        self._flag = torch.zeros(1, dtype=f32, device=self.device)
+        if exchange == "p2p":
+            self._setup_p2p()
+            e.gather_fn, e.update_fn = self._gather_p2p, self._update_p2p
+        elif exchange != "nccl":
+            raise SystemExit("ERROR: exchange must be nccl or p2p")
+
+    # ------------------------------------------------------------------ peer-mapped exchange
+    def _setup_p2p(self):
+        """Map every rank's interaction operand T and its gradient dT into this process (CUDA IPC over
+        NVLink).  peer_T[d] / peer_dT[s] point at feature (1 + my first table) of rank d's / s's buffer."""
+        import ctypes as C
+
+        from torch.multiprocessing.reductions import reduce_tensor
+
+        e = self.eng
+        mine = (reduce_tensor(e.Tbuf), reduce_tensor(e.dT))
+        allh = [None] * self.world
+        dist.all_gather_object(allh, mine)
+        self._peer_keep = []
+        pT, pdT = [], []
+        col = (1 + self.t0) * self.D * 4
+        for r in range(self.world):
+            if r == self.rank:
+                t, g = e.Tbuf, e.dT
+            else:
+                (fT, aT), (fG, aG) = allh[r]
+                t, g = fT(*aT), fG(*aG)
+            self._peer_keep += [t, g]
+            pT.append(t.data_ptr() + col)
+            pdT.append(g.data_ptr() + col)
+        self._peer_T = (C.c_void_p * self.world)(*pT)
+        self._peer_dT = (C.c_void_p * self.world)(*pdT)
+        dist.barrier()
+
+    def _barrier(self):
+        """Device-side ordering across ranks on the current stream (no host sync)."""
+        dist.all_reduce(self._flag)
+
+    def _gather_p2p(self, sp, link):
+        from . import _lib
+        from .engine import _stream
+
+        e = self.eng
+        if not link:
+            self._barrier()   # inference loops: peers must be done reading T of the previous batch
+        FD = e.F * self.D
+        if link:
+            e._ensure_link(sp.nnz_total if sp.include_last else sum(int(i.numel()) for i in sp.indices))
+        desc = e._fwd_desc(sp, range(self.Tl))
+        bdesc = e._bwd_desc_chunk(sp, list(range(self.Tl)))[0] if link else None
+        _lib.check(e.lib.dlrm_b200_emb_bag_fwd_p2p(desc, bdesc, self.Tl, self.D, sp.batch, sp.idx_bytes,
+                                                   int(sp.include_last), e.link.data_ptr() if link else None,
+                                                   self._peer_T, self.world, self.B, FD, self.D, _stream()),
+                   "emb_bag_fwd_p2p")
+        e.n_launch += 1
+        self._barrier()       # every rank's pooled rows have landed in every T
+
+    def _update_p2p(self, sp, optimizer, clr):
+        from . import _lib
+        from .engine import _OPT, _stream
+
+        e = self.eng
+        self._barrier()       # every rank's dT is complete
+        FD = e.F * self.D
+        bdesc, _ = e._bwd_desc_chunk(sp, list(range(self.Tl)))
+        _lib.check(e.lib.dlrm_b200_emb_bwd_update_p2p(bdesc, self.Tl, self.D, sp.batch, sp.idx_bytes,
+                                                      int(sp.include_last), e.link.data_ptr(), self._peer_dT,
+                                                      self.world, self.B, FD, self.D, _OPT[optimizer], clr,
+                                                      1e-10, _stream()), "emb_bwd_update_p2p")
+        e.n_launch += 1
 
     # -- forward: pool local tables for the global batch, exchange, land in T
     def _gather(self, sp, link):
@@ -198,7 +268,7 @@ def bench_main(args, CFG, metric_name, config_dict, ClockSampler):
     ln_emb = [CFG["rows"]] * T
     ln_top = [D + (T + 1) * T // 2] + CFG["top_tail"]
     de = DistEngine(D, ln_emb, CFG["ln_bot"], ln_top, local_batch=B, device=dev, gemm=args.gemm,
-                    exchange=getattr(args, "exchange", "nccl"))
+                    exchange=getattr(args, "exchange", "p2p"))
     de.eng.init_params(100 + rank)
     de.sync_dense_params_from_rank0()
     de.eng.ensure_optimizer_state("rwsadagrad")

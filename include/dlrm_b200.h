@@ -33,6 +33,7 @@ extern "C" {
 
 #define DLRM_B200_ABI_VERSION 1
 #define DLRM_B200_MAX_TABLES_PER_CALL 64 /* larger T: split into several calls */
+#define DLRM_B200_MAX_PEERS 8            /* GPUs of one NVSwitch box */
 
 /* activations of create_mlp (dlrm_s_pytorch.py:237-241) */
 enum { DLRM_ACT_NONE = 0, DLRM_ACT_RELU = 1, DLRM_ACT_SIGMOID = 2 };
@@ -114,6 +115,26 @@ int dlrm_b200_emb_bwd_update(const dlrm_emb_bwd_table_t* tables /*[host]*/, int 
                              const int32_t* next, const float* dY, int64_t dy_stride_sample,
                              int64_t dy_stride_table, int optimizer, float lr, float eps,
                              void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Table-wise sharded runs (replaces extend_distributed.alltoall, extend_distributed.py:389-486, and
+ * the butterfly shuffle of parallel_forward, dlrm_s_pytorch.py:693-699): the exchange is fused into
+ * the kernels through peer-mapped memory (cudaIpc / NVLink), no staging buffer, no collective.
+ *   fwd : this rank pools ITS tables for the GLOBAL batch; bag b is stored into rank (b / batch_local)'s
+ *         buffer: peer_out[d] + (b % batch_local) * out_stride_sample + k * out_stride_table.
+ *   bwd : the dY row of global bag b is loaded from peer_dY[b / batch_local] with the same strides.
+ * The caller synchronises the ranks (a barrier after fwd, before bwd).  train may be NULL (inference).
+ * ------------------------------------------------------------------------------------------ */
+int dlrm_b200_emb_bag_fwd_p2p(const dlrm_emb_fwd_table_t* tables /*[host]*/,
+                              const dlrm_emb_bwd_table_t* train /*[host] or NULL*/, int num_tables, int dim,
+                              int64_t batch_global, int idx_bytes, int include_last, int32_t* next,
+                              float* const* peer_out /*[host][world]*/, int world, int64_t batch_local,
+                              int64_t out_stride_sample, int64_t out_stride_table, void* stream);
+int dlrm_b200_emb_bwd_update_p2p(const dlrm_emb_bwd_table_t* tables /*[host]*/, int num_tables, int dim,
+                                 int64_t batch_global, int idx_bytes, int include_last, const int32_t* next,
+                                 const float* const* peer_dY /*[host][world]*/, int world,
+                                 int64_t batch_local, int64_t dy_stride_sample, int64_t dy_stride_table,
+                                 int optimizer, float lr, float eps, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * apply_mlp layer (dlrm_s_pytorch.py:399-405: nn.Linear -> addmm, + ReLU / Sigmoid modules)

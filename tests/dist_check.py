@@ -26,6 +26,7 @@ def main():
     rank, world = init_distributed("nccl")
     dev = "cuda:%d" % int(os.environ.get("LOCAL_RANK", rank))
     gemm = os.environ.get("DLRM_GEMM", "tc")
+    exchange = os.environ.get("DLRM_EXCHANGE", "nccl")
     D, ln_emb, ln_bot = 128, [3000, 500, 40, 1000, 77], [13, 64, 128]
     Tg = len(ln_emb)
     ln_top = [D + (Tg + 1) * Tg // 2, 64, 32, 1]
@@ -44,7 +45,7 @@ def main():
     p_full = full.forward(Xg, spg).clone()
     # ---- sharded run
     t0, t1 = table_slices(Tg, world)[rank]
-    de = DistEngine(D, ln_emb, ln_bot, ln_top, local_batch=B, device=dev, gemm=gemm)
+    de = DistEngine(D, ln_emb, ln_bot, ln_top, local_batch=B, device=dev, gemm=gemm, exchange=exchange)
     loc = dict(emb=params["emb"][t0:t1], bot=params["bot"], top=params["top"], v_W_l=None)
     de.eng.load_params(loc)
     spl = sparse_from_reference([torch.from_numpy(o) for o in off[t0:t1]],
@@ -77,8 +78,8 @@ def main():
     ok = ok and err_l < 2e-6
     flag = torch.tensor([1.0 if ok else 0.0], device=dev)
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)
-    print("rank %d gemm=%s fwd_err=%.2e table_err=%.2e dense_err=%.2e loss_err=%.2e -> %s" % (
-        rank, gemm, err_f, err_t, err_d, err_l, "PASS" if ok else "FAIL"), flush=True)
+    print("rank %d exchange=%s gemm=%s fwd_err=%.2e table_err=%.2e dense_err=%.2e loss_err=%.2e -> %s" % (
+        rank, exchange, gemm, err_f, err_t, err_d, err_l, "PASS" if ok else "FAIL"), flush=True)
     dist.barrier()
     dist.destroy_process_group()
     sys.exit(0 if flag.item() == 1.0 else 1)

@@ -17,7 +17,7 @@ def _grad_close(got, want, what):
     agrees to bf16x3 accuracy.  Compare with robust statistics relative to the tensor's scale."""
     err = np.abs(np.asarray(got, np.float64) - np.asarray(want, np.float64)).ravel()
     sc = float(np.abs(want).max()) + 1e-12
-    assert np.median(err) <= 2e-5 * sc, (what, "median", np.median(err) / sc)
+    assert np.median(err) <= 2e-5 * sc + 1e-7, (what, "median", np.median(err) / sc)
     assert np.quantile(err, 0.99) <= 5e-3 * sc, (what, "p99", np.quantile(err, 0.99) / sc)
     assert err.max() <= 0.25 * sc, (what, "max", err.max() / sc)
 

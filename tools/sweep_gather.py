@@ -72,6 +72,25 @@ def main():
     res.append(dict(kernel="link+update", us=t_both * 1e6, update_us=(t_both - t_link) * 1e6,
                     update_GBs=bytes_bwd / (t_both - t_link) / 1e9))
     print(res[-2], res[-1], flush=True)
+
+    # what bounds the update?  (a) no momentum traffic (SGD), (b) fused gather+link before it (list heads
+    # evicted from L2 by the 140 MB of rows the gather streams through)
+    def both_sgd(db):
+        eng.emb_link(db.sparse)
+        eng.emb_update(db.sparse, eng.dT.view(-1)[D:], FD, D, "sgd", 1e-6)
+
+    t_sgd = timeit(both_sgd)
+    res.append(dict(kernel="link+update(sgd)", us=t_sgd * 1e6, update_us=(t_sgd - t_link) * 1e6))
+    print(res[-1], flush=True)
+
+    def fused(db):
+        eng.emb_forward(db.sparse, out, FD, D, link=True)
+        eng.emb_update(db.sparse, eng.dT.view(-1)[D:], FD, D, "rwsadagrad", 1e-6)
+
+    t_g = timeit(lambda db: eng.emb_forward(db.sparse, out, FD, D))
+    t_f = timeit(fused)
+    res.append(dict(kernel="gather+link -> update(rwsadagrad)", us=t_f * 1e6, gather_only_us=t_g * 1e6))
+    print(res[-1], flush=True)
     if len(sys.argv) > 1:
         json.dump(res, open(sys.argv[1], "w"), indent=1)
 
