@@ -63,10 +63,11 @@ __device__ __forceinline__ long long bag_end(const idx_t* off, long long b, long
 }
 
 // G lanes per bag, NV float4 per lane (dim = 4*G*NV when exact; columns >= dim are masked).
-// Persistent: the grid is sized to one resident wave (SMs x blocks/SM) and every lane group strides
-// over work items of S consecutive bags, so there is no partial second wave of CTAs.
+// grid = (groups of S bags, table).  Measured on B200 (profiles/r1_gather_sweep_*.json): the plain grid
+// at 64 registers / 4 CTAs per SM (S=4, U=8: 32.8 us = 5.1 TB/s) beats a persistent one-wave grid at 78
+// registers / 3 CTAs per SM (34-42 us): the gather is latency-bound, resident warps matter most.
 template <int G, int NV, int U, typename idx_t, bool WEIGHTED, bool LINK>
-__global__ void __launch_bounds__(256, (G == 32 && NV == 1) ? 3 : 1) emb_fwd_vec_kernel(
+__global__ void __launch_bounds__(256, (G == 32 && NV == 1) ? 4 : 1) emb_fwd_vec_kernel(
     const __grid_constant__ EmbFwdParams P, int num_tables) {
   const int D = P.dim;
   constexpr int GROUPS_PER_WARP = 32 / G;
@@ -75,19 +76,15 @@ __global__ void __launch_bounds__(256, (G == 32 && NV == 1) ? 3 : 1) emb_fwd_vec
   const int grp = lane / G;  // group inside the warp
   const unsigned gmask = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << (grp * G));
   const int S = P.bags_per_group;
-  const long long items_per_table = (P.batch + S - 1) / S;
-  const long long total_items = items_per_table * num_tables;
-  const long long group0 =
-      ((long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * GROUPS_PER_WARP + grp;
-  const long long group_stride = (long long)gridDim.x * (blockDim.x >> 5) * GROUPS_PER_WARP;
-
-  for (long long item = group0; item < total_items; item += group_stride) {
-    const int table = (int)(item / items_per_table);
+  const int table = blockIdx.y;
+  {
     const EmbFwdTable& tb = P.t[table];
     const idx_t* __restrict__ idx = static_cast<const idx_t*>(tb.idx);
     const idx_t* __restrict__ off = static_cast<const idx_t*>(tb.off);
     const float* __restrict__ W = tb.w;
-    const long long b0 = (item - (long long)table * items_per_table) * S;
+    const long long b0 =
+        (((long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * GROUPS_PER_WARP + grp) * S;
+    if (b0 >= P.batch) return;
     const int nb = (int)min((long long)S, P.batch - b0);
 
     // bag boundaries of this run of bags: one coalesced load, then shuffles (S < G, host-enforced).
@@ -203,20 +200,10 @@ __global__ void emb_fwd_scalar_kernel(const __grid_constant__ EmbFwdParams P) {
 template <int G, int NV, int U, typename idx_t, bool WEIGHTED, bool LINK>
 static int launch_vec(const EmbFwdParams& P, int num_tables, cudaStream_t st) {
   const int block = 256;
-  static int resident = 0;  // CTAs in one full wave on this device, for this instantiation
-  if (!resident) {
-    int dev = 0, sms = 0, per_sm = 0;
-    DLRM_CUDA(cudaGetDevice(&dev));
-    DLRM_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-    DLRM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(
-        &per_sm, emb_fwd_vec_kernel<G, NV, U, idx_t, WEIGHTED, LINK>, block, 0));
-    resident = sms * (per_sm > 0 ? per_sm : 1);
-  }
   const long long groups_per_block = (long long)(block / 32) * (32 / G);
-  const long long items = ((P.batch + P.bags_per_group - 1) / P.bags_per_group) * num_tables;
-  long long grid = (items + groups_per_block - 1) / groups_per_block;
-  if (grid > resident) grid = resident;
-  emb_fwd_vec_kernel<G, NV, U, idx_t, WEIGHTED, LINK><<<(unsigned)grid, block, 0, st>>>(P, num_tables);
+  const long long groups = (P.batch + P.bags_per_group - 1) / P.bags_per_group;
+  dim3 grid((unsigned)((groups + groups_per_block - 1) / groups_per_block), (unsigned)num_tables);
+  emb_fwd_vec_kernel<G, NV, U, idx_t, WEIGHTED, LINK><<<grid, block, 0, st>>>(P, num_tables);
   DLRM_CHECK_LAUNCH("emb_fwd_vec_kernel");
   return 0;
 }
@@ -228,7 +215,7 @@ static int dispatch(const EmbFwdParams& Pin, int num_tables, bool vec_ok, cudaSt
   if (vec_ok) {
     const int u8 = get_tunable(TUNE_EMB_UNROLL) != 4;
     int S = get_tunable(TUNE_EMB_BAGS_PER_GROUP);
-    if (S <= 0) S = 4;  // bags per work item of the persistent loop
+    if (S <= 0) S = 4;  // bags handled back to back by one lane group
 #define VEC(G, NV)                                                                   \
   do {                                                                               \
     P.bags_per_group = S < (G) ? S : (G)-1;                                          \

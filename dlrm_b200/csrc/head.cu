@@ -88,18 +88,27 @@ __global__ void __launch_bounds__(256) head_kernel(const HeadArgs a) {
     for (int k = threadIdx.x; k < a.K; k += blockDim.x) {
       const float wk = a.w[k];
       float acc = 0.f;
-      for (int rl = 0; rl < nrows; ++rl) {
-        const float hv = a.h[(r0 + rl) * a.ldh + k];
-        const float g = s_gz[rl];
-        acc = fmaf(g, hv, acc);
-        float gp = g * wk;
-        if (a.act_prev == DLRM_ACT_RELU) gp = hv > 0.f ? gp : 0.f;
-        else if (a.act_prev == DLRM_ACT_SIGMOID) gp *= (1.0f - hv) * hv;
-        if (a.gprev) a.gprev[(r0 + rl) * a.ld_gprev + k] = gp;
-        if (a.gprev_hi) {
-          const __nv_bfloat16 hb = __float2bfloat16_rn(gp);
-          a.gprev_hi[(r0 + rl) * a.ld_gb + k] = hb;
-          if (a.gprev_lo) a.gprev_lo[(r0 + rl) * a.ld_gb + k] = __float2bfloat16_rn(gp - __bfloat162float(hb));
+      for (int rl0 = 0; rl0 < nrows; rl0 += 8) {
+        float hv8[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u)   // 8 independent loads in flight before the dependent math / stores
+          hv8[u] = (rl0 + u < nrows) ? a.h[(r0 + rl0 + u) * a.ldh + k] : 0.f;
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const int rl = rl0 + u;
+          if (rl >= nrows) break;
+          const float hv = hv8[u];
+          const float g = s_gz[rl];
+          acc = fmaf(g, hv, acc);
+          float gp = g * wk;
+          if (a.act_prev == DLRM_ACT_RELU) gp = hv > 0.f ? gp : 0.f;
+          else if (a.act_prev == DLRM_ACT_SIGMOID) gp *= (1.0f - hv) * hv;
+          if (a.gprev) a.gprev[(r0 + rl) * a.ld_gprev + k] = gp;
+          if (a.gprev_hi) {
+            const __nv_bfloat16 hb = __float2bfloat16_rn(gp);
+            a.gprev_hi[(r0 + rl) * a.ld_gb + k] = hb;
+            if (a.gprev_lo) a.gprev_lo[(r0 + rl) * a.ld_gb + k] = __float2bfloat16_rn(gp - __bfloat162float(hb));
+          }
         }
       }
       part[k] = acc;

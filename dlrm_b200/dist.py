@@ -280,8 +280,30 @@ def bench_main(args, CFG, metric_name, config_dict, ClockSampler):
         ring.append((hb, db, X, X.to(dev), Tt, Tt.to(dev)))
     lr = 0.01
 
+    # static staging buffers + (optionally) the whole sharded step, collectives included, in one CUDA graph
+    stage = DeviceBatch(ring[0][0].layout, dev)
+    stage.load(ring[0][0], non_blocking=False)
+    Xs = ring[0][3].clone()
+    Ts = ring[0][5].clone()
+    graph = None
+    if not getattr(args, "no_graph", False):
+        from .engine import GraphedTrainStep
+
+        try:
+            graph = GraphedTrainStep(de.eng, stage, lr, "rwsadagrad", warmup=3, train=train, X=Xs, target=Ts)
+        except Exception as ex:  # noqa: BLE001  (capture of the collectives not possible on this stack)
+            if rank == 0:
+                print("dist: CUDA-graph capture failed (%s); running eagerly" % str(ex)[:200], flush=True)
+            graph = None
+
     def step(i):
         hb, db, Xh, Xd, Th, Td = ring[i % args.ring]
+        if graph is not None:
+            nbytes = db.layout.used(db.nnz)
+            stage.buf[:nbytes].copy_(db.buf[:nbytes], non_blocking=True)
+            Xs.copy_(Xd, non_blocking=True)
+            Ts.copy_(Td, non_blocking=True)
+            return graph.replay()
         if train:
             return de.train_step(Xd, db.sparse, Td, lr, "rwsadagrad")
         return de.forward(Xd, db.sparse)
@@ -312,9 +334,6 @@ def bench_main(args, CFG, metric_name, config_dict, ClockSampler):
     ms = float(ms.item())
 
     # e2e: host batches (packed sparse part + dense slice) copied every step, loss read back
-    stage = DeviceBatch(ring[0][0].layout, dev)
-    Xs = torch.empty((B, 13), device=dev)
-    Ts = torch.empty((B, 1), device=dev)
     loss_host = torch.zeros(1).pin_memory()
     h2d = 0
 
@@ -325,7 +344,9 @@ def bench_main(args, CFG, metric_name, config_dict, ClockSampler):
         Xs.copy_(Xh, non_blocking=True)
         Ts.copy_(Th, non_blocking=True)
         h2d += Xh.numel() * 4 + Th.numel() * 4
-        if train:
+        if graph is not None:
+            out = graph.replay()
+        elif train:
             out = de.train_step(Xs, stage.sparse, Ts, lr, "rwsadagrad")
         else:
             out = de.forward(Xs, stage.sparse)
@@ -360,7 +381,7 @@ def bench_main(args, CFG, metric_name, config_dict, ClockSampler):
                     "d2h_bytes_per_step": 4, "ms_per_step": ms2,
                     "note": "per rank: packed pinned sparse batch (its tables, global batch) + dense slice, "
                             "H2D every step, loss read back"},
-            "gpu_launches": int(launches), "exchange": de.exchange,
+            "gpu_launches": int(launches), "exchange": de.exchange, "cuda_graph": graph is not None,
             "a2a_bytes_per_rank_per_step": int(2 * 4 * (sum(de.send_splits) - de.send_splits[rank])),
             "clocks": clocks,
         }

@@ -924,8 +924,11 @@ class GraphedTrainStep:
     rate is baked into the graph (re-capture to change it)."""
 
     def __init__(self, eng: "Engine", stage, lr: float, optimizer: str = "rwsadagrad", warmup: int = 3,
-                 train: bool = True):
+                 train: bool = True, X: Optional[torch.Tensor] = None, target: Optional[torch.Tensor] = None):
         self.eng, self.stage, self.train = eng, stage, train
+        # table-wise sharded runs: the dense slice / targets are separate static tensors
+        self.X = X if X is not None else stage.X
+        self.target = target if target is not None else stage.target
         self.lr, self.optimizer = lr, optimizer
         eng.ensure_optimizer_state(optimizer)
         if warmup > 0:
@@ -936,7 +939,7 @@ class GraphedTrainStep:
                     self._eager()
             torch.cuda.current_stream().wait_stream(side)
         else:
-            eng.prepare(stage.sparse, train)  # allocate lazily-created buffers without running a step
+            eng.prepare(stage.sparse, train, batch=self.X.shape[0])  # allocate lazily-created buffers
         torch.cuda.synchronize()
         n0 = eng.n_launch
         self.graph = torch.cuda.CUDAGraph()
@@ -947,8 +950,8 @@ class GraphedTrainStep:
     def _eager(self):
         st = self.stage
         if self.train:
-            return self.eng.train_step(st.X, st.sparse, st.target, self.lr, self.optimizer)
-        return self.eng.forward(st.X, st.sparse)
+            return self.eng.train_step(self.X, st.sparse, self.target, self.lr, self.optimizer)
+        return self.eng.forward(self.X, st.sparse)
 
     def replay(self):
         self.graph.replay()
