@@ -27,6 +27,10 @@ class EmbBwdTable(C.Structure):
                 ("rows", C.c_int64), ("pair_base", C.c_int64)]
 
 
+class EmbDedup(C.Structure):
+    _fields_ = [("filter", C.c_void_p), ("log2_size", C.c_int32), ("flags", C.c_void_p), ("suspects", C.c_void_p)]
+
+
 class GemmTcDesc(C.Structure):
     _fields_ = [("A_hi", C.c_void_p), ("A_lo", C.c_void_p), ("lda", C.c_int64), ("a_mn_major", C.c_int),
                 ("B_hi", C.c_void_p), ("B_lo", C.c_void_p), ("ldb", C.c_int64), ("b_mn_major", C.c_int),
@@ -55,7 +59,7 @@ SYMBOLS = [
     "dlrm_b200_emb_bag_fwd", "dlrm_b200_emb_bag_fwd_train", "dlrm_b200_emb_bwd_link",
     "dlrm_b200_emb_bwd_update", "dlrm_b200_head_scratch_bytes", "dlrm_b200_head_fused",
     "dlrm_b200_interact_fwd_ex", "dlrm_b200_interact_bwd_ex", "dlrm_b200_act_bwd",
-    "dlrm_b200_emb_bag_fwd_p2p", "dlrm_b200_emb_bwd_update_p2p",
+    "dlrm_b200_emb_bag_fwd_p2p", "dlrm_b200_emb_bwd_update_p2p", "dlrm_b200_emb_bwd_classify",
     "dlrm_b200_linear_fwd", "dlrm_b200_linear_dgrad", "dlrm_b200_linear_wgrad",
     "dlrm_b200_interact_fwd", "dlrm_b200_interact_bwd", "dlrm_b200_loss_fwd_bwd",
     "dlrm_b200_dense_update",
@@ -72,20 +76,21 @@ def _declare(lib):
     lib.dlrm_b200_device_info.argtypes = [i32, C.POINTER(i32), C.POINTER(i32), C.POINTER(i32)]
     lib.dlrm_b200_emb_bag_fwd.argtypes = [C.POINTER(EmbFwdTable), i32, i32, i64, i32, i32, vp, i64, i64, vp]
     lib.dlrm_b200_emb_bag_fwd_train.argtypes = [C.POINTER(EmbFwdTable), C.POINTER(EmbBwdTable), i32, i32, i64, i32,
-                                                i32, vp, vp, i64, i64, vp]
+                                                i32, vp, vp, i64, i64, C.POINTER(EmbDedup), vp]
+    lib.dlrm_b200_emb_bwd_classify.argtypes = [C.POINTER(EmbBwdTable), i32, i64, i32, i32, vp, C.POINTER(EmbDedup), vp]
     lib.dlrm_b200_head_scratch_bytes.argtypes = [i64, i64]
     lib.dlrm_b200_head_fused.argtypes = [vp, i64, vp, vp, vp, vp, i64, i64, i32, i32, i32, f32, vp, vp, vp, vp, vp,
                                          vp, i64, vp, vp, i64, vp, vp]
     lib.dlrm_b200_interact_fwd_ex.argtypes = [vp, i64, vp, i64, vp, vp, i64, i64, i32, i32, i32, vp]
     lib.dlrm_b200_interact_bwd_ex.argtypes = [vp, i64, vp, i64, vp, i64, i64, i32, i32, i32, i32, vp, vp, i64, vp]
     lib.dlrm_b200_emb_bag_fwd_p2p.argtypes = [C.POINTER(EmbFwdTable), C.POINTER(EmbBwdTable), i32, i32, i64, i32, i32,
-                                              vp, C.POINTER(vp), i32, i64, i64, i64, vp]
+                                              vp, C.POINTER(vp), i32, i64, i64, i64, C.POINTER(EmbDedup), vp]
     lib.dlrm_b200_emb_bwd_update_p2p.argtypes = [C.POINTER(EmbBwdTable), i32, i32, i64, i32, i32, vp, C.POINTER(vp),
-                                                 i32, i64, i64, i64, i32, f32, f32, vp]
+                                                 i32, i64, i64, i64, i32, f32, f32, C.POINTER(EmbDedup), vp]
     lib.dlrm_b200_act_bwd.argtypes = [vp, vp, vp, i64, i32, f32, vp]
     lib.dlrm_b200_emb_bwd_link.argtypes = [C.POINTER(EmbBwdTable), i32, i64, i32, i32, vp, vp]
     lib.dlrm_b200_emb_bwd_update.argtypes = [C.POINTER(EmbBwdTable), i32, i32, i64, i32, i32, vp, vp,
-                                             i64, i64, i32, f32, f32, vp]
+                                             i64, i64, i32, f32, f32, C.POINTER(EmbDedup), vp]
     lib.dlrm_b200_linear_fwd.argtypes = [vp, i64, vp, i64, vp, vp, i64, i64, i64, i64, i32, i32, vp]
     lib.dlrm_b200_linear_dgrad.argtypes = [vp, i64, vp, i64, vp, i64, i32, vp, i64, i64, i64, i64, i32, vp]
     lib.dlrm_b200_linear_wgrad.argtypes = [vp, i64, vp, i64, vp, i64, vp, i64, i64, i64, i32, vp]

@@ -47,6 +47,12 @@ __device__ __forceinline__ float4 ldg_stream_f4(const float* p) {
   return v;
 }
 
+// slot of a (table,row) in the duplicate filter: the address of the row's list head is a unique key
+__device__ __forceinline__ unsigned filter_slot(const int* head_of_row, int log2_size) {
+  const unsigned long long key = reinterpret_cast<unsigned long long>(head_of_row) >> 2;
+  return (unsigned)((key * 11400714819323198485ull) >> (64 - log2_size));
+}
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

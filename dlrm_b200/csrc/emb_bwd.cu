@@ -48,6 +48,8 @@ struct EmbBwdParams {
   // peer-mapped memory (NVLink load).  peer_batch == 0: local dY.
   const float* peer_dY[DLRM_B200_MAX_PEERS];
   long long peer_batch;
+  // duplicate filter (optional): occurrences with flags[pos] == 0 are the only occurrence of their row
+  const unsigned char* flags;
 };
 
 __device__ __forceinline__ const float* dy_row(const EmbBwdParams& P, long long bag) {
@@ -120,15 +122,10 @@ __device__ __forceinline__ void st_pack(float* p, const Pack<W>& r) {
   }
 }
 
-// Occurrence-centric: a warp takes 32 consecutive index positions (all tables share one global
-// position space: reference format = per-table arrays + pair_base, packed format = one array),
-// reads index / link / head with coalesced + gathered loads, and processes the rows it owns with
-// up to PF weight rows AND their dY rows in flight.  The bag of an occurrence comes from link[],
-// so the offsets are not needed (packed format reads only the per-table bounds).
-template <int W, int NV, typename idx_t>
-__global__ void __launch_bounds__(256, NV == 1 ? 3 : 1) emb_update_kernel(const __grid_constant__ EmbBwdParams P,
-                                                                          int num_tables, long long total_hint) {
-  __shared__ long long bound[DLRM_B200_MAX_TABLES_PER_CALL + 1];
+// first global position of every table (+ end) in shared memory; see emb_update_kernel
+template <typename idx_t>
+__device__ __forceinline__ void load_bounds(long long* bound, const EmbBwdParams& P, int num_tables,
+                                            long long total_hint) {
   if ((int)threadIdx.x <= num_tables) {
     const int k = threadIdx.x;
     long long v;
@@ -140,6 +137,76 @@ __global__ void __launch_bounds__(256, NV == 1 ? 3 : 1) emb_update_kernel(const 
     bound[k] = v;
   }
   __syncthreads();
+}
+// table of a position: largest k with bound[k] <= pos (empty tables share a bound)
+__device__ __forceinline__ int table_of(const long long* bound, int num_tables, long long pos) {
+  int lo = 0, hi = num_tables - 1;
+  while (lo < hi) {
+    const int mid = (lo + hi + 1) >> 1;
+    if (bound[mid] <= pos) lo = mid; else hi = mid - 1;
+  }
+  return lo;
+}
+
+// ---------------------------------------------------------------------------------------------
+// duplicate filter, step 2: flag the occurrences whose hashed counter is > 1 and collect them
+// ---------------------------------------------------------------------------------------------
+template <typename idx_t>
+__global__ void __launch_bounds__(256) emb_classify_kernel(const __grid_constant__ EmbBwdParams P, int num_tables,
+                                                           long long total_hint, const unsigned* filter,
+                                                           int log2_size, unsigned char* flags, int* suspects,
+                                                           int* n_suspects) {
+  __shared__ long long bound[DLRM_B200_MAX_TABLES_PER_CALL + 1];
+  load_bounds<idx_t>(bound, P, num_tables, total_hint);
+  const int lane = threadIdx.x & 31;
+  const long long first = bound[0], total = bound[num_tables];
+  const long long warp0 = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const long long wstride = (long long)gridDim.x * (blockDim.x >> 5);
+  for (long long base = first + warp0 * 32; base < total; base += wstride * 32) {
+    const long long pos = base + lane;
+    bool susp = false;
+    if (pos < total) {
+      const EmbBwdTable& tb = P.t[table_of(bound, num_tables, pos)];
+      const long long r = static_cast<const idx_t*>(tb.idx)[pos - tb.pair_base];
+      susp = filter[filter_slot(tb.head + r, log2_size)] > 1u;
+      flags[pos] = susp ? 1 : 0;
+    }
+    const unsigned m = __ballot_sync(0xffffffffu, susp);
+    if (m) {
+      int slot0 = 0;
+      if (lane == 0) slot0 = atomicAdd(n_suspects, __popc(m));
+      slot0 = __shfl_sync(0xffffffffu, slot0, 0);
+      if (susp) suspects[slot0 + __popc(m & ((1u << lane) - 1u))] = (int)pos;
+    }
+  }
+}
+
+// step 3: thread ONLY the suspects onto the per-row lists (link[pos].x; .y = bag was written by the gather)
+template <typename idx_t>
+__global__ void __launch_bounds__(256) emb_link_suspects_kernel(const __grid_constant__ EmbBwdParams P,
+                                                                int num_tables, long long total_hint,
+                                                                const int* suspects, const int* n_suspects) {
+  __shared__ long long bound[DLRM_B200_MAX_TABLES_PER_CALL + 1];
+  load_bounds<idx_t>(bound, P, num_tables, total_hint);
+  const int n = *n_suspects;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const long long pos = suspects[i];
+    const EmbBwdTable& tb = P.t[table_of(bound, num_tables, pos)];
+    const long long r = static_cast<const idx_t*>(tb.idx)[pos - tb.pair_base];
+    P.link[pos].x = atomicExch(tb.head + r, (int)(pos + 1));
+  }
+}
+
+// Occurrence-centric: a warp takes 32 consecutive index positions (all tables share one global
+// position space: reference format = per-table arrays + pair_base, packed format = one array),
+// reads index / link / head with coalesced + gathered loads, and processes the rows it owns with
+// up to PF weight rows AND their dY rows in flight.  The bag of an occurrence comes from link[],
+// so the offsets are not needed (packed format reads only the per-table bounds).
+template <int W, int NV, typename idx_t>
+__global__ void __launch_bounds__(256, NV == 1 ? 3 : 1) emb_update_kernel(const __grid_constant__ EmbBwdParams P,
+                                                                          int num_tables, long long total_hint) {
+  __shared__ long long bound[DLRM_B200_MAX_TABLES_PER_CALL + 1];
+  load_bounds<idx_t>(bound, P, num_tables, total_hint);
   const int D = P.dim;
   const int lane = threadIdx.x & 31;
   const long long first = bound[0], total = bound[num_tables];
@@ -154,26 +221,22 @@ __global__ void __launch_bounds__(256, NV == 1 ? 3 : 1) emb_update_kernel(const 
   for (long long base = first + warp0 * 32; base < total; base += wstride * 32) {
     const long long pos = base + lane;
     const bool valid = pos < total;
-    // table of this position: largest k with bound[k] <= pos (empty tables share a bound)
-    int k = 0;
-    {
-      int lo = 0, hi = num_tables - 1;
-      while (lo < hi) {
-        const int mid = (lo + hi + 1) >> 1;
-        if (bound[mid] <= pos) lo = mid; else hi = mid - 1;
-      }
-      k = lo;
-    }
+    const int k = table_of(bound, num_tables, pos);
     long long my_r = 0;
     int my_head = 0;
     int2 my_link = make_int2(0, 0);
+    bool my_susp = true;
     if (valid) {
       const EmbBwdTable& tb = P.t[k];
       my_r = static_cast<const idx_t*>(tb.idx)[pos - tb.pair_base];
       my_link = P.link[pos];
-      my_head = tb.head[my_r];
+      if (P.flags) my_susp = P.flags[pos] != 0;
+      // an unflagged occurrence is the only one of its row: it owns the row, head[] is never touched
+      my_head = my_susp ? tb.head[my_r] : (int)(pos + 1);
+      if (!my_susp) my_link.x = 0;
     }
     const unsigned owners = __ballot_sync(0xffffffffu, valid && my_head == (int)(pos + 1));
+    const unsigned susp_mask = __ballot_sync(0xffffffffu, my_susp);
     for (int u0 = 0; u0 < 32; u0 += PF) {
       if (((owners >> u0) & ((1u << PF) - 1u)) == 0u) continue;
       Pack<W> wpf[PF][NV], gpf[PF][NV];
@@ -277,7 +340,7 @@ __global__ void __launch_bounds__(256, NV == 1 ? 3 : 1) emb_update_kernel(const 
               st_pack<W>(wrow + lane * W + v * 32 * W, w[v]);
             }
         }
-        if (lane == 0) tb.head[r] = 0;
+        if (lane == 0 && ((susp_mask >> src) & 1u)) tb.head[r] = 0;
       }
     }
   }
@@ -336,7 +399,7 @@ static int emb_update_impl(const dlrm_emb_bwd_table_t* tables, int num_tables, i
                            int idx_bytes, int include_last, const int32_t* next, const float* dY,
                            int64_t dy_stride_sample, int64_t dy_stride_table, int optimizer, float lr,
                            float eps, void* stream, const float* const* peer_dY, int world,
-                           int64_t batch_local) {
+                           int64_t batch_local, const dlrm_emb_dedup_t* dedup) {
   using namespace dlrm;
   EmbBwdParams P{};
   if (int rc = fill_params(P, tables, num_tables, "emb_bwd_update")) return rc;
@@ -347,6 +410,7 @@ static int emb_update_impl(const dlrm_emb_bwd_table_t* tables, int num_tables, i
   if (num_tables == 0 || batch == 0) return 0;
   if (!next || (!dY && !peer_dY)) return set_error("emb_bwd_update: NULL next/dY");
   bool vec = (dim % 4 == 0) && (peer_dY || aligned16(dY)) && dy_stride_sample % 4 == 0 && dy_stride_table % 4 == 0;
+  P.flags = (dedup && dedup->flags) ? dedup->flags : nullptr;
   P.peer_batch = 0;
   for (int d = 0; d < DLRM_B200_MAX_PEERS; ++d) P.peer_dY[d] = nullptr;
   if (peer_dY) {
@@ -421,9 +485,54 @@ extern "C" int dlrm_b200_emb_bwd_update(const dlrm_emb_bwd_table_t* tables, int 
                                         int64_t batch, int idx_bytes, int include_last,
                                         const int32_t* next, const float* dY,
                                         int64_t dy_stride_sample, int64_t dy_stride_table,
-                                        int optimizer, float lr, float eps, void* stream) {
+                                        int optimizer, float lr, float eps, const dlrm_emb_dedup_t* dedup,
+                                        void* stream) {
   return emb_update_impl(tables, num_tables, dim, batch, idx_bytes, include_last, next, dY, dy_stride_sample,
-                         dy_stride_table, optimizer, lr, eps, stream, nullptr, 0, 0);
+                         dy_stride_table, optimizer, lr, eps, stream, nullptr, 0, 0, dedup);
+}
+
+extern "C" int dlrm_b200_emb_bwd_classify(const dlrm_emb_bwd_table_t* tables, int num_tables, int64_t batch,
+                                          int idx_bytes, int include_last, int32_t* next,
+                                          const dlrm_emb_dedup_t* dedup, void* stream) {
+  using namespace dlrm;
+  EmbBwdParams P{};
+  if (int rc = fill_params(P, tables, num_tables, "emb_bwd_classify")) return rc;
+  if (idx_bytes != 4 && idx_bytes != 8) return set_error("emb_bwd_classify: idx_bytes=%d", idx_bytes);
+  if (!dedup || !dedup->filter || !dedup->flags || !dedup->suspects || !next)
+    return set_error("emb_bwd_classify: NULL dedup buffers");
+  if (num_tables == 0 || batch == 0) return 0;
+  P.link = reinterpret_cast<int2*>(next);
+  P.batch = batch;
+  P.include_last = include_last;
+  long long total = 0;
+  for (int k = 0; k < num_tables; ++k) total += tables[k].nnz;
+  if (include_last) {
+    total = 0;
+    for (int k = 0; k < num_tables; ++k) total = tables[k].nnz > total ? tables[k].nnz : total;
+  }
+  if (total == 0) return 0;
+  const long long total_hint = include_last ? 0 : (tables[num_tables - 1].pair_base + tables[num_tables - 1].nnz);
+  int dev = 0, sms = 0;
+  DLRM_CUDA(cudaGetDevice(&dev));
+  DLRM_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  long long gridx = (total / 32 + 7) / 8;
+  if (gridx > (long long)sms * 8) gridx = (long long)sms * 8;
+  if (gridx < 1) gridx = 1;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  int* n_susp = reinterpret_cast<int*>(dedup->filter + ((size_t)1 << dedup->log2_size));
+  if (idx_bytes == 8) {
+    emb_classify_kernel<long long><<<(unsigned)gridx, 256, 0, st>>>(P, num_tables, total_hint, dedup->filter,
+                                                                    dedup->log2_size, dedup->flags, dedup->suspects, n_susp);
+    DLRM_CHECK_LAUNCH("emb_classify_kernel");
+    emb_link_suspects_kernel<long long><<<sms, 256, 0, st>>>(P, num_tables, total_hint, dedup->suspects, n_susp);
+  } else {
+    emb_classify_kernel<int><<<(unsigned)gridx, 256, 0, st>>>(P, num_tables, total_hint, dedup->filter,
+                                                              dedup->log2_size, dedup->flags, dedup->suspects, n_susp);
+    DLRM_CHECK_LAUNCH("emb_classify_kernel");
+    emb_link_suspects_kernel<int><<<sms, 256, 0, st>>>(P, num_tables, total_hint, dedup->suspects, n_susp);
+  }
+  DLRM_CHECK_LAUNCH("emb_link_suspects_kernel");
+  return 0;
 }
 
 extern "C" int dlrm_b200_emb_bwd_update_p2p(const dlrm_emb_bwd_table_t* tables, int num_tables, int dim,
@@ -431,9 +540,9 @@ extern "C" int dlrm_b200_emb_bwd_update_p2p(const dlrm_emb_bwd_table_t* tables, 
                                             const int32_t* next, const float* const* peer_dY, int world,
                                             int64_t batch_local, int64_t dy_stride_sample,
                                             int64_t dy_stride_table, int optimizer, float lr, float eps,
-                                            void* stream) {
+                                            const dlrm_emb_dedup_t* dedup, void* stream) {
   if (!peer_dY) return dlrm::set_error("emb_bwd_update_p2p: peer_dY is NULL");
   return emb_update_impl(tables, num_tables, dim, batch_global, idx_bytes, include_last, next, nullptr,
                          dy_stride_sample, dy_stride_table, optimizer, lr, eps, stream, peer_dY, world,
-                         batch_local);
+                         batch_local, dedup);
 }

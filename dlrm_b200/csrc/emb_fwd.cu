@@ -37,7 +37,20 @@ struct EmbFwdParams {
   // into that rank's buffer through peer-mapped memory (NVLink store).  peer_batch == 0: local output.
   float* peer_out[DLRM_B200_MAX_PEERS];
   long long peer_batch;
+  unsigned* filter;   // training with a duplicate filter: count instead of linking
+  int filter_log2;
 };
+
+// training: either thread the occurrence onto its row's list (returns the previous head) or, with a
+// duplicate filter, just bump the row's hashed counter (no return value -> RED, nothing to wait for)
+__device__ __forceinline__ int note_occurrence(const EmbFwdParams& P, const EmbFwdTable& tb, long long row,
+                                               long long pos_local) {
+  if (P.filter) {
+    atomicAdd(P.filter + filter_slot(tb.head + row, P.filter_log2), 1u);
+    return 0;
+  }
+  return atomicExch(tb.head + row, (int)(tb.pair_base + pos_local + 1));
+}
 
 __device__ __forceinline__ float* out_row(const EmbFwdParams& P, long long b) {
   if (P.peer_batch > 0) {
@@ -47,14 +60,7 @@ __device__ __forceinline__ float* out_row(const EmbFwdParams& P, long long b) {
   return P.out + b * P.stride_sample;
 }
 
-// Fused "link" step of the sort-free coalesce (emb_bwd.cu): thread the occurrence at position j
-// of this table onto the per-row list while its index is already in a register.
-__device__ __forceinline__ void link_occurrence(const EmbFwdTable& tb, int2* link, long long j,
-                                                long long row, long long bag) {
-  const long long pos = tb.pair_base + j;
-  const int prev = atomicExch(tb.head + row, (int)(pos + 1));
-  link[pos] = make_int2(prev, (int)bag);
-}
+
 
 template <typename idx_t>
 __device__ __forceinline__ long long bag_end(const idx_t* off, long long b, long long batch,
@@ -100,7 +106,7 @@ __global__ void __launch_bounds__(256, (G == 32 && NV == 1) ? 4 : 1) emb_fwd_vec
     // first index chunk of bag 0 (+ fused link: the atomic's result is only stored after the rows)
     long long my_row = (start + gl < end) ? (long long)idx[start + gl] : 0;
     int my_prev = 0;
-    if (LINK && start + gl < end) my_prev = atomicExch(tb.head + my_row, (int)(tb.pair_base + start + gl + 1));
+    if (LINK && start + gl < end) my_prev = note_occurrence(P, tb, my_row, start + gl);
 
     for (int s = 0; s < nb; ++s) {
       // prefetch boundaries + first index chunk of the next bag
@@ -111,7 +117,7 @@ __global__ void __launch_bounds__(256, (G == 32 && NV == 1) ? 4 : 1) emb_fwd_vec
         nend = __shfl_sync(gmask, my_bound, s + 2, G);
         next_row = (nstart + gl < nend) ? (long long)idx[nstart + gl] : 0;
         if (LINK && nstart + gl < nend)
-          next_prev = atomicExch(tb.head + next_row, (int)(tb.pair_base + nstart + gl + 1));
+          next_prev = note_occurrence(P, tb, next_row, nstart + gl);
       }
       float4 acc[NV];
 #pragma unroll
@@ -120,7 +126,7 @@ __global__ void __launch_bounds__(256, (G == 32 && NV == 1) ? 4 : 1) emb_fwd_vec
       for (int j0 = start; j0 < end; j0 += G) {
         if (j0 != start) {
           my_row = (j0 + gl < end) ? (long long)idx[j0 + gl] : 0;
-          if (LINK && j0 + gl < end) my_prev = atomicExch(tb.head + my_row, (int)(tb.pair_base + j0 + gl + 1));
+          if (LINK && j0 + gl < end) my_prev = note_occurrence(P, tb, my_row, j0 + gl);
         }
         const int n = min(G, end - j0);
         for (int jj = 0; jj < n; jj += U) {
@@ -190,7 +196,7 @@ __global__ void emb_fwd_scalar_kernel(const __grid_constant__ EmbFwdParams P) {
   float acc = 0.f;
   for (long long j = start; j < end; ++j) {
     const long long r = idx[j];
-    if (LINK && d == 0) link_occurrence(tb, P.link, j, r, b);
+    if (LINK && d == 0) P.link[tb.pair_base + j] = make_int2(note_occurrence(P, tb, r, j), (int)b);
     const float x = tb.w[r * D + d];
     acc = WEIGHTED ? fmaf(tb.rw[r], x, acc) : acc + x;
   }
@@ -244,7 +250,7 @@ static int emb_fwd_impl(const dlrm_emb_fwd_table_t* tables, const dlrm_emb_bwd_t
                         int32_t* link, int num_tables, int dim, int64_t batch, int idx_bytes,
                         int include_last, float* out, int64_t out_stride_sample,
                         int64_t out_stride_table, void* stream, float* const* peer_out = nullptr,
-                        int world = 0, int64_t batch_local = 0) {
+                        int world = 0, int64_t batch_local = 0, const dlrm_emb_dedup_t* dedup = nullptr) {
   using namespace dlrm;
   if (num_tables < 0 || num_tables > DLRM_B200_MAX_TABLES_PER_CALL)
     return set_error("emb_bag_fwd: num_tables=%d out of range [0,%d]", num_tables,
@@ -286,6 +292,14 @@ static int emb_fwd_impl(const dlrm_emb_fwd_table_t* tables, const dlrm_emb_bwd_t
   P.include_last = include_last;
   P.bags_per_group = 1;
   P.link = reinterpret_cast<int2*>(link);
+  P.filter = nullptr;
+  P.filter_log2 = 0;
+  if (train && dedup && dedup->filter) {
+    if (dedup->log2_size < 10 || dedup->log2_size > 30)
+      return set_error("emb_bag_fwd_train: dedup log2_size=%d out of range [10,30]", dedup->log2_size);
+    P.filter = dedup->filter;
+    P.filter_log2 = dedup->log2_size;
+  }
   P.peer_batch = 0;
   for (int d = 0; d < DLRM_B200_MAX_PEERS; ++d) P.peer_out[d] = nullptr;
   if (peer_out) {
@@ -325,18 +339,20 @@ extern "C" int dlrm_b200_emb_bag_fwd_train(const dlrm_emb_fwd_table_t* tables,
                                            const dlrm_emb_bwd_table_t* train, int num_tables, int dim,
                                            int64_t batch, int idx_bytes, int include_last, int32_t* next,
                                            float* out, int64_t out_stride_sample,
-                                           int64_t out_stride_table, void* stream) {
+                                           int64_t out_stride_table, const dlrm_emb_dedup_t* dedup,
+                                           void* stream) {
   if (!train) return dlrm::set_error("emb_bag_fwd_train: train descriptors are NULL");
   return emb_fwd_impl(tables, train, next, num_tables, dim, batch, idx_bytes, include_last, out,
-                      out_stride_sample, out_stride_table, stream);
+                      out_stride_sample, out_stride_table, stream, nullptr, 0, 0, dedup);
 }
 
 extern "C" int dlrm_b200_emb_bag_fwd_p2p(const dlrm_emb_fwd_table_t* tables,
                                          const dlrm_emb_bwd_table_t* train, int num_tables, int dim,
                                          int64_t batch_global, int idx_bytes, int include_last, int32_t* next,
                                          float* const* peer_out, int world, int64_t batch_local,
-                                         int64_t out_stride_sample, int64_t out_stride_table, void* stream) {
+                                         int64_t out_stride_sample, int64_t out_stride_table,
+                                         const dlrm_emb_dedup_t* dedup, void* stream) {
   if (!peer_out) return dlrm::set_error("emb_bag_fwd_p2p: peer_out is NULL");
   return emb_fwd_impl(tables, train, next, num_tables, dim, batch_global, idx_bytes, include_last, nullptr,
-                      out_stride_sample, out_stride_table, stream, peer_out, world, batch_local);
+                      out_stride_sample, out_stride_table, stream, peer_out, world, batch_local, dedup);
 }

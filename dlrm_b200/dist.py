@@ -180,16 +180,28 @@ class DistEngine:
             e._ensure_link(sp.nnz_total if sp.include_last else sum(int(i.numel()) for i in sp.indices))
         desc = e._fwd_desc(sp, range(self.Tl))
         bdesc = e._bwd_desc_chunk(sp, list(range(self.Tl)))[0] if link else None
+        import ctypes as C
+
+        filt = link and e.use_filter
+        if filt:
+            e.filter.zero_()
         _lib.check(e.lib.dlrm_b200_emb_bag_fwd_p2p(desc, bdesc, self.Tl, self.D, sp.batch, sp.idx_bytes,
                                                    int(sp.include_last), e.link.data_ptr() if link else None,
-                                                   self._peer_T, self.world, self.B, FD, self.D, _stream()),
+                                                   self._peer_T, self.world, self.B, FD, self.D,
+                                                   C.byref(e.dedup) if filt else None, _stream()),
                    "emb_bag_fwd_p2p")
         e.n_launch += 1
+        if link:
+            e._filtered = filt
+            if filt:
+                e.emb_classify(sp)
         self._barrier()       # every rank's pooled rows have landed in every T
 
     def _update_p2p(self, sp, optimizer, clr):
         from . import _lib
         from .engine import _OPT, _stream
+
+        import ctypes as C
 
         e = self.eng
         self._barrier()       # every rank's dT is complete
@@ -198,7 +210,8 @@ class DistEngine:
         _lib.check(e.lib.dlrm_b200_emb_bwd_update_p2p(bdesc, self.Tl, self.D, sp.batch, sp.idx_bytes,
                                                       int(sp.include_last), e.link.data_ptr(), self._peer_dT,
                                                       self.world, self.B, FD, self.D, _OPT[optimizer], clr,
-                                                      1e-10, _stream()), "emb_bwd_update_p2p")
+                                                      1e-10, C.byref(e.dedup) if e._filtered else None, _stream()),
+                   "emb_bwd_update_p2p")
         e.n_launch += 1
 
     # -- forward: pool local tables for the global batch, exchange, land in T

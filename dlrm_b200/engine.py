@@ -175,11 +175,25 @@ class Engine:
         self.loss_buf = torch.zeros(1, dtype=f32, device=dev)
         self.scratch = torch.zeros(1024, dtype=f32, device=dev)
         self.link = None  # int32 [2 * nnz capacity]
+        self.dedup, self._filtered = None, False
+        # duplicate filter for the training gather / update (one suspect list per call: <= 64 tables)
+        self.use_filter = self.T <= _lib.MAX_TABLES
 
     def _ensure_link(self, nnz_total: int):
         if self.link is None or self.link.numel() < 2 * nnz_total:
             cap = max(2 * nnz_total, 1024)
             self.link = torch.empty(cap, dtype=torch.int32, device=self.device)
+            # duplicate filter (see include/dlrm_b200.h, dlrm_emb_dedup_t): ~8 hashed counters per occurrence
+            n = max(nnz_total, 512)
+            log2 = max(16, int(np.ceil(np.log2(8 * n))))
+            self.filter = torch.zeros((1 << log2) + 4, dtype=torch.int32, device=self.device)
+            self.flags = torch.zeros(n, dtype=torch.uint8, device=self.device)
+            self.suspects = torch.zeros(n, dtype=torch.int32, device=self.device)
+            d = _lib.EmbDedup()
+            d.filter, d.log2_size = self.filter.data_ptr(), log2
+            d.flags, d.suspects = self.flags.data_ptr(), self.suspects.data_ptr()
+            self.dedup = d
+        self._filtered = False
 
     def table(self, k: int) -> torch.Tensor:
         return self.tables[int(self.row_base[k]):int(self.row_base[k + 1])]
@@ -282,15 +296,21 @@ class Engine:
             optr = out.data_ptr() + c0 * stride_table * 4
             if link:
                 bdesc, _ = self._bwd_desc_chunk(sp, ks)
+                dd = C.byref(self.dedup) if self.use_filter else None
+                if self.use_filter and c0 == 0:
+                    self.filter.zero_()     # counters + suspect count
                 chk(self.lib.dlrm_b200_emb_bag_fwd_train(desc, bdesc, len(ks), self.D, sp.batch, sp.idx_bytes,
                                                          int(sp.include_last), self.link.data_ptr(), optr,
-                                                         stride_sample, stride_table, _stream()),
+                                                         stride_sample, stride_table, dd, _stream()),
                     "emb_bag_fwd_train")
+                self._filtered = self.use_filter
             else:
                 chk(self.lib.dlrm_b200_emb_bag_fwd(desc, len(ks), self.D, sp.batch, sp.idx_bytes,
                                                    int(sp.include_last), optr, stride_sample, stride_table,
                                                    _stream()), "emb_bag_fwd")
             self.n_launch += 1
+        if link and self.use_filter:
+            self.emb_classify(sp)
 
     def mlp_forward(self, which: str, x: torch.Tensor, ldx: int, B: int, outs: List[torch.Tensor],
                     lds: List[int], upto: Optional[int] = None):
@@ -398,6 +418,16 @@ class Engine:
             self._tc_prepare(B)
         torch.cuda.synchronize()
 
+    def emb_classify(self, sp: SparseInput):
+        """After a filtered training gather (counters still L2-hot): flag suspects, link only those."""
+        for c0 in range(0, self.T, _lib.MAX_TABLES):
+            ks = list(range(c0, min(self.T, c0 + _lib.MAX_TABLES)))
+            desc, _ = self._bwd_desc_chunk(sp, ks)
+            _lib.check(self.lib.dlrm_b200_emb_bwd_classify(desc, len(ks), sp.batch, sp.idx_bytes,
+                                                           int(sp.include_last), self.link.data_ptr(),
+                                                           C.byref(self.dedup), _stream()), "emb_bwd_classify")
+            self.n_launch += 2
+
     def emb_link(self, sp: SparseInput):
         """Thread this batch's (table,row) occurrences onto per-row lists.  Indices only: may be
         issued on a side stream, concurrently with the forward pass."""
@@ -410,6 +440,7 @@ class Engine:
                                                        int(sp.include_last), self.link.data_ptr(),
                                                        _stream()), "emb_bwd_link")
             self.n_launch += 1
+        self._filtered = False
 
     def _bwd_desc_chunk(self, sp, ks):
         # pair_base must be global over ALL tables of the batch, not per chunk
@@ -428,7 +459,8 @@ class Engine:
                                                          int(sp.include_last), self.link.data_ptr(),
                                                          dY.data_ptr() + c0 * stride_table * 4,
                                                          stride_sample, stride_table, _OPT[optimizer],
-                                                         lr, eps, _stream()), "emb_bwd_update")
+                                                         lr, eps, C.byref(self.dedup) if self._filtered else None,
+                                                         _stream()), "emb_bwd_update")
             self.n_launch += 1
 
     def mlp_backward(self, which: str, x_in: torch.Tensor, ldx: int, in_act: int, B: int,

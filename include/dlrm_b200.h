@@ -98,13 +98,36 @@ typedef struct {
   int64_t pair_base;    /* first slot of this table in next[] / (sum of nnz of earlier tables) */
 } dlrm_emb_bwd_table_t;
 
+/* Optional duplicate filter (dlrm_emb_dedup_t): at 1e6-row tables almost every row of a batch is
+ * touched once, and the 4-byte random accesses to head[] cost as much HBM time as the 512-byte rows.
+ * With a filter the training gather only bumps a counter in an L2-sized hashed array
+ * (fire-and-forget RED), dlrm_b200_emb_bwd_classify() -- right after the gather, while the
+ * counters are L2-hot -- marks the occurrences whose counter is > 1 as suspects (hash collisions
+ * only add false suspects) and threads ONLY those onto the per-row lists; the update kernel then
+ * treats unflagged occurrences as sole owners of their row without touching head[] or link[].x.
+ *   filter   : uint32 [2^log2_size + 1], zeroed by the caller before every training gather
+ *              (the last element is the suspect counter)
+ *   flags    : uint8  [nnz capacity]   suspects : int32 [nnz capacity]
+ * dedup == NULL everywhere: every occurrence is linked (the original scheme). */
+typedef struct {
+  uint32_t* filter;
+  int32_t log2_size;
+  uint8_t* flags;
+  int32_t* suspects;
+} dlrm_emb_dedup_t;
+
 /* Training forward: the gather of dlrm_b200_emb_bag_fwd AND step 1 (link) in the same launch --
  * the index of every occurrence is already in a register, so linking costs one atomicExch. */
 int dlrm_b200_emb_bag_fwd_train(const dlrm_emb_fwd_table_t* tables /*[host]*/,
                                 const dlrm_emb_bwd_table_t* train /*[host]*/, int num_tables, int dim,
                                 int64_t batch, int idx_bytes, int include_last, int32_t* next,
                                 float* out, int64_t out_stride_sample, int64_t out_stride_table,
-                                void* stream);
+                                const dlrm_emb_dedup_t* dedup /*[host] or NULL*/, void* stream);
+
+/* After a filtered training gather: flag suspects and link them (two small launches). */
+int dlrm_b200_emb_bwd_classify(const dlrm_emb_bwd_table_t* tables /*[host]*/, int num_tables,
+                               int64_t batch, int idx_bytes, int include_last, int32_t* next,
+                               const dlrm_emb_dedup_t* dedup /*[host]*/, void* stream);
 
 int dlrm_b200_emb_bwd_link(const dlrm_emb_bwd_table_t* tables /*[host]*/, int num_tables,
                            int64_t batch, int idx_bytes, int include_last,
@@ -114,7 +137,7 @@ int dlrm_b200_emb_bwd_update(const dlrm_emb_bwd_table_t* tables /*[host]*/, int 
                              int64_t batch, int idx_bytes, int include_last,
                              const int32_t* next, const float* dY, int64_t dy_stride_sample,
                              int64_t dy_stride_table, int optimizer, float lr, float eps,
-                             void* stream);
+                             const dlrm_emb_dedup_t* dedup /*[host] or NULL*/, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * Table-wise sharded runs (replaces extend_distributed.alltoall, extend_distributed.py:389-486, and
@@ -129,12 +152,14 @@ int dlrm_b200_emb_bag_fwd_p2p(const dlrm_emb_fwd_table_t* tables /*[host]*/,
                               const dlrm_emb_bwd_table_t* train /*[host] or NULL*/, int num_tables, int dim,
                               int64_t batch_global, int idx_bytes, int include_last, int32_t* next,
                               float* const* peer_out /*[host][world]*/, int world, int64_t batch_local,
-                              int64_t out_stride_sample, int64_t out_stride_table, void* stream);
+                              int64_t out_stride_sample, int64_t out_stride_table,
+                              const dlrm_emb_dedup_t* dedup /*[host] or NULL*/, void* stream);
 int dlrm_b200_emb_bwd_update_p2p(const dlrm_emb_bwd_table_t* tables /*[host]*/, int num_tables, int dim,
                                  int64_t batch_global, int idx_bytes, int include_last, const int32_t* next,
                                  const float* const* peer_dY /*[host][world]*/, int world,
                                  int64_t batch_local, int64_t dy_stride_sample, int64_t dy_stride_table,
-                                 int optimizer, float lr, float eps, void* stream);
+                                 int optimizer, float lr, float eps,
+                                 const dlrm_emb_dedup_t* dedup /*[host] or NULL*/, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * apply_mlp layer (dlrm_s_pytorch.py:399-405: nn.Linear -> addmm, + ReLU / Sigmoid modules)

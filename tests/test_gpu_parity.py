@@ -179,10 +179,11 @@ def test_train_steps_vs_reference_golden(name, opt):
 
 
 # ----------------------------------------------------------------------------- sparse update kernel
+@pytest.mark.parametrize("filtered", [False, True])
 @pytest.mark.parametrize("opt", ["sgd", "rwsadagrad"])
 @pytest.mark.parametrize("D,rows,B,lmax", [(128, 50, 300, 10), (128, 3, 400, 3), (16, 40, 100, 8),
-                                            (6, 10, 50, 4), (256, 1000, 64, 20)])
-def test_emb_update_with_duplicates(opt, D, rows, B, lmax):
+                                            (6, 10, 50, 4), (256, 1000, 64, 20), (128, 200000, 256, 10)])
+def test_emb_update_with_duplicates(opt, D, rows, B, lmax, filtered):
     """Heavy duplication (few rows, many bags): coalesce + optimizer vs the oracle
     (optim/rwsadagrad.py:117-143 restated).  Lists longer than 32 exercise the chunked path."""
     from dlrm_b200.engine import Engine, sparse_from_reference
@@ -202,7 +203,12 @@ def test_emb_update_with_duplicates(opt, D, rows, B, lmax):
     if opt == "rwsadagrad":
         for k in range(2):
             e.momentum[int(e.row_base[k]):int(e.row_base[k + 1])].copy_(torch.from_numpy(mom[k]))
-    e.emb_link(sp)
+    if filtered:   # training gather with the duplicate filter + classify (suspects only are linked)
+        scratch = torch.empty((B, 3, D), device=DEV)
+        e.emb_forward(sp, scratch.view(-1)[D:], 3 * D, D, link=True)
+        assert e._filtered
+    else:          # every occurrence linked (stand-alone link kernel)
+        e.emb_link(sp)
     e.emb_update(sp, e.dT.view(-1)[D:], 3 * D, D, opt, 0.05)
     torch.cuda.synchronize()
     assert int(e.head.abs().sum().item()) == 0
