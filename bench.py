@@ -384,7 +384,7 @@ def main():
     ap.add_argument("--ring", type=int, default=16)
     ap.add_argument("--gemm", default="tc", choices=["tc", "tc_bf16", "simt"])
     ap.add_argument("--no-graph", action="store_true")
-    ap.add_argument("--exchange", default="p2p", choices=["p2p", "nccl"],
+    ap.add_argument("--exchange", default="nccl", choices=["p2p", "nccl"],
                     help="N>1: pooled-vector exchange fused into the kernels over peer memory, or NCCL all-to-all")
     ap.add_argument("--cpu-budget", type=float, default=15.0)
     ap.add_argument("--no-cpu", action="store_true")

@@ -145,28 +145,58 @@ class DistEngine:
         from torch.multiprocessing.reductions import reduce_tensor
 
         e = self.eng
-        mine = (reduce_tensor(e.Tbuf), reduce_tensor(e.dT))
+        e._tc_prepare(self.B)    # final allocation of the dense-gradient arena (split-K slabs)
+        self._sig = torch.zeros(16, dtype=torch.int32, device=self.device)    # barrier slots, one per rank
+        self._epoch = torch.zeros(1, dtype=torch.int32, device=self.device)
+        torch.cuda.synchronize()
+        mine = tuple(reduce_tensor(t) for t in (e.Tbuf, e.dT, self._sig, e.dense_grad))
         allh = [None] * self.world
         dist.all_gather_object(allh, mine)
         self._peer_keep = []
-        pT, pdT = [], []
+        pT, pdT, psig, pgrad = [], [], [], []
         col = (1 + self.t0) * self.D * 4
         for r in range(self.world):
             if r == self.rank:
-                t, g = e.Tbuf, e.dT
+                t, g, sg, dg = e.Tbuf, e.dT, self._sig, e.dense_grad
             else:
-                (fT, aT), (fG, aG) = allh[r]
-                t, g = fT(*aT), fG(*aG)
-            self._peer_keep += [t, g]
+                t, g, sg, dg = (fn(*args) for fn, args in allh[r])
+            self._peer_keep += [t, g, sg, dg]
             pT.append(t.data_ptr() + col)
             pdT.append(g.data_ptr() + col)
-        self._peer_T = (C.c_void_p * self.world)(*pT)
-        self._peer_dT = (C.c_void_p * self.world)(*pdT)
+            psig.append(sg.data_ptr())
+            pgrad.append(dg.data_ptr())
+        W = self.world
+        self._peer_T = (C.c_void_p * W)(*pT)
+        self._peer_dT = (C.c_void_p * W)(*pdT)
+        self._peer_sig = (C.c_void_p * W)(*psig)
+        self._peer_grad = (C.c_void_p * W)(*pgrad)
+        self.own_sync = os.environ.get("DLRM_P2P_NCCL_SYNC") != "1"   # our kernels instead of NCCL all_reduce
+        if self.own_sync:
+            e.dense_sync_fn = self._dense_sync_p2p
         dist.barrier()
 
     def _barrier(self):
         """Device-side ordering across ranks on the current stream (no host sync)."""
-        dist.all_reduce(self._flag)
+        if getattr(self, "own_sync", False):
+            from . import _lib
+            from .engine import _stream
+
+            _lib.check(self.eng.lib.dlrm_b200_p2p_barrier(self._peer_sig, self.rank, self.world,
+                                                          self._epoch.data_ptr(), _stream()), "p2p_barrier")
+            self.eng.n_launch += 1
+        else:
+            dist.all_reduce(self._flag)
+
+    def _dense_sync_p2p(self):
+        """Mean of the dense gradients over the ranks with our own two-shot all-reduce over NVLink."""
+        from . import _lib
+        from .engine import _stream
+
+        self._barrier()       # every rank's gradient arena is complete
+        _lib.check(self.eng.lib.dlrm_b200_p2p_allreduce_mean(self._peer_grad, self.rank, self.world,
+                                                             self.eng.dense_numel, _stream()), "p2p_allreduce_mean")
+        self.eng.n_launch += 1
+        self._barrier()       # every slice has been written back everywhere
 
     def _gather_p2p(self, sp, link):
         from . import _lib
@@ -281,7 +311,7 @@ def bench_main(args, CFG, metric_name, config_dict, ClockSampler):
     ln_emb = [CFG["rows"]] * T
     ln_top = [D + (T + 1) * T // 2] + CFG["top_tail"]
     de = DistEngine(D, ln_emb, CFG["ln_bot"], ln_top, local_batch=B, device=dev, gemm=args.gemm,
-                    exchange=getattr(args, "exchange", "p2p"))
+                    exchange=getattr(args, "exchange", "nccl"))
     de.eng.init_params(100 + rank)
     de.sync_dense_params_from_rank0()
     de.eng.ensure_optimizer_state("rwsadagrad")
@@ -299,7 +329,10 @@ def bench_main(args, CFG, metric_name, config_dict, ClockSampler):
     Xs = ring[0][3].clone()
     Ts = ring[0][5].clone()
     graph = None
-    if not getattr(args, "no_graph", False):
+    # capturing NCCL collectives into a CUDA graph hangs on this stack (r7: torch 2.11 / NCCL 2.28):
+    # the sharded step runs eagerly unless DLRM_DIST_GRAPH=1 asks for the experiment
+    want_graph = (de.exchange == "p2p" and getattr(de, "own_sync", False)) or os.environ.get("DLRM_DIST_GRAPH") == "1"
+    if want_graph and not getattr(args, "no_graph", False):
         from .engine import GraphedTrainStep
 
         try:

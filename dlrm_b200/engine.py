@@ -176,8 +176,11 @@ class Engine:
         self.scratch = torch.zeros(1024, dtype=f32, device=dev)
         self.link = None  # int32 [2 * nnz capacity]
         self.dedup, self._filtered = None, False
-        # duplicate filter for the training gather / update (one suspect list per call: <= 64 tables)
-        self.use_filter = self.T <= _lib.MAX_TABLES
+        # Optional duplicate filter for the training gather / update (dlrm_emb_dedup_t).  Measured on B200
+        # (profiles/, r8): it removes the list-head traffic from the update but adds a memset + two small
+        # launches to the gather side and the update time does not move (110 us in-step either way: the
+        # row read-modify-write and the momentum accesses dominate), so it is OFF by default.
+        self.use_filter = False
 
     def _ensure_link(self, nnz_total: int):
         if self.link is None or self.link.numel() < 2 * nnz_total:

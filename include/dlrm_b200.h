@@ -161,6 +161,16 @@ int dlrm_b200_emb_bwd_update_p2p(const dlrm_emb_bwd_table_t* tables /*[host]*/, 
                                  int optimizer, float lr, float eps,
                                  const dlrm_emb_dedup_t* dedup /*[host] or NULL*/, void* stream);
 
+/* NCCL-free cross-GPU steps over the same peer mappings (graph-capturable):
+ *   barrier        : peer_sig[r] = int32[world] on rank r (zero-initialised once); epoch = device int32.
+ *   allreduce_mean : peer_grad[r] = dense-gradient arena of rank r (n floats); every rank ends with
+ *                    the mean over ranks (DDP semantics), summed in rank order.  The caller places a
+ *                    barrier before and after. */
+int dlrm_b200_p2p_barrier(void* const* peer_sig /*[host][world]*/, int rank, int world, int32_t* epoch,
+                          void* stream);
+int dlrm_b200_p2p_allreduce_mean(void* const* peer_grad /*[host][world]*/, int rank, int world, int64_t n,
+                                 void* stream);
+
 /* ------------------------------------------------------------------------------------------
  * apply_mlp layer (dlrm_s_pytorch.py:399-405: nn.Linear -> addmm, + ReLU / Sigmoid modules)
  *   fwd  : Y[M,N]  = act(X[M,K] W[N,K]^T + bias[N])

@@ -204,6 +204,7 @@ def test_emb_update_with_duplicates(opt, D, rows, B, lmax, filtered):
         for k in range(2):
             e.momentum[int(e.row_base[k]):int(e.row_base[k + 1])].copy_(torch.from_numpy(mom[k]))
     if filtered:   # training gather with the duplicate filter + classify (suspects only are linked)
+        e.use_filter = True
         scratch = torch.empty((B, 3, D), device=DEV)
         e.emb_forward(sp, scratch.view(-1)[D:], 3 * D, D, link=True)
         assert e._filtered
