@@ -206,31 +206,53 @@ def ours(args):
         devb.append(db)
     torch.cuda.synchronize()
     lr = 0.01
-    # two static staging buffers, each with its own captured graph of the whole step
-    stage = [DeviceBatch(host[0].layout, dev) for _ in range(2)]
-    for st in stage:
-        st.load(host[0], non_blocking=False)
+    # K consecutive steps per CUDA graph (the embedding update of step j overlaps the bottom MLP of step
+    # j+1 on a side stream); two sets of K static staging buffers so the H2D of the next K batches can
+    # run while the current graph executes.
+    Kp = 1
+    if train and not args.no_pipeline:
+        for cand in (args.pipeline, 4, 2):
+            if cand >= 1 and args.steps % cand == 0:
+                Kp = cand
+                break
+    sets = [[DeviceBatch(host[0].layout, dev) for _ in range(Kp)] for _ in range(2)]
+    for st_set in sets:
+        for st in st_set:
+            st.load(host[0], non_blocking=False)
     use_graph = not args.no_graph
-    steps_g = [GraphedTrainStep(eng, st, lr, "rwsadagrad", train=train) for st in stage] if use_graph else None
+    from dlrm_b200.engine import GraphedTrainSteps
 
-    def run_on(st_i):
-        if use_graph:
-            return steps_g[st_i].replay()
-        st = stage[st_i]
+    graphs = None
+    if use_graph:
         if train:
-            return eng.train_step(st.X, st.sparse, st.target, lr, "rwsadagrad")
-        return eng.forward(st.X, st.sparse)
+            graphs = [GraphedTrainSteps(eng, st_set, lr, "rwsadagrad") for st_set in sets]
+        else:
+            graphs = [GraphedTrainStep(eng, st_set[0], lr, "rwsadagrad", train=False) for st_set in sets]
 
-    def step_resident(i):
-        # inputs already resident in HBM: device-to-device copy of the packed batch into the
-        # graph's static buffer (2.7 MB), then the step
-        src = devb[i % args.ring]
-        nbytes = src.layout.used(src.nnz)
-        stage[0].buf[:nbytes].copy_(src.buf[:nbytes], non_blocking=True)
-        run_on(0)
+    def run_set(si):
+        """Kp steps on the batches currently in staging set si; returns a tensor holding a loss / output."""
+        if graphs is not None:
+            return graphs[si].replay()
+        out = None
+        for j, st in enumerate(sets[si]):
+            if train:
+                out = eng.train_step(st.X, st.sparse, st.target, lr, "rwsadagrad", join_update=(j == Kp - 1))
+            else:
+                out = eng.forward(st.X, st.sparse)
+        return out
 
-    for w in range(args.warmup):
-        step_resident(w)
+    def resident_round(i):
+        # inputs already resident in HBM: device-to-device copies of the packed batches into the
+        # graph's static buffers (2.7 MB each), then Kp steps
+        for j, st in enumerate(sets[0]):
+            src = devb[(i * Kp + j) % args.ring]
+            nbytes = src.layout.used(src.nnz)
+            st.buf[:nbytes].copy_(src.buf[:nbytes], non_blocking=True)
+        run_set(0)
+
+    rounds, wrounds = args.steps // Kp, max((args.warmup + Kp - 1) // Kp, 1)
+    for w in range(wrounds):
+        resident_round(w)
     torch.cuda.synchronize()
     sampler = ClockSampler(0)
     sampler.start()
@@ -240,8 +262,8 @@ def ours(args):
     t0 = time.time()
     launches0 = eng.n_launch
     ev0.record()
-    for s in range(args.steps):
-        step_resident(args.warmup + s)
+    for r in range(rounds):
+        resident_round(wrounds + r)
     ev1.record()
     torch.cuda.synchronize()
     t1 = time.time()
@@ -250,47 +272,51 @@ def ours(args):
     ms = ev0.elapsed_time(ev1) / args.steps
     value = B / (ms * 1e-3)
 
-    # ---- e2e: host buffers; H2D of the packed batch + D2H of the loss inside the timed region
+    # ---- e2e: host buffers; H2D of the packed batches + D2H of the loss inside the timed region
     copy_stream = torch.cuda.Stream()
     loss_host = torch.zeros(1).pin_memory()
     main = torch.cuda.current_stream()
     h2d = 0
 
-    def e2e_loop(nsteps, base):
+    def load_set(si, base):
         nonlocal h2d
+        for j, st in enumerate(sets[si]):
+            h2d += st.load(host[(base + j) % args.ring])
+
+    def e2e_loop(nrounds, base):
         ready = [torch.cuda.Event(), torch.cuda.Event()]
         freed = [torch.cuda.Event(), torch.cuda.Event()]
         for f in freed:
             f.record(main)
         with torch.cuda.stream(copy_stream):
             copy_stream.wait_event(freed[0])
-            h2d += stage[0].load(host[base % args.ring])
+            load_set(0, base)
             ready[0].record(copy_stream)
-        for s in range(nsteps):
-            cur, nxt = s & 1, (s + 1) & 1
-            if s + 1 < nsteps:
+        for r in range(nrounds):
+            cur, nxt = r & 1, (r + 1) & 1
+            if r + 1 < nrounds:
                 with torch.cuda.stream(copy_stream):
                     copy_stream.wait_event(freed[nxt])
-                    h2d += stage[nxt].load(host[(base + s + 1) % args.ring])
+                    load_set(nxt, base + (r + 1) * Kp)
                     ready[nxt].record(copy_stream)
             main.wait_event(ready[cur])
-            out = run_on(cur)
-            loss_host.copy_(out.view(-1)[:1], non_blocking=True)
+            out = run_set(cur)
+            loss_host.copy_(out.view(-1)[-1:], non_blocking=True)
             freed[cur].record(main)
         main.synchronize()
 
-    e2e_loop(args.warmup, 0)
+    e2e_loop(wrounds, 0)
     h2d = 0
     torch.cuda.synchronize()
     ev0.record()
-    e2e_loop(args.steps, args.warmup)
+    e2e_loop(rounds, wrounds * Kp)
     ev1.record()
     torch.cuda.synchronize()
     ms_e2e = ev0.elapsed_time(ev1) / args.steps
     e2e = {"value": B / (ms_e2e * 1e-3), "unit": "samples/s", "h2d_bytes_per_step": int(h2d / args.steps),
-           "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e,
-           "note": "packed pinned batch -> one cudaMemcpyAsync on a copy stream (double-buffered) -> "
-                   "one CUDA-graph launch per step; loss read back every step"}
+           "d2h_bytes_per_step": 4.0 / Kp, "ms_per_step": ms_e2e,
+           "note": "packed pinned batches -> one cudaMemcpyAsync each on a copy stream (double-buffered sets of "
+                   "%d) -> one CUDA-graph launch per %d steps; loss read back after every launch" % (Kp, Kp)}
 
     # ---- rooflines of the HBM-bound kernels, timed with CUDA events on the launching stream
     peaks = {}
@@ -312,7 +338,7 @@ def ours(args):
         "dtype": {"simt": "fp32", "tc": "fp32 (bf16x3 split on tcgen05, fp32 accumulate)", "tc_bf16": "bf16"}[args.gemm],
         "data": "synthetic", "config": config_dict(args, 1),
         "roofline": roof, "roofline_update": roof_upd, "cpu_baseline": cb, "e2e": e2e,
-        "gpu_launches": int(launches), "cuda_graph": bool(use_graph), "clocks": clocks,
+        "gpu_launches": int(launches), "cuda_graph": bool(use_graph), "steps_per_graph": Kp, "clocks": clocks,
     }
     print(json.dumps(line))
 
@@ -333,21 +359,28 @@ def _time_loop(fn, n, ring):
 
 
 def measure_update_alone(eng, devb, args, hbm_peak, T, B, D):
-    """Training-mode gather (+link) and the fused coalesce + row-wise Adagrad update, timed alone."""
+    """Training-mode gather (+link) and the fused coalesce + row-wise Adagrad update, timed with CUDA
+    events between the launches of back-to-back (gather+link, update) pairs: each kernel is long enough
+    (>= 35 us) to hide the host's launch latency of the next one, so the intervals hold no idle gaps."""
     FD = eng.F * eng.D
     out = eng.Tbuf.view(-1)[eng.D:]
     eng.dT.normal_()
     eng.head.zero_()
     n = max(args.steps, 32)
-
-    def pair(db):
+    evs = []
+    for i in range(n + 3):
+        db = devb[i % len(devb)]
+        e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+        e0.record()
         eng.emb_forward(db.sparse, out, FD, eng.D, link=True)
+        e1.record()
         eng.emb_update(db.sparse, eng.dT.view(-1)[eng.D:], FD, eng.D, "rwsadagrad", 1e-6)
-
-    t_pair = _time_loop(pair, n, devb)
-    t_gl = _time_loop(lambda db: eng.emb_forward(db.sparse, out, FD, eng.D, link=True), n, devb)
-    eng.head.zero_()   # the link-only loop left list heads behind
-    tu = max(t_pair - t_gl, 1e-9)
+        e2.record()
+        if i >= 3:
+            evs.append((e0, e1, e2))
+    torch.cuda.synchronize()
+    t_gl = float(np.mean([a.elapsed_time(b) for a, b, _ in evs])) * 1e-3
+    tu = float(np.mean([b.elapsed_time(c) for _, b, c in evs])) * 1e-3
     nnz = float(np.mean([d.nnz for d in devb]))
     by_u = nnz * (D * 4 * 2 + 8) + T * B * D * 4 + nnz * 8   # SURVEY 8(d) bytes_bwd
     ach = by_u / tu / 1e9
@@ -355,7 +388,7 @@ def measure_update_alone(eng, devb, args, hbm_peak, T, B, D):
             "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak, "traffic": None,
             "avg_launch_us": tu * 1e6, "algorithmic_bytes_per_launch": by_u,
             "train_gather_plus_link_us": t_gl * 1e6,
-            "how": "back-to-back (gather+link, update) pairs minus back-to-back gather+link, CUDA events"}
+            "how": "CUDA events between the launches of back-to-back (gather+link, update) pairs"}
 
 
 def measure_gather_alone(eng, devb, args, hbm_peak, peak_src, T, B, D):
@@ -384,6 +417,8 @@ def main():
     ap.add_argument("--ring", type=int, default=16)
     ap.add_argument("--gemm", default="tc", choices=["tc", "tc_bf16", "simt"])
     ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--pipeline", type=int, default=4, help="training steps per CUDA graph (cross-step overlap)")
+    ap.add_argument("--no-pipeline", action="store_true")
     ap.add_argument("--exchange", default="nccl", choices=["p2p", "nccl"],
                     help="N>1: pooled-vector exchange fused into the kernels over peer memory, or NCCL all-to-all")
     ap.add_argument("--cpu-budget", type=float, default=15.0)

@@ -86,3 +86,19 @@ extern "C" int dlrm_b200_p2p_allreduce_mean(void* const* peer_grad, int rank, in
   DLRM_CHECK_LAUNCH("p2p_allreduce_mean_kernel");
   return 0;
 }
+
+extern "C" int dlrm_b200_enable_peer_access(int device, int peer_device) {
+  using namespace dlrm;
+  if (device == peer_device) return 0;
+  int can = 0;
+  DLRM_CUDA(cudaDeviceCanAccessPeer(&can, device, peer_device));
+  if (!can) return set_error("enable_peer_access: device %d cannot access device %d", device, peer_device);
+  int cur = 0;
+  DLRM_CUDA(cudaGetDevice(&cur));
+  DLRM_CUDA(cudaSetDevice(device));
+  cudaError_t e = cudaDeviceEnablePeerAccess(peer_device, 0);
+  if (e == cudaErrorPeerAccessAlreadyEnabled) { (void)cudaGetLastError(); e = cudaSuccess; }
+  cudaSetDevice(cur);
+  if (e != cudaSuccess) return set_error("cudaDeviceEnablePeerAccess(%d -> %d): %s", device, peer_device, cudaGetErrorString(e));
+  return 0;
+}

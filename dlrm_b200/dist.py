@@ -160,6 +160,11 @@ class DistEngine:
                 t, g, sg, dg = e.Tbuf, e.dT, self._sig, e.dense_grad
             else:
                 t, g, sg, dg = (fn(*args) for fn, args in allh[r])
+                # the IPC mapping lives on the peer's device in this process: let kernels running on MY
+                # device dereference it (torch only does this for its own peer copies)
+                from . import _lib as _l
+
+                _l.check(e.lib.dlrm_b200_enable_peer_access(self.device.index, t.device.index), "enable_peer_access")
             self._peer_keep += [t, g, sg, dg]
             pT.append(t.data_ptr() + col)
             pdT.append(g.data_ptr() + col)

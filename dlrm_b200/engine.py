@@ -560,6 +560,12 @@ class Engine:
         gz_ld = [t.shape[1] for t in self.bot_gz] + [FD]
         self.mlp_backward("bot", X, X.stride(0), ACT_NONE, B, acts, lds, gz, gz_ld, None, 0)
 
+    def sync_update(self):
+        """Make the current stream wait for an embedding update left running by
+        train_step(join_update=False)."""
+        if self.multi_stream:
+            self._join(self.s_emb)
+
     # ---- entry points used by the DLRM_Net facade (dlrm_b200/dlrm_net.py)
     def backward_from_output_grad(self, X: torch.Tensor, sp: SparseInput, gp: torch.Tensor):
         """Backward pass started from dE/dp computed OUTSIDE (autograd of the module's output).
@@ -617,10 +623,18 @@ class Engine:
         self.n_launch += 1
 
     def train_step(self, X: torch.Tensor, sp: SparseInput, target: torch.Tensor, lr: float,
-                   optimizer: str = "rwsadagrad", lr_decay: float = 0.0, link_done: bool = False):
+                   optimizer: str = "rwsadagrad", lr_decay: float = 0.0, link_done: bool = False,
+                   join_update: bool = True):
         """forward + loss + backward + optimizer.step().  Returns the loss (1-element device
-        tensor, not synchronised)."""
+        tensor, not synchronised).
+
+        join_update=False (tensor-core path): the embedding update is left running on the embedding
+        stream; the NEXT step's gather is ordered behind it on that stream, so the update of step i
+        overlaps the bottom MLP of step i+1 (the dense optimizer does not depend on it).  The caller
+        must then use a different batch buffer for the next step and call `sync_update()` before
+        reading the tables from another stream."""
         self.ensure_optimizer_state(optimizer)
+        self._join_update = bool(join_update) or not self.tc or not self.multi_stream
         self.forward(X, sp, link=not link_done, skip_head=True)
         self.opt_step += 1
         clr = lr / (1.0 + (self.opt_step - 1.0) * lr_decay) if optimizer == "rwsadagrad" else lr
@@ -948,8 +962,45 @@ class Engine:
         self._tc_mlp_backward("bot", B)
         if self.multi_stream:
             self._join(self.s_wg)
-            if update is not None and has_emb:
+            if update is not None and has_emb and getattr(self, "_join_update", True):
                 self._join(self.s_emb)
+
+
+class GraphedTrainSteps:
+    """K consecutive training steps over K static batch buffers in ONE CUDA graph.  Inside the graph
+    the embedding update of step j overlaps the bottom MLP of step j+1 (train_step(join_update=False));
+    only the last update is joined.  `losses[j]` holds the loss of step j after a replay."""
+
+    def __init__(self, eng: "Engine", stages, lr: float, optimizer: str = "rwsadagrad", warmup: int = 2):
+        self.eng, self.stages, self.lr, self.optimizer = eng, list(stages), lr, optimizer
+        self.K = len(self.stages)
+        eng.ensure_optimizer_state(optimizer)
+        self.losses = torch.zeros(self.K, dtype=torch.float32, device=eng.device)
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(max(warmup, 1)):
+                self._eager()
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        n0 = eng.n_launch
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self._eager()
+        self.kernels_per_replay = eng.n_launch - n0
+
+    def _eager(self):
+        for j, st in enumerate(self.stages):
+            loss = self.eng.train_step(st.X, st.sparse, st.target, self.lr, self.optimizer,
+                                       join_update=(j == self.K - 1))
+            self.losses[j:j + 1].copy_(loss)
+        return self.losses
+
+    def replay(self):
+        self.graph.replay()
+        self.eng.n_launch += self.kernels_per_replay
+        self.eng.opt_step += self.K
+        return self.losses
 
 
 class GraphedTrainStep:

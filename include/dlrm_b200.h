@@ -166,6 +166,9 @@ int dlrm_b200_emb_bwd_update_p2p(const dlrm_emb_bwd_table_t* tables /*[host]*/, 
  *   allreduce_mean : peer_grad[r] = dense-gradient arena of rank r (n floats); every rank ends with
  *                    the mean over ranks (DDP semantics), summed in rank order.  The caller places a
  *                    barrier before and after. */
+/* kernels running on `device` may dereference memory of `peer_device` (cudaDeviceEnablePeerAccess);
+ * needed once per peer before passing IPC-mapped peer pointers to the entry points above. */
+int dlrm_b200_enable_peer_access(int device, int peer_device);
 int dlrm_b200_p2p_barrier(void* const* peer_sig /*[host][world]*/, int rank, int world, int32_t* epoch,
                           void* stream);
 int dlrm_b200_p2p_allreduce_mean(void* const* peer_grad /*[host][world]*/, int rank, int world, int64_t n,

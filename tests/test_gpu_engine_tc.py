@@ -142,3 +142,53 @@ def test_cuda_graph_step_equals_eager(gemm):
     np.testing.assert_allclose(res[0][0], res[1][0], rtol=0, atol=1e-6)
     assert torch.allclose(res[0][1], res[1][1], rtol=0, atol=1e-6)
     assert torch.allclose(res[0][2], res[1][2], rtol=0, atol=1e-6)
+
+
+def test_pipelined_multi_step_graph_equals_sequential():
+    """GraphedTrainSteps: K steps per graph, the embedding update of step j overlapping step j+1's bottom
+    MLP on the side stream -> same losses and parameters as K sequential train_step() calls."""
+    from dlrm_b200.data import DeviceBatch, make_batch
+    from dlrm_b200.engine import Engine, GraphedTrainSteps
+
+    rng = np.random.default_rng(4)
+    D, ln_emb, ln_bot = 128, [2000, 300, 25], [13, 64, 128]   # small tables: rows shared between steps
+    ln_top = [D + 4 * 3 // 2, 64, 32, 1]
+    B, K = 160, 3
+    params = O.random_params(rng, D, ln_emb, ln_bot, ln_top)
+    hbs = [make_batch(np.random.default_rng(20 + i), ln_emb, B, 13, 10) for i in range(2 * K)]
+    res = []
+    for mode in ("eager", "graph"):
+        e = Engine(D, ln_emb, ln_bot, ln_top, loss="bce", sigmoid_top=len(ln_top) - 2, device=DEV, max_batch=B,
+                   gemm="tc")
+        e.load_params(params)
+        stages = [DeviceBatch(hbs[0].layout, DEV) for _ in range(K)]
+        losses = []
+        if mode == "graph":
+            for j, st in enumerate(stages):
+                st.load(hbs[j], non_blocking=False)
+            e.prepare(stages[0].sparse, True)
+            gs = GraphedTrainSteps.__new__(GraphedTrainSteps)   # capture without warm-up steps
+            gs.eng, gs.stages, gs.lr, gs.optimizer, gs.K = e, stages, 0.02, "rwsadagrad", K
+            e.ensure_optimizer_state("rwsadagrad")
+            gs.losses = torch.zeros(K, device=DEV)
+            torch.cuda.synchronize()
+            gs.graph = torch.cuda.CUDAGraph()
+            n0 = e.n_launch
+            with torch.cuda.graph(gs.graph):
+                gs._eager()
+            gs.kernels_per_replay = e.n_launch - n0
+            for r in range(2):
+                for j, st in enumerate(stages):
+                    st.load(hbs[r * K + j], non_blocking=False)
+                losses += gs.replay().cpu().tolist()
+        else:
+            st = stages[0]
+            for hb in hbs:
+                st.load(hb, non_blocking=False)
+                losses.append(float(e.train_step(st.X, st.sparse, st.target, 0.02, "rwsadagrad").item()))
+        torch.cuda.synchronize()
+        res.append((losses, e.dense.clone(), e.tables.clone(), e.momentum.clone()))
+    np.testing.assert_allclose(res[0][0], res[1][0], rtol=0, atol=1e-6)
+    assert torch.allclose(res[0][1], res[1][1], rtol=0, atol=1e-6)
+    assert torch.allclose(res[0][2], res[1][2], rtol=0, atol=1e-6)
+    assert torch.allclose(res[0][3], res[1][3], rtol=0, atol=1e-7)

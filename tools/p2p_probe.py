@@ -54,6 +54,9 @@ def main():
         from dlrm_b200 import _lib
 
         lib = _lib.lib()
+        for r in range(world):
+            if r != rank:
+                _lib.check(lib.dlrm_b200_enable_peer_access(dev.index, peers[r].device.index), "enable_peer_access")
         D, B, R = 128, 64, 1000
         W = torch.randn(R, D, device=dev)
         idx = torch.randint(0, R, (B * world * 3,), device=dev)
