@@ -146,8 +146,11 @@ class DistEngine:
 
         e = self.eng
         e._tc_prepare(self.B)    # final allocation of the dense-gradient arena (split-K slabs)
-        self._sig = torch.zeros(16, dtype=torch.int32, device=self.device)    # barrier slots, one per rank
-        self._epoch = torch.zeros(1, dtype=torch.int32, device=self.device)
+        # two barrier channels (slots + epoch each): 0 = embedding stream (gather / update), 1 = main
+        # stream (dense-gradient sync).  Barriers of one channel are ordered by their stream on every
+        # rank; the two streams may interleave differently across ranks, so they must not share slots.
+        self._sig = torch.zeros(32, dtype=torch.int32, device=self.device)
+        self._epoch = torch.zeros(2, dtype=torch.int32, device=self.device)
         torch.cuda.synchronize()
         mine = tuple(reduce_tensor(t) for t in (e.Tbuf, e.dT, self._sig, e.dense_grad))
         allh = [None] * self.world
@@ -173,21 +176,22 @@ class DistEngine:
         W = self.world
         self._peer_T = (C.c_void_p * W)(*pT)
         self._peer_dT = (C.c_void_p * W)(*pdT)
-        self._peer_sig = (C.c_void_p * W)(*psig)
+        self._peer_sig = [(C.c_void_p * W)(*[p + 64 * ch for p in psig]) for ch in range(2)]
         self._peer_grad = (C.c_void_p * W)(*pgrad)
         self.own_sync = os.environ.get("DLRM_P2P_NCCL_SYNC") != "1"   # our kernels instead of NCCL all_reduce
         if self.own_sync:
             e.dense_sync_fn = self._dense_sync_p2p
         dist.barrier()
 
-    def _barrier(self):
+    def _barrier(self, channel: int = 0):
         """Device-side ordering across ranks on the current stream (no host sync)."""
         if getattr(self, "own_sync", False):
             from . import _lib
             from .engine import _stream
 
-            _lib.check(self.eng.lib.dlrm_b200_p2p_barrier(self._peer_sig, self.rank, self.world,
-                                                          self._epoch.data_ptr(), _stream()), "p2p_barrier")
+            _lib.check(self.eng.lib.dlrm_b200_p2p_barrier(self._peer_sig[channel], self.rank, self.world,
+                                                          self._epoch.data_ptr() + 4 * channel, _stream()),
+                       "p2p_barrier")
             self.eng.n_launch += 1
         else:
             dist.all_reduce(self._flag)
@@ -197,11 +201,11 @@ class DistEngine:
         from . import _lib
         from .engine import _stream
 
-        self._barrier()       # every rank's gradient arena is complete
+        self._barrier(1)      # every rank's gradient arena is complete
         _lib.check(self.eng.lib.dlrm_b200_p2p_allreduce_mean(self._peer_grad, self.rank, self.world,
                                                              self.eng.dense_numel, _stream()), "p2p_allreduce_mean")
         self.eng.n_launch += 1
-        self._barrier()       # every slice has been written back everywhere
+        self._barrier(1)      # every slice has been written back everywhere
 
     def _gather_p2p(self, sp, link):
         from . import _lib
@@ -328,39 +332,59 @@ def bench_main(args, CFG, metric_name, config_dict, ClockSampler):
         ring.append((hb, db, X, X.to(dev), Tt, Tt.to(dev)))
     lr = 0.01
 
-    # static staging buffers + (optionally) the whole sharded step, collectives included, in one CUDA graph
-    stage = DeviceBatch(ring[0][0].layout, dev)
-    stage.load(ring[0][0], non_blocking=False)
-    Xs = ring[0][3].clone()
-    Ts = ring[0][5].clone()
-    graph = None
-    # capturing NCCL collectives into a CUDA graph hangs on this stack (r7: torch 2.11 / NCCL 2.28):
-    # the sharded step runs eagerly unless DLRM_DIST_GRAPH=1 asks for the experiment
+    # K static staging buffers per rank; with the NCCL-free exchange the whole sharded step (K of them per
+    # graph, update of step j overlapping step j+1) is captured in one CUDA graph per rank
+    import types
+
+    Kp = 1
     want_graph = (de.exchange == "p2p" and getattr(de, "own_sync", False)) or os.environ.get("DLRM_DIST_GRAPH") == "1"
-    if want_graph and not getattr(args, "no_graph", False):
-        from .engine import GraphedTrainStep
+    want_graph = want_graph and not getattr(args, "no_graph", False)
+    if train and not getattr(args, "no_pipeline", False):
+        cand = getattr(args, "pipeline", 1)
+        if cand >= 1 and args.steps % cand == 0:
+            Kp = cand
+    stages = []
+    for j in range(Kp):
+        st = DeviceBatch(ring[0][0].layout, dev)
+        st.load(ring[0][0], non_blocking=False)
+        stages.append(types.SimpleNamespace(db=st, sparse=st.sparse, X=ring[0][3].clone(), target=ring[0][5].clone()))
+    graph = None
+    if want_graph:
+        from .engine import GraphedTrainStep, GraphedTrainSteps
 
         try:
-            graph = GraphedTrainStep(de.eng, stage, lr, "rwsadagrad", warmup=3, train=train, X=Xs, target=Ts)
-        except Exception as ex:  # noqa: BLE001  (capture of the collectives not possible on this stack)
+            if train:
+                graph = GraphedTrainSteps(de.eng, stages, lr, "rwsadagrad")
+            else:
+                graph = GraphedTrainStep(de.eng, stages[0], lr, "rwsadagrad", train=False)
+        except Exception as ex:  # noqa: BLE001
             if rank == 0:
                 print("dist: CUDA-graph capture failed (%s); running eagerly" % str(ex)[:200], flush=True)
             graph = None
 
-    def step(i):
-        hb, db, Xh, Xd, Th, Td = ring[i % args.ring]
+    def run_round():
         if graph is not None:
-            nbytes = db.layout.used(db.nnz)
-            stage.buf[:nbytes].copy_(db.buf[:nbytes], non_blocking=True)
-            Xs.copy_(Xd, non_blocking=True)
-            Ts.copy_(Td, non_blocking=True)
             return graph.replay()
-        if train:
-            return de.train_step(Xd, db.sparse, Td, lr, "rwsadagrad")
-        return de.forward(Xd, db.sparse)
+        out = None
+        for j, st in enumerate(stages):
+            if train:
+                out = de.eng.train_step(st.X, st.sparse, st.target, lr, "rwsadagrad", join_update=(j == Kp - 1))
+            else:
+                out = de.eng.forward(st.X, st.sparse)
+        return out
 
-    for w in range(args.warmup):
-        step(w)
+    def resident_round(i):
+        for j, st in enumerate(stages):
+            hb, db, Xh, Xd, Th, Td = ring[(i * Kp + j) % args.ring]
+            nbytes = db.layout.used(db.nnz)
+            st.db.buf[:nbytes].copy_(db.buf[:nbytes], non_blocking=True)
+            st.X.copy_(Xd, non_blocking=True)
+            st.target.copy_(Td, non_blocking=True)
+        return run_round()
+
+    rounds, wrounds = args.steps // Kp, max((args.warmup + Kp - 1) // Kp, 1)
+    for w in range(wrounds):
+        resident_round(w)
     torch.cuda.synchronize()
     dist.barrier()
     sampler = ClockSampler(local)
@@ -373,8 +397,8 @@ def bench_main(args, CFG, metric_name, config_dict, ClockSampler):
     t0 = time.time()
     n0 = de.eng.n_launch
     ev0.record()
-    for s in range(args.steps):
-        step(args.warmup + s)
+    for r in range(rounds):
+        resident_round(wrounds + r)
     ev1.record()
     torch.cuda.synchronize()
     dist.barrier()
@@ -388,29 +412,25 @@ def bench_main(args, CFG, metric_name, config_dict, ClockSampler):
     loss_host = torch.zeros(1).pin_memory()
     h2d = 0
 
-    def e2e_step(i):
+    def e2e_round(i):
         nonlocal h2d
-        hb, db, Xh, Xd, Th, Td = ring[i % args.ring]
-        h2d += stage.load(hb)
-        Xs.copy_(Xh, non_blocking=True)
-        Ts.copy_(Th, non_blocking=True)
-        h2d += Xh.numel() * 4 + Th.numel() * 4
-        if graph is not None:
-            out = graph.replay()
-        elif train:
-            out = de.train_step(Xs, stage.sparse, Ts, lr, "rwsadagrad")
-        else:
-            out = de.forward(Xs, stage.sparse)
-        loss_host.copy_(out.view(-1)[:1], non_blocking=True)
+        for j, st in enumerate(stages):
+            hb, db, Xh, Xd, Th, Td = ring[(i * Kp + j) % args.ring]
+            h2d += st.db.load(hb)
+            st.X.copy_(Xh, non_blocking=True)
+            st.target.copy_(Th, non_blocking=True)
+            h2d += Xh.numel() * 4 + Th.numel() * 4
+        out = run_round()
+        loss_host.copy_(out.view(-1)[-1:], non_blocking=True)
 
-    for w in range(3):
-        e2e_step(w)
+    for w in range(2):
+        e2e_round(w)
     h2d = 0
     torch.cuda.synchronize()
     dist.barrier()
     ev0.record()
-    for s in range(args.steps):
-        e2e_step(s)
+    for r in range(rounds):
+        e2e_round(r)
     ev1.record()
     torch.cuda.synchronize()
     dist.barrier()
@@ -432,7 +452,7 @@ def bench_main(args, CFG, metric_name, config_dict, ClockSampler):
                     "d2h_bytes_per_step": 4, "ms_per_step": ms2,
                     "note": "per rank: packed pinned sparse batch (its tables, global batch) + dense slice, "
                             "H2D every step, loss read back"},
-            "gpu_launches": int(launches), "exchange": de.exchange, "cuda_graph": graph is not None,
+            "gpu_launches": int(launches), "exchange": de.exchange, "cuda_graph": graph is not None, "steps_per_graph": Kp,
             "a2a_bytes_per_rank_per_step": int(2 * 4 * (sum(de.send_splits) - de.send_splits[rank])),
             "clocks": clocks,
         }
