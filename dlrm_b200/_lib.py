@@ -18,13 +18,13 @@ TUNE = dict(emb_bags_per_group=0, emb_unroll=1, emb_block=2, upd_block=3, gemm_s
 
 class EmbFwdTable(C.Structure):
     _fields_ = [("weight", C.c_void_p), ("indices", C.c_void_p), ("offsets", C.c_void_p),
-                ("row_weights", C.c_void_p), ("nnz", C.c_int64), ("rows", C.c_int64)]
+                ("row_weights", C.c_void_p), ("nnz", C.c_int64), ("rows", C.c_int64), ("ld", C.c_int64)]
 
 
 class EmbBwdTable(C.Structure):
     _fields_ = [("weight", C.c_void_p), ("momentum", C.c_void_p), ("head", C.c_void_p),
                 ("indices", C.c_void_p), ("offsets", C.c_void_p), ("nnz", C.c_int64),
-                ("rows", C.c_int64), ("pair_base", C.c_int64)]
+                ("rows", C.c_int64), ("pair_base", C.c_int64), ("ld", C.c_int64), ("mom_stride", C.c_int64)]
 
 
 class EmbDedup(C.Structure):

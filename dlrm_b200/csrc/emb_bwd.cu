@@ -30,6 +30,8 @@ struct EmbBwdTable {
   const void* off;
   long long nnz;
   long long pair_base;
+  long long ld;          // row stride of w in floats
+  long long mom_stride;  // elements between consecutive rows' accumulators
 };
 
 struct EmbBwdParams {
@@ -249,7 +251,7 @@ __global__ void __launch_bounds__(256, NV == 1 ? 3 : 1) emb_update_kernel(const 
         const int bag = __shfl_sync(0xffffffffu, my_link.y, src);
         if ((owners >> src) & 1u) {
           const EmbBwdTable& tb = P.t[ku];
-          const float* wrow = tb.w + r * D;
+          const float* wrow = tb.w + r * tb.ld;
           const float* grow = dy_row(P, bag) + (long long)ku * P.dy_stride_table;
 #pragma unroll
           for (int v = 0; v < NV; ++v)
@@ -257,7 +259,7 @@ __global__ void __launch_bounds__(256, NV == 1 ? 3 : 1) emb_update_kernel(const 
               wpf[u][v] = ld_pack<W>(wrow + lane * W + v * 32 * W);
               gpf[u][v] = ld_pack<W>(grow + lane * W + v * 32 * W);
             }
-          mpf[u] = (P.optimizer == DLRM_OPT_RWSADAGRAD) ? tb.mom[r] : 0.f;
+          mpf[u] = (P.optimizer == DLRM_OPT_RWSADAGRAD) ? tb.mom[r * tb.mom_stride] : 0.f;
         }
       }
 #pragma unroll
@@ -269,7 +271,7 @@ __global__ void __launch_bounds__(256, NV == 1 ? 3 : 1) emb_update_kernel(const 
         const int self_bag = __shfl_sync(0xffffffffu, my_link.y, src);
         if (!((owners >> src) & 1u)) continue;
         const EmbBwdTable& tb = P.t[ku];
-        float* wrow = tb.w + r * D;
+        float* wrow = tb.w + r * tb.ld;
         const long long dyk_off = (long long)ku * P.dy_stride_table;
         Pack<W> w[NV], g[NV];
 #pragma unroll
@@ -329,7 +331,7 @@ __global__ void __launch_bounds__(256, NV == 1 ? 3 : 1) emb_update_kernel(const 
               for (int e = 0; e < W; ++e) w[v].x[e] = fmaf(nlr, g[v].x[e] / stdv, w[v].x[e]);
               st_pack<W>(wrow + lane * W + v * 32 * W, w[v]);
             }
-          if (lane == 0) tb.mom[r] = m_new;
+          if (lane == 0) tb.mom[r * tb.mom_stride] = m_new;
         } else {
           const float nlr = -P.lr;
 #pragma unroll
@@ -363,6 +365,8 @@ static int fill_params(EmbBwdParams& P, const dlrm_emb_bwd_table_t* tables, int 
     P.t[k].off = tables[k].offsets;
     P.t[k].nnz = tables[k].nnz;
     P.t[k].pair_base = tables[k].pair_base;
+    P.t[k].ld = tables[k].ld;   // 0 -> dim, resolved by the update entry point
+    P.t[k].mom_stride = tables[k].mom_stride > 0 ? tables[k].mom_stride : 1;
   }
   return 0;
 }
@@ -430,6 +434,9 @@ static int emb_update_impl(const dlrm_emb_bwd_table_t* tables, int num_tables, i
     if (optimizer == DLRM_OPT_RWSADAGRAD && !tables[k].momentum)
       return set_error("emb_bwd_update: table %d momentum NULL", k);
     vec = vec && aligned16(tables[k].weight);
+    if (P.t[k].ld <= 0) P.t[k].ld = dim;
+    if (P.t[k].ld < dim) return set_error("emb_bwd_update: table %d: ld < dim", k);
+    vec = vec && (P.t[k].ld % 4 == 0);
   }
   P.link = reinterpret_cast<int2*>(const_cast<int32_t*>(next));
   P.dY = dY;

@@ -21,6 +21,7 @@ struct EmbFwdTable {
   long long nnz;
   int* head;            // training: per-row list heads of this table (see emb_bwd.cu), else null
   long long pair_base;  // training: first slot of this table in link[]
+  long long ld;         // row stride in floats
 };
 
 struct EmbFwdParams {
@@ -136,7 +137,7 @@ __global__ void __launch_bounds__(256, (G == 32 && NV == 1) ? 4 : 1) emb_fwd_vec
           for (int u = 0; u < U; ++u) {
             const long long r = __shfl_sync(gmask, my_row, jj + u, G);  // jj+u < G always (U | G)
             if (jj + u < n) {
-              const float* rp = W + r * D + gl * 4;
+              const float* rp = W + r * tb.ld + gl * 4;
 #pragma unroll
               for (int v = 0; v < NV; ++v) {
                 if (gl * 4 + v * G * 4 < D) val[u][v] = ldg_stream_f4(rp + v * G * 4);
@@ -197,7 +198,7 @@ __global__ void emb_fwd_scalar_kernel(const __grid_constant__ EmbFwdParams P) {
   for (long long j = start; j < end; ++j) {
     const long long r = idx[j];
     if (LINK && d == 0) P.link[tb.pair_base + j] = make_int2(note_occurrence(P, tb, r, j), (int)b);
-    const float x = tb.w[r * D + d];
+    const float x = tb.w[r * tb.ld + d];
     acc = WEIGHTED ? fmaf(tb.rw[r], x, acc) : acc + x;
   }
   out_row(P, b)[(long long)blockIdx.y * P.stride_table + d] = acc;
@@ -271,6 +272,9 @@ static int emb_fwd_impl(const dlrm_emb_fwd_table_t* tables, const dlrm_emb_bwd_t
     P.t[k].off = tables[k].offsets;
     P.t[k].rw = tables[k].row_weights;
     P.t[k].nnz = tables[k].nnz;
+    P.t[k].ld = tables[k].ld > 0 ? tables[k].ld : dim;
+    if (P.t[k].ld < dim) return set_error("emb_bag_fwd: table %d: ld=%lld < dim", k, (long long)tables[k].ld);
+    vec_ok = vec_ok && (P.t[k].ld % 4 == 0);
     P.t[k].head = train ? train[k].head : nullptr;
     P.t[k].pair_base = train ? train[k].pair_base : 0;
     if (!tables[k].weight || !tables[k].offsets || (!tables[k].indices && tables[k].nnz > 0))

@@ -136,7 +136,7 @@ class DLRM_Net(nn.Module):
                               op=arch_interaction_op, itself=arch_interaction_itself,
                               sigmoid_bot=sigmoid_bot, sigmoid_top=sigmoid_top, loss=loss_function,
                               loss_threshold=loss_threshold, loss_ws=loss_ws, device=device,
-                              max_batch=max_batch, gemm=gemm)
+                              max_batch=max_batch, gemm=gemm, interleave_momentum=False)
         self._m_spa, self._ln_emb = int(m_spa), ln_emb
         # same construction (and numpy RNG consumption) order as the reference: tables, bottom, top
         if ndevices <= 1:

@@ -69,7 +69,8 @@ class Engine:
     def __init__(self, m_spa: int, ln_emb: Sequence[int], ln_bot: Sequence[int], ln_top: Sequence[int],
                  *, op: str = "dot", itself: bool = False, sigmoid_bot: int = -1, sigmoid_top: int = -1,
                  loss: str = "bce", loss_threshold: float = 0.0, loss_ws=None, device="cuda:0",
-                 max_batch: int = 2048, gemm: str = "simt", n_features: Optional[int] = None):
+                 max_batch: int = 2048, gemm: str = "simt", n_features: Optional[int] = None,
+                 interleave_momentum: bool = True):
         if not torch.cuda.is_available():
             raise RuntimeError("dlrm_b200.Engine needs a CUDA device (B200, sm_100a); there is no CPU path")
         self.device = torch.device(device)
@@ -110,9 +111,14 @@ class Engine:
         rows = np.asarray(self.ln_emb, dtype=np.int64)
         self.row_base = np.concatenate([[0], np.cumsum(rows)]).astype(np.int64)
         self.total_rows = int(self.row_base[-1])
-        self.tables = torch.empty((self.total_rows, self.D), dtype=torch.float32, device=dev)
+        # Row layout: [D weights | accumulator | 3 pad] (row stride D+4 floats) keeps the row-wise Adagrad
+        # accumulator in the same DRAM burst as its row; interleave_momentum=False gives dense [rows, D]
+        # tables and a separate accumulator array (what the nn.Module facade exposes to torch optimizers).
+        self.interleave = bool(interleave_momentum)
+        self.ldw = self.D + 4 if self.interleave else self.D
+        self.tables = torch.zeros((self.total_rows, self.ldw), dtype=torch.float32, device=dev)
         self.head = torch.zeros(self.total_rows, dtype=torch.int32, device=dev)
-        self.momentum: Optional[torch.Tensor] = None
+        self._momentum_sep: Optional[torch.Tensor] = None
         self.row_weights: Optional[torch.Tensor] = None  # weighted pooling v_W_l, arena [total_rows]
         # ---- dense arena
         self.dense_slices = []  # (name, layer, kind, offset, shape)
@@ -199,12 +205,18 @@ class Engine:
         self._filtered = False
 
     def table(self, k: int) -> torch.Tensor:
-        return self.tables[int(self.row_base[k]):int(self.row_base[k + 1])]
+        """[rows_k, D] view of table k (strided when the accumulator is interleaved)."""
+        return self.tables[int(self.row_base[k]):int(self.row_base[k + 1]), :self.D]
+
+    @property
+    def momentum(self) -> Optional[torch.Tensor]:
+        """Row-wise Adagrad accumulator of every row, [sum rows] (a strided view when interleaved)."""
+        return self.tables[:, self.D] if self.interleave else self._momentum_sep
 
     def ensure_optimizer_state(self, optimizer: str):
         if optimizer == "rwsadagrad":
-            if self.momentum is None:
-                self.momentum = torch.zeros(self.total_rows, dtype=torch.float32, device=self.device)
+            if not self.interleave and self._momentum_sep is None:
+                self._momentum_sep = torch.zeros(self.total_rows, dtype=torch.float32, device=self.device)
             if self.dense_state is None:
                 self.dense_state = torch.zeros_like(self.dense)
 
@@ -252,7 +264,8 @@ class Engine:
         arr = (EmbFwdTable * len(ks))()
         for n, k in enumerate(ks):
             d = arr[n]
-            d.weight = self.tables.data_ptr() + int(self.row_base[k]) * self.D * 4
+            d.weight = self.tables.data_ptr() + int(self.row_base[k]) * self.ldw * 4
+            d.ld = self.ldw
             d.indices = sp.indices[k].data_ptr() if sp.indices[k].numel() else 0
             d.offsets = sp.offsets[k].data_ptr()
             d.row_weights = (self.row_weights.data_ptr() + int(self.row_base[k]) * 4
@@ -267,9 +280,15 @@ class Engine:
         base = 0
         for n, k in enumerate(ks):
             d = arr[n]
-            d.weight = self.tables.data_ptr() + int(self.row_base[k]) * self.D * 4
-            d.momentum = (self.momentum.data_ptr() + int(self.row_base[k]) * 4
-                          if self.momentum is not None else None)
+            d.weight = self.tables.data_ptr() + int(self.row_base[k]) * self.ldw * 4
+            d.ld = self.ldw
+            if self.interleave:
+                d.momentum = d.weight + self.D * 4
+                d.mom_stride = self.ldw
+            else:
+                d.momentum = (self._momentum_sep.data_ptr() + int(self.row_base[k]) * 4
+                              if self._momentum_sep is not None else None)
+                d.mom_stride = 1
             d.head = self.head.data_ptr() + int(self.row_base[k]) * 4
             d.indices = sp.indices[k].data_ptr() if sp.indices[k].numel() else 0
             d.offsets = sp.offsets[k].data_ptr()

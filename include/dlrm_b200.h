@@ -64,6 +64,7 @@ typedef struct {
   const float* row_weights; /* NULL, or [rows]: v_W_l[k] (weighted pooling, :425-428) */
   int64_t nnz;
   int64_t rows;             /* for bounds checks in debug builds */
+  int64_t ld;               /* row stride of `weight` in floats; 0 = dim (dense rows) */
 } dlrm_emb_fwd_table_t;
 
 int dlrm_b200_emb_bag_fwd(const dlrm_emb_fwd_table_t* tables /*[host]*/, int num_tables, int dim,
@@ -96,6 +97,11 @@ typedef struct {
   int64_t nnz;
   int64_t rows;
   int64_t pair_base;    /* first slot of this table in next[] / (sum of nnz of earlier tables) */
+  int64_t ld;           /* row stride of `weight` in floats; 0 = dim */
+  int64_t mom_stride;   /* elements between consecutive rows' accumulators in `momentum`; 0 = 1.
+                         * ld = dim + 4 with momentum = weight + dim and mom_stride = ld keeps the
+                         * row-wise Adagrad accumulator in the SAME DRAM burst as its row: the update then
+                         * costs one activation per row instead of two (measured: profiles/). */
 } dlrm_emb_bwd_table_t;
 
 /* Optional duplicate filter (dlrm_emb_dedup_t): at 1e6-row tables almost every row of a batch is
