@@ -151,7 +151,8 @@ def test_pipelined_multi_step_graph_equals_sequential():
     from dlrm_b200.engine import Engine, GraphedTrainSteps
 
     rng = np.random.default_rng(4)
-    D, ln_emb, ln_bot = 128, [2000, 300, 25], [13, 64, 128]   # small tables: rows shared between steps
+    # rows are shared between consecutive steps; per-row lists stay <= 32 members (deterministic order)
+    D, ln_emb, ln_bot = 128, [2000, 600, 300], [13, 64, 128]
     ln_top = [D + 4 * 3 // 2, 64, 32, 1]
     B, K = 160, 3
     params = O.random_params(rng, D, ln_emb, ln_bot, ln_top)
