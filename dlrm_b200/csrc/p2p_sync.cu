@@ -9,6 +9,8 @@
 //                   all-reduce, extend_distributed.py:14 / dlrm_s_pytorch.py:1329-1336): rank r
 //                   reduces slice r reading all peers (fixed order -> identical result on every rank)
 //                   and stores the mean back into every peer's slice r.
+#include <string.h>
+
 #include "common.cuh"
 
 namespace dlrm {
@@ -100,5 +102,35 @@ extern "C" int dlrm_b200_enable_peer_access(int device, int peer_device) {
   if (e == cudaErrorPeerAccessAlreadyEnabled) { (void)cudaGetLastError(); e = cudaSuccess; }
   cudaSetDevice(cur);
   if (e != cudaSuccess) return set_error("cudaDeviceEnablePeerAccess(%d -> %d): %s", device, peer_device, cudaGetErrorString(e));
+  return 0;
+}
+
+// Map a buffer exported by another process (cudaIpcGetMemHandle; PyTorch: storage._share_cuda_()) into
+// THIS process for kernels running on `device`.  The handle must be opened with `device` current:
+// a mapping opened under the exporter's device index is not reachable from kernels of another device,
+// even with peer access enabled (measured on this stack).
+extern "C" int dlrm_b200_ipc_open(const void* handle64, int device, void** base_out) {
+  using namespace dlrm;
+  if (!handle64 || !base_out) return set_error("ipc_open: NULL argument");
+  int cur = 0;
+  DLRM_CUDA(cudaGetDevice(&cur));
+  DLRM_CUDA(cudaSetDevice(device));
+  cudaIpcMemHandle_t h;
+  memcpy(&h, handle64, sizeof(h));
+  void* p = nullptr;
+  cudaError_t e = cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess);
+  cudaSetDevice(cur);
+  if (e != cudaSuccess) {
+    (void)cudaGetLastError();
+    return set_error("cudaIpcOpenMemHandle on device %d: %s", device, cudaGetErrorString(e));
+  }
+  *base_out = p;
+  return 0;
+}
+
+extern "C" int dlrm_b200_ipc_close(void* base) {
+  using namespace dlrm;
+  if (!base) return 0;
+  DLRM_CUDA(cudaIpcCloseMemHandle(base));
   return 0;
 }

@@ -142,8 +142,6 @@ class DistEngine:
         NVLink).  peer_T[d] / peer_dT[s] point at feature (1 + my first table) of rank d's / s's buffer."""
         import ctypes as C
 
-        from torch.multiprocessing.reductions import reduce_tensor
-
         e = self.eng
         e._tc_prepare(self.B)    # final allocation of the dense-gradient arena (split-K slabs)
         # two barrier channels (slots + epoch each): 0 = embedding stream (gather / update), 1 = main
@@ -152,27 +150,36 @@ class DistEngine:
         self._sig = torch.zeros(32, dtype=torch.int32, device=self.device)
         self._epoch = torch.zeros(2, dtype=torch.int32, device=self.device)
         torch.cuda.synchronize()
-        mine = tuple(reduce_tensor(t) for t in (e.Tbuf, e.dT, self._sig, e.dense_grad))
+        def export(t):
+            # (device, handle, storage bytes, storage offset, ...) of the cudaMalloc block holding t
+            info = t.untyped_storage()._share_cuda_()
+            return bytes(info[1]), int(info[3]) + t.storage_offset() * t.element_size()
+
+        mine = tuple(export(t) for t in (e.Tbuf, e.dT, self._sig, e.dense_grad))
         allh = [None] * self.world
         dist.all_gather_object(allh, mine)
-        self._peer_keep = []
+        self._ipc_bases = {}
         pT, pdT, psig, pgrad = [], [], [], []
         col = (1 + self.t0) * self.D * 4
+
+        def imp(handle, offset):
+            if handle not in self._ipc_bases:       # one open per exported allocation
+                base = C.c_void_p()
+                _l.check(e.lib.dlrm_b200_ipc_open(handle, self.device.index, C.byref(base)), "ipc_open")
+                self._ipc_bases[handle] = base.value
+            return self._ipc_bases[handle] + offset
+
+        from . import _lib as _l
+
         for r in range(self.world):
             if r == self.rank:
-                t, g, sg, dg = e.Tbuf, e.dT, self._sig, e.dense_grad
+                ptrs = [e.Tbuf.data_ptr(), e.dT.data_ptr(), self._sig.data_ptr(), e.dense_grad.data_ptr()]
             else:
-                t, g, sg, dg = (fn(*args) for fn, args in allh[r])
-                # the IPC mapping lives on the peer's device in this process: let kernels running on MY
-                # device dereference it (torch only does this for its own peer copies)
-                from . import _lib as _l
-
-                _l.check(e.lib.dlrm_b200_enable_peer_access(self.device.index, t.device.index), "enable_peer_access")
-            self._peer_keep += [t, g, sg, dg]
-            pT.append(t.data_ptr() + col)
-            pdT.append(g.data_ptr() + col)
-            psig.append(sg.data_ptr())
-            pgrad.append(dg.data_ptr())
+                ptrs = [imp(hd, off) for hd, off in allh[r]]
+            pT.append(ptrs[0] + col)
+            pdT.append(ptrs[1] + col)
+            psig.append(ptrs[2])
+            pgrad.append(ptrs[3])
         W = self.world
         self._peer_T = (C.c_void_p * W)(*pT)
         self._peer_dT = (C.c_void_p * W)(*pdT)
