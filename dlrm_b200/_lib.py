@@ -61,7 +61,7 @@ SYMBOLS = [
     "dlrm_b200_interact_fwd_ex", "dlrm_b200_interact_bwd_ex", "dlrm_b200_act_bwd",
     "dlrm_b200_emb_bag_fwd_p2p", "dlrm_b200_emb_bwd_update_p2p", "dlrm_b200_emb_bwd_classify",
     "dlrm_b200_p2p_barrier", "dlrm_b200_p2p_allreduce_mean", "dlrm_b200_enable_peer_access",
-    "dlrm_b200_ipc_open", "dlrm_b200_ipc_close",
+    "dlrm_b200_ipc_export", "dlrm_b200_ipc_open", "dlrm_b200_ipc_close",
     "dlrm_b200_linear_fwd", "dlrm_b200_linear_dgrad", "dlrm_b200_linear_wgrad",
     "dlrm_b200_interact_fwd", "dlrm_b200_interact_bwd", "dlrm_b200_loss_fwd_bwd",
     "dlrm_b200_dense_update",
@@ -90,6 +90,7 @@ def _declare(lib):
     lib.dlrm_b200_emb_bwd_update_p2p.argtypes = [C.POINTER(EmbBwdTable), i32, i32, i64, i32, i32, vp, C.POINTER(vp),
                                                  i32, i64, i64, i64, i32, f32, f32, C.POINTER(EmbDedup), vp]
     lib.dlrm_b200_enable_peer_access.argtypes = [i32, i32]
+    lib.dlrm_b200_ipc_export.argtypes = [vp, C.c_char_p, C.POINTER(C.c_int64)]
     lib.dlrm_b200_ipc_open.argtypes = [C.c_char_p, i32, C.POINTER(vp)]
     lib.dlrm_b200_ipc_close.argtypes = [vp]
     lib.dlrm_b200_p2p_barrier.argtypes = [C.POINTER(vp), i32, i32, vp, vp]

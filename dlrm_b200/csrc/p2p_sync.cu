@@ -128,6 +128,32 @@ extern "C" int dlrm_b200_ipc_open(const void* handle64, int device, void** base_
   return 0;
 }
 
+// Export the cudaMalloc allocation holding `ptr` (a device pointer of THIS process): the 64-byte handle
+// for dlrm_b200_ipc_open in another process, and ptr's byte offset inside that allocation.
+extern "C" int dlrm_b200_ipc_export(const void* ptr, void* handle64_out, int64_t* offset_out) {
+  using namespace dlrm;
+  if (!ptr || !handle64_out || !offset_out) return set_error("ipc_export: NULL argument");
+  typedef int (*RangeFn)(unsigned long long*, size_t*, unsigned long long);
+  static RangeFn range = nullptr;
+  if (!range) {
+    void* f = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuMemGetAddressRange", &f, cudaEnableDefault, &q) != cudaSuccess ||
+        q != cudaDriverEntryPointSuccess)
+      return set_error("ipc_export: cuMemGetAddressRange not available");
+    range = reinterpret_cast<RangeFn>(f);
+  }
+  unsigned long long base = 0;
+  size_t size = 0;
+  const int rc = range(&base, &size, (unsigned long long)(uintptr_t)ptr);
+  if (rc != 0) return set_error("ipc_export: cuMemGetAddressRange failed (CUresult %d)", rc);
+  cudaIpcMemHandle_t h;
+  DLRM_CUDA(cudaIpcGetMemHandle(&h, reinterpret_cast<void*>((uintptr_t)base)));
+  memcpy(handle64_out, &h, sizeof(h));
+  *offset_out = (int64_t)((unsigned long long)(uintptr_t)ptr - base);
+  return 0;
+}
+
 extern "C" int dlrm_b200_ipc_close(void* base) {
   using namespace dlrm;
   if (!base) return 0;

@@ -150,10 +150,14 @@ class DistEngine:
         self._sig = torch.zeros(32, dtype=torch.int32, device=self.device)
         self._epoch = torch.zeros(2, dtype=torch.int32, device=self.device)
         torch.cuda.synchronize()
+        from . import _lib as _l
+
         def export(t):
-            # (device, handle, storage bytes, storage offset, ...) of the cudaMalloc block holding t
-            info = t.untyped_storage()._share_cuda_()
-            return bytes(info[1]), int(info[3]) + t.storage_offset() * t.element_size()
+            # handle of the cudaMalloc block holding t + t's byte offset inside it
+            h = C.create_string_buffer(64)
+            off = C.c_int64()
+            _l.check(e.lib.dlrm_b200_ipc_export(t.data_ptr(), h, C.byref(off)), "ipc_export")
+            return h.raw, int(off.value)
 
         mine = tuple(export(t) for t in (e.Tbuf, e.dT, self._sig, e.dense_grad))
         allh = [None] * self.world
@@ -168,8 +172,6 @@ class DistEngine:
                 _l.check(e.lib.dlrm_b200_ipc_open(handle, self.device.index, C.byref(base)), "ipc_open")
                 self._ipc_bases[handle] = base.value
             return self._ipc_bases[handle] + offset
-
-        from . import _lib as _l
 
         for r in range(self.world):
             if r == self.rank:

@@ -175,8 +175,11 @@ int dlrm_b200_emb_bwd_update_p2p(const dlrm_emb_bwd_table_t* tables /*[host]*/, 
 /* kernels running on `device` may dereference memory of `peer_device` (cudaDeviceEnablePeerAccess);
  * needed once per peer before passing IPC-mapped peer pointers to the entry points above. */
 int dlrm_b200_enable_peer_access(int device, int peer_device);
-/* Open a CUDA-IPC memory handle (64 bytes, from cudaIpcGetMemHandle / torch storage._share_cuda_())
- * with `device` current, so that kernels launched on `device` can dereference the mapping. */
+/* Export the cudaMalloc allocation that holds device pointer `ptr` of this process: a 64-byte
+ * cudaIpcMemHandle_t and ptr's byte offset inside the allocation (send both to the peer process). */
+int dlrm_b200_ipc_export(const void* ptr, void* handle64_out /*[host, 64 bytes]*/, int64_t* offset_out /*[host]*/);
+/* Open such a handle in another process with `device` current, so that kernels launched on `device`
+ * can dereference the mapping (base_out + offset = the peer's ptr).  One open per allocation. */
 int dlrm_b200_ipc_open(const void* handle64 /*[host]*/, int device, void** base_out /*[host]*/);
 int dlrm_b200_ipc_close(void* base);
 int dlrm_b200_p2p_barrier(void* const* peer_sig /*[host][world]*/, int rank, int world, int32_t* epoch,

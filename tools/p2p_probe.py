@@ -58,10 +58,12 @@ def main():
         W = torch.randn(R, D, device=dev)
         idx = torch.randint(0, R, (B * world * 3,), device=dev)
         off = torch.arange(0, B * world * 3, 3, device=dev)
-        out = torch.zeros(B, 2, D, device=dev)
+        backing = torch.zeros(8 << 20, device=dev)      # 32 MB: a cudaMalloc segment of its own
+        out = backing[4096:4096 + B * 2 * D].view(B, 2, D)
         torch.cuda.synchronize()
-        info = out.untyped_storage()._share_cuda_()
-        mine = (bytes(info[1]), int(info[3]) + out.storage_offset() * 4)
+        hb, ob = C.create_string_buffer(64), C.c_int64()
+        _lib.check(lib.dlrm_b200_ipc_export(out.data_ptr(), hb, C.byref(ob)), "ipc_export")
+        mine = (hb.raw, int(ob.value))
         allo = [None] * world
         dist.all_gather_object(allo, mine)
         ptrs = []
