@@ -419,8 +419,9 @@ def main():
                     help="training steps per CUDA graph (cross-step overlap of the embedding update; measured "
                          "neutral at CFG2 -- the step is bound by the sum of kernel work, not by its critical path)")
     ap.add_argument("--no-pipeline", action="store_true")
-    ap.add_argument("--exchange", default="nccl", choices=["p2p", "nccl"],
-                    help="N>1: pooled-vector exchange fused into the kernels over peer memory, or NCCL all-to-all")
+    ap.add_argument("--exchange", default="auto", choices=["auto", "p2p", "nccl"],
+                    help="N>1: pooled-vector / gradient exchange fused into the kernels over NVLink peer memory (p2p), or "
+                         "NCCL all-to-all; auto = p2p when every GPU pair has peer access, else nccl")
     ap.add_argument("--cpu-budget", type=float, default=15.0)
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()

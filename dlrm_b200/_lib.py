@@ -58,7 +58,7 @@ SYMBOLS = [
     "dlrm_b200_abi_version", "dlrm_b200_last_error", "dlrm_b200_device_info",
     "dlrm_b200_emb_bag_fwd", "dlrm_b200_emb_bag_fwd_train", "dlrm_b200_emb_bwd_link",
     "dlrm_b200_emb_bwd_update", "dlrm_b200_head_scratch_bytes", "dlrm_b200_head_fused",
-    "dlrm_b200_interact_fwd_ex", "dlrm_b200_interact_bwd_ex", "dlrm_b200_act_bwd",
+    "dlrm_b200_interact_fwd_ex", "dlrm_b200_interact_bwd_ex", "dlrm_b200_interact_bwd_p2p", "dlrm_b200_act_bwd",
     "dlrm_b200_emb_bag_fwd_p2p", "dlrm_b200_emb_bwd_update_p2p", "dlrm_b200_emb_bwd_classify",
     "dlrm_b200_p2p_barrier", "dlrm_b200_p2p_allreduce_mean", "dlrm_b200_enable_peer_access",
     "dlrm_b200_ipc_export", "dlrm_b200_ipc_open", "dlrm_b200_ipc_close",
@@ -103,6 +103,8 @@ def _declare(lib):
     lib.dlrm_b200_linear_dgrad.argtypes = [vp, i64, vp, i64, vp, i64, i32, vp, i64, i64, i64, i64, i32, vp]
     lib.dlrm_b200_linear_wgrad.argtypes = [vp, i64, vp, i64, vp, i64, vp, i64, i64, i64, i32, vp]
     lib.dlrm_b200_interact_fwd.argtypes = [vp, i64, vp, i64, i64, i32, i32, i32, vp]
+    lib.dlrm_b200_interact_bwd_p2p.argtypes = [vp, i64, vp, i64, C.POINTER(vp), C.POINTER(i64), i64, i32, i32, i32, i32,
+                                               vp, vp, i64, vp]
     lib.dlrm_b200_interact_bwd.argtypes = [vp, i64, vp, i64, vp, i64, i64, i32, i32, i32, i32, vp]
     lib.dlrm_b200_loss_fwd_bwd.argtypes = [vp, vp, vp, i64, i32, f32, i32, vp, vp, vp, vp]
     lib.dlrm_b200_dense_update.argtypes = [vp, vp, vp, i64, i32, f32, f32, vp]

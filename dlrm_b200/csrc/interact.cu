@@ -188,14 +188,26 @@ __global__ void __launch_bounds__(192) interact_fwd2_kernel(const float* __restr
 // One thread owns a column d of one sample: T[:, d] lives in registers, S rows are read as
 // broadcast float4 from shared memory.
 // ------------------------------------------------------------------------------------------
-template <int MAXF>
+// ROUTE: feature i's gradient rows go to route.base[i] + sample * route.ld[i] instead of dT -- on a sharded
+// run base[1 + t] points into the buffer of the rank that owns table t (NVLink peer store, 512-byte
+// rows), so the gradient exchange rides on this kernel's stores and needs no all-to-all.
+struct FeatRoute {
+  float* base[64];
+  long long ld[64];
+};
+
+struct NoRoute {};
+
+template <int MAXF, typename Route>
 __global__ void __launch_bounds__(128) interact_bwd_kernel(const float* __restrict__ T, long long ldt,
                                                            const float* __restrict__ dR, long long lddr,
                                                            float* __restrict__ dT, long long lddt,
                                                            long long batch, int F, int D, int itself,
                                                            int mask0, int spb,
                                                            __nv_bfloat16* __restrict__ g0h,
-                                                           __nv_bfloat16* __restrict__ g0l, long long ldg0) {
+                                                           __nv_bfloat16* __restrict__ g0l, long long ldg0,
+                                                           const __grid_constant__ Route route) {
+  constexpr bool ROUTE = sizeof(Route) > 8;
   extern __shared__ __align__(128) float smem[];
   const int F4 = (F + 3) & ~3;
   const long long s0 = (long long)blockIdx.x * spb;
@@ -240,7 +252,8 @@ __global__ void __launch_bounds__(128) interact_bwd_kernel(const float* __restri
       }
       if (i == 0 && mask0 == DLRM_ACT_RELU) acc = (t[0] > 0.f) ? acc : 0.f;
       if (i == 0 && mask0 == DLRM_ACT_SIGMOID) acc *= (1.0f - t[0]) * t[0];
-      out[(long long)i * D] = acc;
+      if constexpr (ROUTE) route.base[i][(s0 + s) * route.ld[i] + d] = acc;
+      else out[(long long)i * D] = acc;
       if (i == 0 && g0h) {  // feature 0 = gradient into the bottom MLP: also as a (hi, lo) bf16 pair
         const __nv_bfloat16 hb = __float2bfloat16_rn(acc);
         g0h[(s0 + s) * ldg0 + d] = hb;
@@ -311,15 +324,16 @@ extern "C" int dlrm_b200_interact_fwd(const float* T, int64_t ldt, float* R, int
   return dlrm_b200_interact_fwd_ex(T, ldt, R, ldr, nullptr, nullptr, 0, batch, num_features, dim, itself, stream);
 }
 
-extern "C" int dlrm_b200_interact_bwd_ex(const float* T, int64_t ldt, const float* dR, int64_t lddr,
-                                         float* dT, int64_t lddt, int64_t batch, int num_features,
-                                         int dim, int itself, int mask_feature0, void* g0_hi, void* g0_lo,
-                                         int64_t ld_g0, void* stream) {
-  using namespace dlrm;
+namespace dlrm {
+static int interact_bwd_launch(const float* T, int64_t ldt, const float* dR, int64_t lddr, float* dT,
+                               int64_t lddt, const FeatRoute* route, int64_t batch, int num_features,
+                               int dim, int itself, int mask_feature0, void* g0_hi, void* g0_lo,
+                               int64_t ld_g0, void* stream) {
   if (batch == 0) return 0;
   const int F = num_features, D = dim;
   if (F < 1 || D < 1) return set_error("interact_bwd: F=%d D=%d", F, D);
   if (F > 64) return set_error("interact_bwd: num_features=%d > 64 not supported yet", F);
+  if (!T || !dR || (!dT && !route)) return set_error("interact_bwd: NULL pointer");
   const int F4 = (F + 3) & ~3;
   int spb = 128 / D;
   if (spb < 1) spb = 1;
@@ -329,14 +343,45 @@ extern "C" int dlrm_b200_interact_bwd_ex(const float* T, int64_t ldt, const floa
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   __nv_bfloat16* gh = static_cast<__nv_bfloat16*>(g0_hi);
   __nv_bfloat16* gl = static_cast<__nv_bfloat16*>(g0_lo);
-  if (F <= 8)
-    interact_bwd_kernel<8><<<(unsigned)grid, 128, smem, st>>>(T, ldt, dR, lddr, dT, lddt, batch, F, D, itself, mask_feature0, spb, gh, gl, ld_g0);
-  else if (F <= 32)
-    interact_bwd_kernel<32><<<(unsigned)grid, 128, smem, st>>>(T, ldt, dR, lddr, dT, lddt, batch, F, D, itself, mask_feature0, spb, gh, gl, ld_g0);
-  else
-    interact_bwd_kernel<64><<<(unsigned)grid, 128, smem, st>>>(T, ldt, dR, lddr, dT, lddt, batch, F, D, itself, mask_feature0, spb, gh, gl, ld_g0);
+#define DLRM_IB(MAXF)                                                                                         \
+  if (route)                                                                                                  \
+    interact_bwd_kernel<MAXF, FeatRoute><<<(unsigned)grid, 128, smem, st>>>(T, ldt, dR, lddr, dT, lddt, batch, F, D, \
+                                                                       itself, mask_feature0, spb, gh, gl, ld_g0, *route); \
+  else                                                                                                        \
+    interact_bwd_kernel<MAXF, NoRoute><<<(unsigned)grid, 128, smem, st>>>(T, ldt, dR, lddr, dT, lddt, batch, F, D, \
+                                                                        itself, mask_feature0, spb, gh, gl, ld_g0, NoRoute{})
+  if (F <= 8) { DLRM_IB(8); }
+  else if (F <= 32) { DLRM_IB(32); }
+  else { DLRM_IB(64); }
+#undef DLRM_IB
   DLRM_CHECK_LAUNCH("interact_bwd_kernel");
   return 0;
+}
+}  // namespace dlrm
+
+extern "C" int dlrm_b200_interact_bwd_ex(const float* T, int64_t ldt, const float* dR, int64_t lddr,
+                                         float* dT, int64_t lddt, int64_t batch, int num_features,
+                                         int dim, int itself, int mask_feature0, void* g0_hi, void* g0_lo,
+                                         int64_t ld_g0, void* stream) {
+  return dlrm::interact_bwd_launch(T, ldt, dR, lddr, dT, lddt, nullptr, batch, num_features, dim, itself,
+                                   mask_feature0, g0_hi, g0_lo, ld_g0, stream);
+}
+
+extern "C" int dlrm_b200_interact_bwd_p2p(const float* T, int64_t ldt, const float* dR, int64_t lddr,
+                                          void* const* feat_dst, const int64_t* feat_ld, int64_t batch,
+                                          int num_features, int dim, int itself, int mask_feature0,
+                                          void* g0_hi, void* g0_lo, int64_t ld_g0, void* stream) {
+  using namespace dlrm;
+  if (!feat_dst || !feat_ld) return set_error("interact_bwd_p2p: NULL route");
+  if (num_features > 64) return set_error("interact_bwd_p2p: num_features=%d > 64", num_features);
+  FeatRoute r = {};
+  for (int i = 0; i < num_features; ++i) {
+    if (!feat_dst[i]) return set_error("interact_bwd_p2p: feat_dst[%d] is NULL", i);
+    r.base[i] = static_cast<float*>(feat_dst[i]);
+    r.ld[i] = feat_ld[i];
+  }
+  return interact_bwd_launch(T, ldt, dR, lddr, nullptr, 0, &r, batch, num_features, dim, itself,
+                             mask_feature0, g0_hi, g0_lo, ld_g0, stream);
 }
 
 extern "C" int dlrm_b200_interact_bwd(const float* T, int64_t ldt, const float* dR, int64_t lddr,

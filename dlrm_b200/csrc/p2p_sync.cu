@@ -34,7 +34,7 @@ __global__ void __launch_bounds__(32) p2p_barrier_kernel(PeerPtrs sig, int rank,
     volatile int* mine = static_cast<volatile int*>(sig.p[rank]) + t;     // rank t's slot on me
     long long spins = 0;
     while (*mine < e) {
-      if (++spins > (1ll << 31)) __trap();   // a lost peer must trap, not hang the GPU forever
+      if (++spins > (1ll << 28)) __trap();   // a lost peer must trap, not hang the GPU forever
     }
     __threadfence_system();
   }

@@ -138,8 +138,10 @@ class DistEngine:
 
     # ------------------------------------------------------------------ peer-mapped exchange
     def _setup_p2p(self):
-        """Map every rank's interaction operand T and its gradient dT into this process (CUDA IPC over
-        NVLink).  peer_T[d] / peer_dT[s] point at feature (1 + my first table) of rank d's / s's buffer."""
+        """Map every rank's interaction operand T and gradient receive buffer into this process (CUDA IPC
+        over NVLink).  Both directions PUSH: the gather stores pooled rows into the T of the rank that owns
+        the sample, interact_bwd stores per-table gradient rows into the receive buffer of the table's owner;
+        every load on the data path stays local (L2-cacheable)."""
         import ctypes as C
 
         e = self.eng
@@ -159,7 +161,11 @@ class DistEngine:
             _l.check(e.lib.dlrm_b200_ipc_export(t.data_ptr(), h, C.byref(off)), "ipc_export")
             return h.raw, int(off.value)
 
-        mine = tuple(export(t) for t in (e.Tbuf, e.dT, self._sig, e.dense_grad))
+        # gradient receive buffer: slab s = [B, Tl, D] written by rank s's interact_bwd (push over NVLink)
+        self._grecv_p2p = torch.zeros(self.world * self.B * max(self.Tl, 1) * self.D, dtype=torch.float32,
+                                      device=self.device)
+        torch.cuda.synchronize()
+        mine = tuple(export(t) for t in (e.Tbuf, self._grecv_p2p, self._sig, e.dense_grad))
         allh = [None] * self.world
         dist.all_gather_object(allh, mine)
         self._ipc_bases = {}
@@ -175,16 +181,28 @@ class DistEngine:
 
         for r in range(self.world):
             if r == self.rank:
-                ptrs = [e.Tbuf.data_ptr(), e.dT.data_ptr(), self._sig.data_ptr(), e.dense_grad.data_ptr()]
+                ptrs = [e.Tbuf.data_ptr(), self._grecv_p2p.data_ptr(), self._sig.data_ptr(), e.dense_grad.data_ptr()]
             else:
                 ptrs = [imp(hd, off) for hd, off in allh[r]]
             pT.append(ptrs[0] + col)
-            pdT.append(ptrs[1] + col)
+            pdT.append(ptrs[1])
             psig.append(ptrs[2])
             pgrad.append(ptrs[3])
         W = self.world
         self._peer_T = (C.c_void_p * W)(*pT)
-        self._peer_dT = (C.c_void_p * W)(*pdT)
+        # update side: slab s of MY receive buffer holds the gradients of rank s's samples
+        slab = self.B * self.Tl * self.D * 4
+        self._peer_dT = (C.c_void_p * W)(*[self._grecv_p2p.data_ptr() + s_ * slab for s_ in range(W)])
+        # interact_bwd side: feature 1 + t -> slab `rank` of the owner of table t; feature 0 stays local
+        dst, ld = [e.dT.data_ptr()], [e.F * self.D]
+        for r in range(W):
+            lo, hi = self.slices[r]
+            tl_r = hi - lo
+            for t in range(lo, hi):
+                dst.append(pdT[r] + (self.rank * self.B * tl_r * self.D + (t - lo) * self.D) * 4)
+                ld.append(tl_r * self.D)
+        assert len(dst) == e.F
+        e.dT_route = ((C.c_void_p * e.F)(*dst), (C.c_int64 * e.F)(*ld))
         self._peer_sig = [(C.c_void_p * W)(*[p + 64 * ch for p in psig]) for ch in range(2)]
         self._peer_grad = (C.c_void_p * W)(*pgrad)
         self.own_sync = os.environ.get("DLRM_P2P_NCCL_SYNC") != "1"   # our kernels instead of NCCL all_reduce
@@ -252,12 +270,13 @@ class DistEngine:
         import ctypes as C
 
         e = self.eng
-        self._barrier()       # every rank's dT is complete
+        self._barrier()       # every rank's interact_bwd stores have landed in my receive buffer
         FD = e.F * self.D
         bdesc, _ = e._bwd_desc_chunk(sp, list(range(self.Tl)))
         _lib.check(e.lib.dlrm_b200_emb_bwd_update_p2p(bdesc, self.Tl, self.D, sp.batch, sp.idx_bytes,
                                                       int(sp.include_last), e.link.data_ptr(), self._peer_dT,
-                                                      self.world, self.B, FD, self.D, _OPT[optimizer], clr,
+                                                      self.world, self.B, self.Tl * self.D, self.D,
+                                                      _OPT[optimizer], clr,
                                                       1e-10, C.byref(e.dedup) if e._filtered else None, _stream()),
                    "emb_bwd_update_p2p")
         e.n_launch += 1
@@ -328,8 +347,15 @@ def bench_main(args, CFG, metric_name, config_dict, ClockSampler):
     D, T, B = CFG["m_spa"], CFG["T"], CFG["B"]
     ln_emb = [CFG["rows"]] * T
     ln_top = [D + (T + 1) * T // 2] + CFG["top_tail"]
+    exchange = getattr(args, "exchange", "auto")
+    if exchange == "auto":
+        # capability check, same answer on every rank (one node): peer access between all GPU pairs
+        n = torch.cuda.device_count()
+        ok = world <= n and all(torch.cuda.can_device_access_peer(a, b)
+                                for a in range(world) for b in range(world) if a != b)
+        exchange = "p2p" if ok else "nccl"
     de = DistEngine(D, ln_emb, CFG["ln_bot"], ln_top, local_batch=B, device=dev, gemm=args.gemm,
-                    exchange=getattr(args, "exchange", "nccl"))
+                    exchange=exchange)
     de.eng.init_params(100 + rank)
     de.sync_dense_params_from_rank0()
     de.eng.ensure_optimizer_state("rwsadagrad")

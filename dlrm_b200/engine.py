@@ -154,6 +154,7 @@ class Engine:
         self.gather_fn = None       # (sp, link) -> fills Tbuf[:, 1:, :] for the LOCAL batch
         self.update_fn = None       # (sp, optimizer, clr) -> embedding update from dT[:, 1:, :]
         self.dense_sync_fn = None   # () -> make dense_grad slab 0 the cross-rank mean gradient
+        self.dT_route = None        # (void*[F], int64[F]): per-feature destination of interact_bwd's output
         self.n_launch = 0            # kernels launched by this engine (bench: gpu_launches)
         # side streams: the gather runs beside the bottom MLP, the weight-gradient GEMMs and the
         # embedding update beside the dgrad chain (independent work; parallel branches in the graph)
@@ -554,10 +555,13 @@ class Engine:
         if self.op == "dot":
             self.mlp_backward("top", xin, ldx, ACT_NONE, B, self.top_act, top_ld, self.top_gz, top_ld,
                               self.dR, self.ldr)
-            _lib.check(self.lib.dlrm_b200_interact_bwd(self.Tbuf.data_ptr(), FD, self.dR.data_ptr(), self.ldr,
-                                                       self.dT.data_ptr(), FD, B, self.F, self.D,
-                                                       int(self.itself), bot_last_act, _stream()),
-                       "interact_bwd")
+            if self.dT_route is not None:
+                self._interact_bwd_routed(B, bot_last_act, None, None, 0, _stream())
+            else:
+                _lib.check(self.lib.dlrm_b200_interact_bwd(self.Tbuf.data_ptr(), FD, self.dR.data_ptr(), self.ldr,
+                                                           self.dT.data_ptr(), FD, B, self.F, self.D,
+                                                           int(self.itself), bot_last_act, _stream()),
+                           "interact_bwd")
             self.n_launch += 1
         else:
             # cat: dR == dT; feature 0 additionally goes through the bottom MLP's last activation
@@ -686,6 +690,14 @@ class Engine:
     # activation / gradient / weight is kept as a (hi, lo) bf16 pair, activations carry a
     # constant-1 column and weights a bias column, so the bias add and the bias gradient come
     # out of the GEMMs themselves.
+    def _interact_bwd_routed(self, B, bot_last_act, g0h, g0l, ldg0, stream):
+        """interact_bwd whose per-feature gradient rows go straight to their (possibly remote) consumers."""
+        dst, ld = self.dT_route
+        _lib.check(self.lib.dlrm_b200_interact_bwd_p2p(self.Tbuf.data_ptr(), self.F * self.D, self.dR.data_ptr(),
+                                                       self.ldr, dst, ld, B, self.F, self.D, int(self.itself),
+                                                       bot_last_act, g0h, g0l, ldg0, stream),
+                   "interact_bwd_p2p")
+
     def _fork(self, side):
         """side stream starts after everything enqueued so far on the current stream."""
         ev = torch.cuda.Event()
@@ -963,10 +975,14 @@ class Engine:
         self._tc_mlp_backward("top", B)
         bot_last_act = self._act("bot", len(self.ln_bot) - 2)
         g0h, g0l, ldg0 = self.tc_gz["bot"][-1]
-        _lib.check(self.lib.dlrm_b200_interact_bwd_ex(self.Tbuf.data_ptr(), FD, self.dR.data_ptr(), self.ldr,
-                                                      self.dT.data_ptr(), FD, B, self.F, self.D, int(self.itself),
-                                                      bot_last_act, g0h.data_ptr(), g0l.data_ptr(), ldg0, s),
-                   "interact_bwd_ex")
+        if self.dT_route is not None:
+            self._interact_bwd_routed(B, bot_last_act, g0h.data_ptr(), g0l.data_ptr(), ldg0, s)
+        else:
+            _lib.check(self.lib.dlrm_b200_interact_bwd_ex(self.Tbuf.data_ptr(), FD, self.dR.data_ptr(), self.ldr,
+                                                          self.dT.data_ptr(), FD, B, self.F, self.D,
+                                                          int(self.itself), bot_last_act, g0h.data_ptr(),
+                                                          g0l.data_ptr(), ldg0, s),
+                       "interact_bwd_ex")
         self.n_launch += 1
         has_emb = self.T > 0 or self.update_fn is not None
         if update is not None and has_emb:

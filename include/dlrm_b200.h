@@ -227,6 +227,14 @@ int dlrm_b200_interact_fwd_ex(const float* T, int64_t ldt, float* R, int64_t ldr
 int dlrm_b200_interact_bwd_ex(const float* T, int64_t ldt, const float* dR, int64_t lddr, float* dT,
                               int64_t lddt, int64_t batch, int num_features, int dim, int itself,
                               int mask_feature0, void* g0_hi, void* g0_lo, int64_t ld_g0, void* stream);
+/* Sharded variant: feature i's gradient rows are stored at feat_dst[i] + sample * feat_ld[i] (floats)
+ * instead of dT.  On a table-wise sharded run feat_dst[1 + t] points into the receive buffer of the rank
+ * that owns table t (peer-mapped over NVLink), which replaces the backward all-to-all of
+ * dlrm_s_pytorch.py:545-560 / extend_distributed.py:alltoall backward; feat_dst[0] stays local. */
+int dlrm_b200_interact_bwd_p2p(const float* T, int64_t ldt, const float* dR, int64_t lddr,
+                               void* const* feat_dst /*[host][F]*/, const int64_t* feat_ld /*[host][F]*/,
+                               int64_t batch, int num_features, int dim, int itself, int mask_feature0,
+                               void* g0_hi, void* g0_lo, int64_t ld_g0, void* stream);
 int dlrm_b200_interact_bwd(const float* T, int64_t ldt, const float* dR, int64_t lddr,
                            float* dT, int64_t lddt, int64_t batch, int num_features, int dim,
                            int itself, int mask_feature0, void* stream);

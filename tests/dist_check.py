@@ -28,6 +28,8 @@ def main():
     gemm = os.environ.get("DLRM_GEMM", "tc")
     exchange = os.environ.get("DLRM_EXCHANGE", "nccl")
     D, ln_emb, ln_bot = 128, [3000, 500, 40, 1000, 77], [13, 64, 128]
+    if world > 4:      # uneven table-wise slices (2 or 1 tables per rank at world 8)
+        ln_emb = ln_emb + [250, 1200, 64, 900, 333, 2100]
     Tg = len(ln_emb)
     ln_top = [D + (Tg + 1) * Tg // 2, 64, 32, 1]
     B = 96

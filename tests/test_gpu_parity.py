@@ -267,3 +267,42 @@ def test_cfg1_full_size_gather_properties():
         rows = torch.from_numpy(idx[offs[k, 0]:offs[k, B]]).to(DEV)
         tot += float(e.table(k)[rows].double().sum().item())
     assert abs(float(out.double().sum().item()) - tot) < 1e-6 * max(1.0, abs(tot)) + 1e-3
+
+
+# ----------------------------------------------------------------------------- routed interaction backward
+@pytest.mark.parametrize("F,D,itself", [(4, 16, 0), (27, 128, 0), (9, 64, 1), (40, 32, 0)])
+def test_interact_bwd_routed_equals_plain(F, D, itself):
+    """interact_bwd_p2p (per-feature destinations, the sharded gradient exchange) writes exactly the
+    values interact_bwd writes, into an arbitrary per-feature layout (here: two 'owner' slabs)."""
+    from dlrm_b200 import _lib
+
+    lib = _lib.lib()
+    B = 300
+    torch.manual_seed(F * 131 + D)
+    npairs = F * (F + 1) // 2 if itself else F * (F - 1) // 2
+    T = torch.randn(B, F * D, device=DEV)
+    dR = torch.randn(B, D + npairs, device=DEV)
+    dT = torch.zeros(B, F * D, device=DEV)
+    s = torch.cuda.current_stream().cuda_stream
+    _lib.check(lib.dlrm_b200_interact_bwd(T.data_ptr(), F * D, dR.data_ptr(), D + npairs, dT.data_ptr(), F * D,
+                                          B, F, D, itself, 1, s), "interact_bwd")
+    # features 1..h -> slab A [B, h, D] (at an offset, like slab `rank` of a peer); the rest -> slab B
+    h = (F - 1) // 2
+    f0 = torch.zeros(B, D, device=DEV)
+    slabA = torch.zeros(2, B, max(h, 1), D, device=DEV)
+    slabB = torch.zeros(B, max(F - 1 - h, 1), D, device=DEV)
+    dst, ld = [f0.data_ptr()], [D]
+    for i in range(1, F):
+        if i - 1 < h:
+            dst.append(slabA[1].data_ptr() + (i - 1) * D * 4); ld.append(h * D)
+        else:
+            dst.append(slabB.data_ptr() + (i - 1 - h) * D * 4); ld.append((F - 1 - h) * D)
+    _lib.check(lib.dlrm_b200_interact_bwd_p2p(T.data_ptr(), F * D, dR.data_ptr(), D + npairs,
+                                              (C.c_void_p * F)(*dst), (C.c_int64 * F)(*ld), B, F, D, itself, 1,
+                                              None, None, 0, s), "interact_bwd_p2p")
+    torch.cuda.synchronize()
+    ref = dT.view(B, F, D)
+    assert torch.equal(f0, ref[:, 0])
+    assert torch.equal(slabA[1][:, :h], ref[:, 1:1 + h])
+    assert torch.equal(slabB[:, :F - 1 - h], ref[:, 1 + h:])
+    assert float(slabA[0].abs().sum()) == 0.0
