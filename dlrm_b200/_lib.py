@@ -13,7 +13,8 @@ ACT_NONE, ACT_RELU, ACT_SIGMOID = 0, 1, 2
 LOSS_MSE, LOSS_BCE, LOSS_WBCE = 0, 1, 2
 OPT_SGD, OPT_RWSADAGRAD = 0, 1
 GEMM_SIMT_FP32, GEMM_TC_BF16X3, GEMM_TC_BF16 = 0, 1, 2
-TUNE = dict(emb_bags_per_group=0, emb_unroll=1, emb_block=2, upd_block=3, gemm_splitk=4)
+TUNE = dict(emb_bags_per_group=0, emb_unroll=1, emb_block=2, upd_block=3, gemm_splitk=4, gemm_smem_kb=5,
+            head_rows=6, interact_bwd_cols=7)
 
 
 class EmbFwdTable(C.Structure):
@@ -139,6 +140,11 @@ def lib():
         _declare(_lib)
         if _lib.dlrm_b200_abi_version() != 1:
             raise RuntimeError("libdlrm_b200.so ABI mismatch")
+        # experiment knob: DLRM_TUNE="name=value,name=value" (names in TUNE) applied once at load
+        for kv in filter(None, os.environ.get("DLRM_TUNE", "").split(",")):
+            k, v = kv.split("=")
+            if _lib.dlrm_b200_set_tunable(TUNE[k.strip()], int(v)) != 0:
+                raise RuntimeError("DLRM_TUNE: " + _lib.dlrm_b200_last_error().decode())
     return _lib
 
 

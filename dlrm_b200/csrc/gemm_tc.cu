@@ -458,6 +458,14 @@ extern "C" int dlrm_b200_gemm_tc_plan_create(const dlrm_gemm_tc_desc_t* d, void*
     if (d->N <= 32) bn = 32; else if (d->N <= 64 && bn > 64) bn = 64;
   }
   if (a.b_mn && bn < 64) bn = 64;  // MN-major boxes are 64 wide
+  // operand-ring budget: 200 KB = deepest pipeline, one CTA per SM; ~100 KB lets two CTAs (of this or of
+  // a concurrent GEMM on another stream) share an SM, which hides the latency of these small problems
+  int budget_kb = get_tunable(TUNE_GEMM_SMEM_KB);
+  if (budget_kb <= 0 || budget_kb > 200) budget_kb = 200;
+  if (budget_kb < 48) budget_kb = 48;
+  if (!(d->tile_n == 128) && bn == 128 &&
+      (size_t)budget_kb * 1024 < 2 * (size_t)(a.x3 ? 2 : 1) * (TC_BM * TC_BK * 2 + 128 * TC_BK * 2))
+    bn = 64;                       // two stages of a 128-wide tile would not fit the budget
   p->bn = bn;
   a.num_kb = (int)((d->K + TC_BK - 1) / TC_BK);
   int splits = d->split_k > 1 ? d->split_k : 1;
@@ -469,8 +477,9 @@ extern "C" int dlrm_b200_gemm_tc_plan_create(const dlrm_gemm_tc_desc_t* d, void*
     delete p; return set_error("gemm_tc: split-K only supports fp32 slab outputs");
   }
   const size_t stage_bytes = (size_t)(a.x3 ? 2 : 1) * (TC_BM * TC_BK * 2 + bn * TC_BK * 2);
-  int stages = (int)((200 * 1024) / stage_bytes);
+  int stages = (int)(((size_t)budget_kb * 1024) / stage_bytes);
   if (stages > 8) stages = 8;
+  if (stages < 2) stages = 2;
   if (stages > a.kb_per_split) stages = a.kb_per_split < 2 ? 2 : a.kb_per_split;
   p->stages = stages;
   p->smem = stages * stage_bytes + (2 * stages + 1) * 8 + 16 + 1024;

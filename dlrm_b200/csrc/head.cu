@@ -29,8 +29,9 @@ struct HeadArgs {
   float thr;
 };
 
-constexpr int HEAD_ROWS = 32;
+constexpr int HEAD_ROWS_MIN = 16;   // scratch is sized for the smaller tile
 
+template <int HEAD_ROWS>
 __global__ void __launch_bounds__(256) head_kernel(const HeadArgs a) {
   __shared__ float s_gz[HEAD_ROWS], s_loss[HEAD_ROWS];
   __shared__ bool s_last;
@@ -145,7 +146,7 @@ __global__ void __launch_bounds__(256) head_kernel(const HeadArgs a) {
 }  // namespace dlrm
 
 extern "C" int64_t dlrm_b200_head_scratch_bytes(int64_t batch, int64_t K) {
-  const int64_t nb = (batch + dlrm::HEAD_ROWS - 1) / dlrm::HEAD_ROWS;
+  const int64_t nb = (batch + dlrm::HEAD_ROWS_MIN - 1) / dlrm::HEAD_ROWS_MIN;
   return 16 + nb * (K + 2) * 4;
 }
 
@@ -171,8 +172,11 @@ extern "C" int dlrm_b200_head_fused(const float* h, int64_t ldh, const float* w,
   a.partial = scratch ? reinterpret_cast<float*>(static_cast<char*>(scratch) + 16) : nullptr;
   a.B = batch; a.K = (int)K; a.act_last = act_last; a.act_prev = act_prev; a.loss_kind = loss_kind;
   a.thr = loss_threshold;
-  const long long nb = (batch + HEAD_ROWS - 1) / HEAD_ROWS;
-  head_kernel<<<(unsigned)nb, 256, 0, static_cast<cudaStream_t>(stream)>>>(a);
+  // 16 samples per CTA: 128 CTAs at batch 2048 (one wave of the 148 SMs) instead of 64
+  const int rows = get_tunable(TUNE_HEAD_ROWS) == 32 ? 32 : 16;
+  const long long nb = (batch + rows - 1) / rows;
+  if (rows == 32) head_kernel<32><<<(unsigned)nb, 256, 0, static_cast<cudaStream_t>(stream)>>>(a);
+  else head_kernel<16><<<(unsigned)nb, 256, 0, static_cast<cudaStream_t>(stream)>>>(a);
   DLRM_CHECK_LAUNCH("head_kernel");
   return 0;
 }

@@ -263,6 +263,84 @@ __global__ void __launch_bounds__(128) interact_bwd_kernel(const float* __restri
   }
 }
 
+
+// Two adjacent columns per thread (float2): every S value read from shared memory feeds two FMAs, and a
+// warp moves 256 contiguous bytes per feature row.  Needs an even D and 8-byte aligned rows.
+template <int MAXF, typename Route>
+__global__ void __launch_bounds__(128) interact_bwd2_kernel(const float* __restrict__ T, long long ldt,
+                                                            const float* __restrict__ dR, long long lddr,
+                                                            float* __restrict__ dT, long long lddt,
+                                                            long long batch, int F, int D, int itself,
+                                                            int mask0, int spb,
+                                                            __nv_bfloat16* __restrict__ g0h,
+                                                            __nv_bfloat16* __restrict__ g0l, long long ldg0,
+                                                            const __grid_constant__ Route route) {
+  constexpr bool ROUTE = sizeof(Route) > 8;
+  extern __shared__ __align__(128) float smem[];
+  const int F4 = (F + 3) & ~3;
+  const int D2 = D >> 1;
+  const long long s0 = (long long)blockIdx.x * spb;
+  const int ns = (int)min((long long)spb, batch - s0);
+  // S[s][i][j] = dZ + dZ^T, row stride F4, zero padded; one (s, i) row per loop trip, j = inner lanes
+  for (int row = threadIdx.x / F4; row < ns * F; row += blockDim.x / F4) {
+    const int j = threadIdx.x % F4;
+    if (threadIdx.x / F4 >= blockDim.x / F4) break;
+    const int s = row / F, i = row - s * F;
+    float v = 0.f;
+    if (j < F) {
+      const float* g = dR + (s0 + s) * lddr + D;
+      if (i == j) {
+        if (itself) v = 2.f * g[i * (i + 1) / 2 + i];
+      } else {
+        const int hi = i > j ? i : j, lo = i > j ? j : i;
+        v = g[itself ? hi * (hi + 1) / 2 + lo : hi * (hi - 1) / 2 + lo];
+      }
+    }
+    smem[row * F4 + j] = v;
+  }
+  __syncthreads();
+  for (int item = threadIdx.x; item < ns * D2; item += blockDim.x) {
+    const int s = item / D2, d = (item - s * D2) * 2;
+    const float* Tb = T + (s0 + s) * ldt + d;
+    float2 t[MAXF];
+#pragma unroll
+    for (int j = 0; j < MAXF; ++j)
+      t[j] = (j < F) ? *reinterpret_cast<const float2*>(Tb + (long long)j * D) : make_float2(0.f, 0.f);
+    const float* Ss = smem + s * F * F4;
+    for (int i = 0; i < F; ++i) {
+      float2 acc = make_float2(0.f, 0.f);
+      if (i == 0) acc = *reinterpret_cast<const float2*>(dR + (s0 + s) * lddr + d);
+#pragma unroll
+      for (int j4 = 0; j4 < MAXF / 4; ++j4) {
+        if (j4 * 4 < F) {
+          const float4 sv = *reinterpret_cast<const float4*>(Ss + i * F4 + j4 * 4);
+          acc.x = fmaf(sv.x, t[j4 * 4 + 0].x, acc.x); acc.y = fmaf(sv.x, t[j4 * 4 + 0].y, acc.y);
+          acc.x = fmaf(sv.y, t[j4 * 4 + 1].x, acc.x); acc.y = fmaf(sv.y, t[j4 * 4 + 1].y, acc.y);
+          acc.x = fmaf(sv.z, t[j4 * 4 + 2].x, acc.x); acc.y = fmaf(sv.z, t[j4 * 4 + 2].y, acc.y);
+          acc.x = fmaf(sv.w, t[j4 * 4 + 3].x, acc.x); acc.y = fmaf(sv.w, t[j4 * 4 + 3].y, acc.y);
+        }
+      }
+      if (i == 0 && mask0 == DLRM_ACT_RELU) {
+        acc.x = (t[0].x > 0.f) ? acc.x : 0.f;
+        acc.y = (t[0].y > 0.f) ? acc.y : 0.f;
+      }
+      if (i == 0 && mask0 == DLRM_ACT_SIGMOID) {
+        acc.x *= (1.0f - t[0].x) * t[0].x;
+        acc.y *= (1.0f - t[0].y) * t[0].y;
+      }
+      if constexpr (ROUTE) *reinterpret_cast<float2*>(route.base[i] + (s0 + s) * route.ld[i] + d) = acc;
+      else *reinterpret_cast<float2*>(dT + (s0 + s) * lddt + (long long)i * D + d) = acc;
+      if (i == 0 && g0h) {  // feature 0 = gradient into the bottom MLP: also as a (hi, lo) bf16 pair
+        const __nv_bfloat162 hb = __floats2bfloat162_rn(acc.x, acc.y);
+        *reinterpret_cast<__nv_bfloat162*>(g0h + (s0 + s) * ldg0 + d) = hb;
+        if (g0l)
+          *reinterpret_cast<__nv_bfloat162*>(g0l + (s0 + s) * ldg0 + d) =
+              __floats2bfloat162_rn(acc.x - __low2float(hb), acc.y - __high2float(hb));
+      }
+    }
+  }
+}
+
 }  // namespace dlrm
 
 extern "C" int dlrm_b200_interact_fwd_ex(const float* T, int64_t ldt, float* R, int64_t ldr, void* R_hi,
@@ -335,24 +413,39 @@ static int interact_bwd_launch(const float* T, int64_t ldt, const float* dR, int
   if (F > 64) return set_error("interact_bwd: num_features=%d > 64 not supported yet", F);
   if (!T || !dR || (!dT && !route)) return set_error("interact_bwd: NULL pointer");
   const int F4 = (F + 3) & ~3;
-  int spb = 128 / D;
-  if (spb < 1) spb = 1;
-  const size_t smem = (size_t)spb * F * F4 * sizeof(float);
-  if (smem > 48 * 1024) return set_error("interact_bwd: shared memory %zu too large", smem);
-  const long long grid = (batch + spb - 1) / spb;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   __nv_bfloat16* gh = static_cast<__nv_bfloat16*>(g0_hi);
   __nv_bfloat16* gl = static_cast<__nv_bfloat16*>(g0_lo);
-#define DLRM_IB(MAXF)                                                                                         \
+  // float2 variant: even D, 8-byte aligned rows everywhere
+  auto even8 = [](const void* p, long long ld) { return (reinterpret_cast<uintptr_t>(p) & 7) == 0 && (ld & 1) == 0; };
+  bool two = get_tunable(TUNE_INTERACT_BWD_COLS) != 1 && (D % 2 == 0) && even8(T, ldt) && even8(dR, lddr) && (route || even8(dT, lddt)) &&
+             (!gh || ((reinterpret_cast<uintptr_t>(gh) & 3) == 0 && (ld_g0 & 1) == 0)) &&
+             (!gl || (reinterpret_cast<uintptr_t>(gl) & 3) == 0);
+  if (route)
+    for (int i = 0; i < F; ++i) two = two && even8(route->base[i], route->ld[i]);
+  const int cols = two ? D / 2 : D;
+  int spb = 128 / cols;
+  if (spb < 1) spb = 1;
+  while (spb > 1 && (size_t)spb * F * F4 * sizeof(float) > 48 * 1024) --spb;
+  const size_t smem = (size_t)spb * F * F4 * sizeof(float);
+  if (smem > 48 * 1024) return set_error("interact_bwd: shared memory %zu too large", smem);
+  const long long grid = (batch + spb - 1) / spb;
+#define DLRM_IB(KERNEL, MAXF)                                                                                 \
   if (route)                                                                                                  \
-    interact_bwd_kernel<MAXF, FeatRoute><<<(unsigned)grid, 128, smem, st>>>(T, ldt, dR, lddr, dT, lddt, batch, F, D, \
-                                                                       itself, mask_feature0, spb, gh, gl, ld_g0, *route); \
+    KERNEL<MAXF, FeatRoute><<<(unsigned)grid, 128, smem, st>>>(T, ldt, dR, lddr, dT, lddt, batch, F, D, itself, \
+                                                               mask_feature0, spb, gh, gl, ld_g0, *route);    \
   else                                                                                                        \
-    interact_bwd_kernel<MAXF, NoRoute><<<(unsigned)grid, 128, smem, st>>>(T, ldt, dR, lddr, dT, lddt, batch, F, D, \
-                                                                        itself, mask_feature0, spb, gh, gl, ld_g0, NoRoute{})
-  if (F <= 8) { DLRM_IB(8); }
-  else if (F <= 32) { DLRM_IB(32); }
-  else { DLRM_IB(64); }
+    KERNEL<MAXF, NoRoute><<<(unsigned)grid, 128, smem, st>>>(T, ldt, dR, lddr, dT, lddt, batch, F, D, itself,  \
+                                                             mask_feature0, spb, gh, gl, ld_g0, NoRoute{})
+  if (two) {
+    if (F <= 8) { DLRM_IB(interact_bwd2_kernel, 8); }
+    else if (F <= 32) { DLRM_IB(interact_bwd2_kernel, 32); }
+    else { DLRM_IB(interact_bwd2_kernel, 64); }
+  } else {
+    if (F <= 8) { DLRM_IB(interact_bwd_kernel, 8); }
+    else if (F <= 32) { DLRM_IB(interact_bwd_kernel, 32); }
+    else { DLRM_IB(interact_bwd_kernel, 64); }
+  }
 #undef DLRM_IB
   DLRM_CHECK_LAUNCH("interact_bwd_kernel");
   return 0;

@@ -32,16 +32,23 @@ struct DenseLayer {
 };
 struct DenseLayers {
   DenseLayer l[16];
+  int cta_begin[17];
+  int num_layers;
   int optimizer;
   float lr, eps;
 };
 
 __global__ void __launch_bounds__(256) dense_update_pack_kernel(const __grid_constant__ DenseLayers P) {
-  const DenseLayer& L = P.l[blockIdx.y];
-  const long long total = (long long)L.N * (L.K + 1);
-  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total;
-       e += (long long)gridDim.x * blockDim.x) {
-    const int n = (int)(e / (L.K + 1)), k = (int)(e - (long long)n * (L.K + 1));
+  // flattened grid: CTAs [cta_begin[i], cta_begin[i+1]) belong to layer i, 256 elements each
+  int li = 0;
+  while (li + 1 < P.num_layers && (int)blockIdx.x >= P.cta_begin[li + 1]) ++li;
+  const DenseLayer& L = P.l[li];
+  const unsigned total = (unsigned)L.N * (unsigned)(L.K + 1);
+  const unsigned K1 = (unsigned)(L.K + 1);
+  {
+    const unsigned e = (unsigned)((int)blockIdx.x - P.cta_begin[li]) * 256u + threadIdx.x;
+    if (e >= total) return;
+    const int n = (int)(e / K1), k = (int)(e - (unsigned)n * K1);
     const bool is_b = k == L.K;
     const long long o = is_b ? n : (long long)n * L.K + k;
     const float* gp = is_b ? L.db : L.dW;
@@ -49,7 +56,7 @@ __global__ void __launch_bounds__(256) dense_update_pack_kernel(const __grid_con
     for (int s = 1; s < L.nslabs; ++s) g += gp[o + s * L.slab_stride];  // fixed order: deterministic
     if (P.optimizer == -2) {  // fold the slabs only (the caller all-reduces slab 0 next)
       const_cast<float*>(gp)[o] = g;
-      continue;
+      return;
     }
     float* pp = is_b ? L.b : L.W;
     float p = pp[o];
@@ -91,7 +98,7 @@ extern "C" int dlrm_b200_dense_update_pack(const dlrm_dense_layer_t* layers, int
   if (num_layers > 16) return set_error("dense_update_pack: at most 16 layers per call (got %d)", num_layers);
   if (optimizer > DLRM_OPT_RWSADAGRAD) return set_error("dense_update_pack: optimizer=%d", optimizer);
   DenseLayers P;
-  long long max_total = 0;
+  long long ctas = 0;
   for (int i = 0; i < num_layers; ++i) {
     const dlrm_dense_layer_t& s = layers[i];
     if (!s.W || !s.b) return set_error("dense_update_pack: layer %d NULL master", i);
@@ -105,12 +112,15 @@ extern "C" int dlrm_b200_dense_update_pack(const dlrm_dense_layer_t* layers, int
     d.slab_stride = s.slab_stride; d.N = (int)s.N; d.K = (int)s.K; d.ldp = (int)s.ld_pack;
     d.nslabs = s.num_slabs < 1 ? 1 : (int)s.num_slabs;
     const long long t = (long long)s.N * (s.K + 1);
-    max_total = t > max_total ? t : max_total;
+    if (t <= 0 || t >= (1ll << 31)) return set_error("dense_update_pack: layer %d has %lld parameters", i, t);
+    P.cta_begin[i] = (int)ctas;
+    ctas += (t + 255) / 256;
   }
+  if (ctas >= (1ll << 31)) return set_error("dense_update_pack: too many parameters");
+  for (int i = num_layers; i <= 16; ++i) P.cta_begin[i] = (int)ctas;
+  P.num_layers = num_layers;
   P.optimizer = optimizer; P.lr = lr; P.eps = eps;
-  long long gx = (max_total + 255) / 256;
-  if (gx > 2048) gx = 2048;
-  dense_update_pack_kernel<<<dim3((unsigned)gx, (unsigned)num_layers), 256, 0, static_cast<cudaStream_t>(stream)>>>(P);
+  dense_update_pack_kernel<<<(unsigned)ctas, 256, 0, static_cast<cudaStream_t>(stream)>>>(P);
   DLRM_CHECK_LAUNCH("dense_update_pack_kernel");
   return 0;
 }

@@ -22,6 +22,7 @@ HBM layout (fp32 unless noted)
 from __future__ import annotations
 
 import ctypes as C
+import os
 from dataclasses import dataclass
 from typing import List, Optional, Sequence
 
@@ -159,6 +160,7 @@ class Engine:
         # side streams: the gather runs beside the bottom MLP, the weight-gradient GEMMs and the
         # embedding update beside the dgrad chain (independent work; parallel branches in the graph)
         self.multi_stream = True
+        self.tc_smem_kb = (0, 0)    # (forward, backward) operand-ring budget of the tcgen05 GEMM plans, KB; 0 = 200
         self.s_emb = torch.cuda.Stream(device=self.device)
         self.s_wg = torch.cuda.Stream(device=self.device)
         self._gather_events = None   # optional (start, end) CUDA events recorded around the gather
@@ -764,7 +766,19 @@ class Engine:
                 Ws.append((torch.zeros((N, Kp), dtype=bf, device=dev), torch.zeros((N, Kp), dtype=bf, device=dev), Kp))
             self.tc_in[which], self.tc_gz[which], self.tc_W[which] = ins, gzs, Ws
         FD = self.F * self.D
-        GP = _lib.GemmTcPlan
+        # operand-ring budget per GEMM CTA (KB; 0 = library default 200 = one CTA per SM).  The backward
+        # GEMMs run two at a time (dgrad chain beside the wgrad stream): a ~100 KB ring lets two CTAs share
+        # an SM.  Measured choice, see DESIGN.md section 8.
+        fwd_kb = int(os.environ.get("DLRM_TC_FWD_SMEM_KB", self.tc_smem_kb[0]))
+        bwd_kb = int(os.environ.get("DLRM_TC_BWD_SMEM_KB", self.tc_smem_kb[1]))
+
+        def GP(_kb, **kw):
+            _lib.set_tunable("gemm_smem_kb", _kb)
+            try:
+                return _lib.GemmTcPlan(**kw)
+            finally:
+                _lib.set_tunable("gemm_smem_kb", 0)
+
         for which in ("bot", "top"):
             ln = self.ln_bot if which == "bot" else self.ln_top
             ntc = self.ntc[which]
@@ -785,12 +799,12 @@ class Engine:
                     kw.update(out_f32=self.Tbuf.data_ptr(), ld_f32=FD)
                 elif which == "top" and (i == ntc - 1):
                     kw.update(out_f32=self.top_act[i].data_ptr(), ld_f32=self.top_act[i].shape[1])
-                self.tc_plans["fwd"][(which, i)] = GP(**kw)
+                self.tc_plans["fwd"][(which, i)] = GP(fwd_kb, **kw)
                 # ---- wgrad: [dW | db] = gz^T [X | 1]   (both operands read MN-major, split-K slabs)
                 oW = self._dense_off[(which, i, "W")]
                 ob = self._dense_off[(which, i, "b")]
                 self.tc_plans["wgrad"][(which, i)] = GP(
-                    A_hi=gh.data_ptr(), A_lo=gl.data_ptr(), lda=Np, a_mn_major=1,
+                    bwd_kb, A_hi=gh.data_ptr(), A_lo=gl.data_ptr(), lda=Np, a_mn_major=1,
                     B_hi=ih.data_ptr(), B_lo=il.data_ptr(), ldb=Kp, b_mn_major=1,
                     M=N, N=K + 1, K=B, mode_x3=x3, split_k=self.tc_splits[(which, i)],
                     out_f32=self.dense_grad.data_ptr() + oW * 4, ld_f32=K, slab_stride=P,
@@ -799,14 +813,14 @@ class Engine:
                 if i > 0:
                     ph, pl, Np_prev = self.tc_gz[which][i - 1]
                     self.tc_plans["dgrad"][(which, i)] = GP(
-                        A_hi=gh.data_ptr(), A_lo=gl.data_ptr(), lda=Np, a_mn_major=0,
+                        bwd_kb, A_hi=gh.data_ptr(), A_lo=gl.data_ptr(), lda=Np, a_mn_major=0,
                         B_hi=wh.data_ptr(), B_lo=wl.data_ptr(), ldb=Kp, b_mn_major=1,
                         M=B, N=K, K=N, mode_x3=x3, split_k=1,
                         mask_act=self._act(which, i - 1), mask_hi=ih.data_ptr(), mask_lo=il.data_ptr(), ldmask=Kp,
                         out_hi=ph.data_ptr(), out_lo=pl.data_ptr(), ld_out=Np_prev)
                 elif which == "top" and self.op == "dot":
                     self.tc_plans["dgrad"][(which, 0)] = GP(
-                        A_hi=gh.data_ptr(), A_lo=gl.data_ptr(), lda=Np, a_mn_major=0,
+                        bwd_kb, A_hi=gh.data_ptr(), A_lo=gl.data_ptr(), lda=Np, a_mn_major=0,
                         B_hi=wh.data_ptr(), B_lo=wl.data_ptr(), ldb=Kp, b_mn_major=1,
                         M=B, N=K, K=N, mode_x3=x3, split_k=1,
                         out_f32=self.dR.data_ptr(), ld_f32=self.ldr)
