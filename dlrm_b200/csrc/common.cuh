@@ -22,6 +22,7 @@ enum Tunable {
   TUNE_GEMM_SMEM_KB = 5,        // operand-ring budget per GEMM CTA at plan creation (0 = 200 KB = 1 CTA/SM)
   TUNE_HEAD_ROWS = 6,           // samples per CTA in the fused head (16 or 32; 0 = default)
   TUNE_INTERACT_BWD_COLS = 7,   // 1 = one column per thread (first kernel), else float2 columns
+  TUNE_PDL = 8,                 // 1 = launch the dense chain with programmatic dependent launch
   TUNE_COUNT = 16
 };
 
@@ -38,6 +39,29 @@ enum Tunable {
     if (e__ != cudaSuccess)                                                             \
       return dlrm::set_error("%s failed: %s", #call, cudaGetErrorString(e__));          \
   } while (0)
+
+// Programmatic dependent launch (griddepcontrol): a kernel launched through launch_chain() may become
+// resident while its predecessor in the stream is still draining; it must not touch global memory
+// before pdl_wait() (which returns once the predecessor grid has completed and its writes are visible).
+// Every kernel launched this way executes BOTH calls, so completion stays transitive along the stream.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
+template <typename... KArgs, typename... Args>
+static inline cudaError_t launch_chain(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem,
+                                       cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = get_tunable(TUNE_PDL) == 1 ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
 
 static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 

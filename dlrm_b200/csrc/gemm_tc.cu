@@ -143,6 +143,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
   // bars[0..stages) full, [stages..2*stages) empty, [2*stages] accumulator ready
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * stages + 1);
 
+  pdl_launch_dependents();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int m0 = blockIdx.y * TC_BM, n0 = blockIdx.x * BN;
   const int kb0 = blockIdx.z * g.kb_per_split;
@@ -169,6 +170,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();   // barriers and TMEM are set up; global memory is first touched below
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
@@ -418,7 +420,7 @@ static int launch_tc(const TcPlan& p, cudaStream_t st) {
     DLRM_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     configured = true;
   }
-  gemm_tc_kernel<BN><<<p.grid, 192, p.smem, st>>>(p.tmAh, p.tmAl, p.tmBh, p.tmBl, p.args, p.stages);
+  (void)launch_chain(gemm_tc_kernel<BN>, p.grid, dim3(192), p.smem, st, p.tmAh, p.tmAl, p.tmBh, p.tmBl, p.args, p.stages);
   DLRM_CHECK_LAUNCH("gemm_tc_kernel");
   return 0;
 }

@@ -33,6 +33,8 @@ constexpr int HEAD_ROWS_MIN = 16;   // scratch is sized for the smaller tile
 
 template <int HEAD_ROWS>
 __global__ void __launch_bounds__(256) head_kernel(const HeadArgs a) {
+  pdl_launch_dependents();
+  pdl_wait();
   __shared__ float s_gz[HEAD_ROWS], s_loss[HEAD_ROWS];
   __shared__ bool s_last;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -175,8 +177,8 @@ extern "C" int dlrm_b200_head_fused(const float* h, int64_t ldh, const float* w,
   // 16 samples per CTA: 128 CTAs at batch 2048 (one wave of the 148 SMs) instead of 64
   const int rows = get_tunable(TUNE_HEAD_ROWS) == 32 ? 32 : 16;
   const long long nb = (batch + rows - 1) / rows;
-  if (rows == 32) head_kernel<32><<<(unsigned)nb, 256, 0, static_cast<cudaStream_t>(stream)>>>(a);
-  else head_kernel<16><<<(unsigned)nb, 256, 0, static_cast<cudaStream_t>(stream)>>>(a);
+  if (rows == 32) (void)launch_chain(head_kernel<32>, dim3((unsigned)nb), dim3(256), 0, static_cast<cudaStream_t>(stream), a);
+  else (void)launch_chain(head_kernel<16>, dim3((unsigned)nb), dim3(256), 0, static_cast<cudaStream_t>(stream), a);
   DLRM_CHECK_LAUNCH("head_kernel");
   return 0;
 }

@@ -91,6 +91,8 @@ __global__ void __launch_bounds__(192) interact_fwd2_kernel(const float* __restr
                                                             __nv_bfloat16* __restrict__ Rl, long long ldrb,
                                                             long long batch, int F, int D, int itself,
                                                             int spb) {
+  pdl_launch_dependents();
+  pdl_wait();
   extern __shared__ __align__(128) float smem[];
   const int nb = (F + 2) / 3;
   const int Fp = nb * 3;
@@ -207,6 +209,8 @@ __global__ void __launch_bounds__(128) interact_bwd_kernel(const float* __restri
                                                            __nv_bfloat16* __restrict__ g0h,
                                                            __nv_bfloat16* __restrict__ g0l, long long ldg0,
                                                            const __grid_constant__ Route route) {
+  pdl_launch_dependents();
+  pdl_wait();
   constexpr bool ROUTE = sizeof(Route) > 8;
   extern __shared__ __align__(128) float smem[];
   const int F4 = (F + 3) & ~3;
@@ -275,6 +279,8 @@ __global__ void __launch_bounds__(128) interact_bwd2_kernel(const float* __restr
                                                             __nv_bfloat16* __restrict__ g0h,
                                                             __nv_bfloat16* __restrict__ g0l, long long ldg0,
                                                             const __grid_constant__ Route route) {
+  pdl_launch_dependents();
+  pdl_wait();
   constexpr bool ROUTE = sizeof(Route) > 8;
   extern __shared__ __align__(128) float smem[];
   const int F4 = (F + 3) & ~3;
@@ -368,9 +374,9 @@ extern "C" int dlrm_b200_interact_fwd_ex(const float* T, int64_t ldt, float* R, 
         configured = true;
       }
       const long long grid = (batch + spb - 1) / spb;
-      interact_fwd2_kernel<<<(unsigned)grid, 192, smem, st>>>(T, ldt, R, ldr, static_cast<__nv_bfloat16*>(R_hi),
-                                                              static_cast<__nv_bfloat16*>(R_lo), ld_rb, batch, F, D,
-                                                              itself, spb);
+      (void)launch_chain(interact_fwd2_kernel, dim3((unsigned)grid), dim3(192), smem, st, T, (long long)ldt, R,
+                         (long long)ldr, static_cast<__nv_bfloat16*>(R_hi), static_cast<__nv_bfloat16*>(R_lo),
+                         (long long)ld_rb, (long long)batch, F, D, itself, spb);
       DLRM_CHECK_LAUNCH("interact_fwd2_kernel");
       return 0;
     }
@@ -432,11 +438,13 @@ static int interact_bwd_launch(const float* T, int64_t ldt, const float* dR, int
   const long long grid = (batch + spb - 1) / spb;
 #define DLRM_IB(KERNEL, MAXF)                                                                                 \
   if (route)                                                                                                  \
-    KERNEL<MAXF, FeatRoute><<<(unsigned)grid, 128, smem, st>>>(T, ldt, dR, lddr, dT, lddt, batch, F, D, itself, \
-                                                               mask_feature0, spb, gh, gl, ld_g0, *route);    \
+    (void)launch_chain(KERNEL<MAXF, FeatRoute>, dim3((unsigned)grid), dim3(128), smem, st, T, (long long)ldt, \
+                       dR, (long long)lddr, dT, (long long)lddt, (long long)batch, F, D, itself,               \
+                       mask_feature0, spb, gh, gl, (long long)ld_g0, *route);                                  \
   else                                                                                                        \
-    KERNEL<MAXF, NoRoute><<<(unsigned)grid, 128, smem, st>>>(T, ldt, dR, lddr, dT, lddt, batch, F, D, itself,  \
-                                                             mask_feature0, spb, gh, gl, ld_g0, NoRoute{})
+    (void)launch_chain(KERNEL<MAXF, NoRoute>, dim3((unsigned)grid), dim3(128), smem, st, T, (long long)ldt,   \
+                       dR, (long long)lddr, dT, (long long)lddt, (long long)batch, F, D, itself,               \
+                       mask_feature0, spb, gh, gl, (long long)ld_g0, NoRoute{})
   if (two) {
     if (F <= 8) { DLRM_IB(interact_bwd2_kernel, 8); }
     else if (F <= 32) { DLRM_IB(interact_bwd2_kernel, 32); }

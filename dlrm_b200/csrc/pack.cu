@@ -13,6 +13,8 @@ __global__ void __launch_bounds__(256) split_bf16_kernel(const float* __restrict
                                                          long long M, long long N,
                                                          __nv_bfloat16* __restrict__ hi,
                                                          __nv_bfloat16* __restrict__ lo, long long ldo) {
+  pdl_launch_dependents();
+  pdl_wait();
   const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= M * N) return;
   const long long m = e / N, n = e - m * N;
@@ -39,6 +41,8 @@ struct DenseLayers {
 };
 
 __global__ void __launch_bounds__(256) dense_update_pack_kernel(const __grid_constant__ DenseLayers P) {
+  pdl_launch_dependents();
+  pdl_wait();
   // flattened grid: CTAs [cta_begin[i], cta_begin[i+1]) belong to layer i, 256 elements each
   int li = 0;
   while (li + 1 < P.num_layers && (int)blockIdx.x >= P.cta_begin[li + 1]) ++li;
@@ -85,8 +89,9 @@ extern "C" int dlrm_b200_split_bf16(const float* X, int64_t ldx, int64_t M, int6
   if (M <= 0 || N <= 0) return 0;
   if (!X || !hi) return set_error("split_bf16: NULL pointer");
   const long long n = M * N;
-  split_bf16_kernel<<<(unsigned)((n + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      X, ldx, M, N, static_cast<__nv_bfloat16*>(hi), static_cast<__nv_bfloat16*>(lo), ld_out);
+  (void)launch_chain(split_bf16_kernel, dim3((unsigned)((n + 255) / 256)), dim3(256), 0,
+                     static_cast<cudaStream_t>(stream), X, (long long)ldx, (long long)M, (long long)N,
+                     static_cast<__nv_bfloat16*>(hi), static_cast<__nv_bfloat16*>(lo), (long long)ld_out);
   DLRM_CHECK_LAUNCH("split_bf16_kernel");
   return 0;
 }
@@ -120,7 +125,7 @@ extern "C" int dlrm_b200_dense_update_pack(const dlrm_dense_layer_t* layers, int
   for (int i = num_layers; i <= 16; ++i) P.cta_begin[i] = (int)ctas;
   P.num_layers = num_layers;
   P.optimizer = optimizer; P.lr = lr; P.eps = eps;
-  dense_update_pack_kernel<<<(unsigned)ctas, 256, 0, static_cast<cudaStream_t>(stream)>>>(P);
+  (void)launch_chain(dense_update_pack_kernel, dim3((unsigned)ctas), dim3(256), 0, static_cast<cudaStream_t>(stream), P);
   DLRM_CHECK_LAUNCH("dense_update_pack_kernel");
   return 0;
 }
