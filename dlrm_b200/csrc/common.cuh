@@ -22,7 +22,7 @@ enum Tunable {
   TUNE_GEMM_SMEM_KB = 5,        // operand-ring budget per GEMM CTA at plan creation (0 = 200 KB = 1 CTA/SM)
   TUNE_HEAD_ROWS = 6,           // samples per CTA in the fused head (16 or 32; 0 = default)
   TUNE_INTERACT_BWD_COLS = 7,   // 1 = one column per thread (first kernel), else float2 columns
-  TUNE_PDL = 8,                 // 1 = launch the dense chain with programmatic dependent launch
+  TUNE_PDL = 8,                 // programmatic dependent launch on the dense chain: 0/1 = on, 2 = off
   TUNE_COUNT = 16
 };
 
@@ -59,7 +59,7 @@ static inline cudaError_t launch_chain(void (*kernel)(KArgs...), dim3 grid, dim3
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = get_tunable(TUNE_PDL) == 1 ? 1 : 0;
+  cfg.numAttrs = get_tunable(TUNE_PDL) == 2 ? 0 : 1;   // on by default (r20: 0.518 -> 0.502 ms/step); 2 = off
   return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
 }
 
