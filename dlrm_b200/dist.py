@@ -75,6 +75,28 @@ def pack_dT_into_send(dT: torch.Tensor, gsend: torch.Tensor, n_tables: int, worl
         o += n
 
 
+def push_route(n_tables: int, world: int, rank: int, local_batch: int, dim: int):
+    """Where rank `rank`'s interact_bwd stores the gradient rows of every table (peer-memory exchange).
+
+    Returns one (owner, offset, ld) per table t, in ELEMENTS: the row of local sample b goes to
+    `recv_of(owner)[offset + b * ld : ... + dim]`.  The receive buffer of a rank with T_r tables is
+    [world][local_batch][T_r][dim]; slab `rank` holds what this rank sends, so the owner's update kernel
+    sees the same [global batch][T_r][dim] view the all-to-all path assembles (a2a_splits)."""
+    out = []
+    for r, (s, e) in enumerate(table_slices(n_tables, world)):
+        for t in range(s, e):
+            out.append((r, (rank * local_batch * (e - s) + (t - s)) * dim, (e - s) * dim))
+    return out
+
+
+def gather_route(n_tables: int, world: int, rank: int, dim: int):
+    """Forward twin of push_route: byte-free description of where the gather of rank `rank` stores the
+    pooled row of (global sample g, local table k): T_of(g // local_batch)[(g % local_batch), 1 + s + k, :]
+    -> returns the element offset of feature (1 + s) inside one sample of T ([F, dim] per sample)."""
+    s, _ = table_slices(n_tables, world)[rank]
+    return (1 + s) * dim
+
+
 def init_distributed(backend: Optional[str] = None):
     """Process-group bring-up from the torchrun environment (extend_distributed.init_distributed)."""
     if dist.is_initialized():
@@ -170,7 +192,7 @@ class DistEngine:
         dist.all_gather_object(allh, mine)
         self._ipc_bases = {}
         pT, pdT, psig, pgrad = [], [], [], []
-        col = (1 + self.t0) * self.D * 4
+        col = gather_route(self.Tg, self.world, self.rank, self.D) * 4
 
         def imp(handle, offset):
             if handle not in self._ipc_bases:       # one open per exported allocation
@@ -195,12 +217,9 @@ class DistEngine:
         self._peer_dT = (C.c_void_p * W)(*[self._grecv_p2p.data_ptr() + s_ * slab for s_ in range(W)])
         # interact_bwd side: feature 1 + t -> slab `rank` of the owner of table t; feature 0 stays local
         dst, ld = [e.dT.data_ptr()], [e.F * self.D]
-        for r in range(W):
-            lo, hi = self.slices[r]
-            tl_r = hi - lo
-            for t in range(lo, hi):
-                dst.append(pdT[r] + (self.rank * self.B * tl_r * self.D + (t - lo) * self.D) * 4)
-                ld.append(tl_r * self.D)
+        for owner, off, ldr in push_route(self.Tg, W, self.rank, self.B, self.D):
+            dst.append(pdT[owner] + off * 4)
+            ld.append(ldr)
         assert len(dst) == e.F
         e.dT_route = ((C.c_void_p * e.F)(*dst), (C.c_int64 * e.F)(*ld))
         self._peer_sig = [(C.c_void_p * W)(*[p + 64 * ch for p in psig]) for ch in range(2)]

@@ -81,3 +81,48 @@ def test_a2a_layout_world2_gloo():
     ok = ctx.Array("i", [0] * world)
     mp.spawn(_worker, args=(world, port, 5, 4, 3, ok), nprocs=world, join=True)
     assert list(ok) == [1] * world
+
+
+def test_push_route_equals_all_to_all_layout():
+    """The peer-memory backward exchange (interact_bwd stores rows at push_route offsets) fills every
+    owner's receive buffer exactly like pack_dT_into_send + all_to_all_single does (emulated on CPU)."""
+
+    from dlrm_b200.dist import gather_route, push_route
+
+    for world, n_tables, B, D in [(2, 5, 3, 4), (3, 7, 2, 2), (8, 26, 2, 4), (8, 11, 1, 2), (4, 2, 2, 2)]:
+        sl = table_slices(n_tables, world)
+        g = torch.Generator().manual_seed(world * 100 + n_tables)
+        dT = [torch.randn(B, n_tables + 1, D, generator=g) for _ in range(world)]
+        # all-to-all path: block d of rank s's send buffer lands as block s of rank d's receive buffer
+        sends = []
+        for s in range(world):
+            buf = torch.zeros(B * n_tables * D)
+            pack_dT_into_send(dT[s], buf, n_tables, world, B, D)
+            sends.append(buf)
+        want = []
+        for d in range(world):
+            t_d = sl[d][1] - sl[d][0]
+            parts = []
+            for s in range(world):
+                o = sum(B * (e - b0) * D for b0, e in sl[:d])
+                parts.append(sends[s][o:o + B * t_d * D])
+            want.append(torch.cat(parts) if t_d else torch.zeros(0))
+        # push path
+        got = [torch.zeros(world * B * (e - s) * D) for s, e in sl]
+        for s in range(world):
+            route = push_route(n_tables, world, s, B, D)
+            assert len(route) == n_tables
+            for t, (owner, off, ld) in enumerate(route):
+                assert sl[owner][0] <= t < sl[owner][1]
+                for b in range(B):
+                    got[owner][off + b * ld: off + b * ld + D] = dT[s][b, 1 + t, :]
+        for d in range(world):
+            assert torch.equal(got[d], want[d]), (world, n_tables, d)
+            # the update kernel's view: sample g = s * B + b of owner d, local table k
+            t_d = sl[d][1] - sl[d][0]
+            if t_d:
+                v = got[d].view(world * B, t_d, D)
+                for s in range(world):
+                    assert torch.equal(v[s * B:(s + 1) * B], dT[s][:, 1 + sl[d][0]:1 + sl[d][1], :])
+        for r in range(world):
+            assert gather_route(n_tables, world, r, D) == (1 + sl[r][0]) * D
