@@ -87,8 +87,10 @@ def build_parser():
 
 
 def reference_order_batch(m_den, ln_emb, n, num_indices_per_lookup, fixed, round_targets):
-    """One batch drawn from numpy's GLOBAL RNG in the reference's order
-    (generate_dist_input_batch, 'uniform' branch, then generate_random_output_batch)."""
+    """One batch drawn sample by sample from numpy's GLOBAL RNG in the reference's order
+    (generate_dist_input_batch, 'uniform' branch, then generate_random_output_batch).  The CLI's loss
+    curves were pinned on these batches; datagen.RandomDataset produces the same ones faster
+    (tests/test_datagen.py::test_cli_batches_are_the_dataset_batches) and is what run() uses."""
     ra = np.random
     X = torch.tensor(ra.rand(n, m_den).astype(np.float32))
     lS_o, lS_i = [], []
@@ -147,10 +149,9 @@ def run(argv=None):
                        (args.mlperf_logging, "--mlperf-logging"), (args.plot_compute_graph, "--plot-compute-graph")):
         if flag:
             sys.exit("ERROR: %s is outside the dlrm_b200 hot path (SURVEY.md section 2)" % name)
-    if args.data_generation != "random":
-        sys.exit("ERROR: --data-generation=" + args.data_generation + " is not supported (synthetic random data only)")
-    if args.rand_data_dist != "uniform":
-        sys.exit("ERROR: --rand-data-dist=" + args.rand_data_dist + " is not supported")
+    if args.data_generation not in ("random", "synthetic"):
+        sys.exit("ERROR: --data-generation=" + args.data_generation + " is not supported (datasets are outside "
+                 "the dlrm_b200 hot path; use random or synthetic)")
     if args.quantize_emb_with_bit in [4, 8] or args.quantize_mlp_with_bit != 32:
         sys.exit("ERROR: 4 and 8-bit quantization on GPU is not supported")
     if not torch.cuda.is_available():
@@ -183,12 +184,14 @@ def run(argv=None):
     nbatches = args.num_batches if args.num_batches > 0 else int(np.ceil(args.data_size / args.mini_batch_size))
     data_size = nbatches * args.mini_batch_size if args.num_batches > 0 else args.data_size
 
+    # RandomDataset(reset_seed_on_access=True): numpy is re-seeded at the first batch of every epoch, and
+    # every batch is drawn in the reference's order (datagen.py; identical batches for identical flags)
+    from . import datagen
+
+    train_data, _, _, _ = datagen.make_random_data_and_loader(args, ln_emb, m_den)
+
     def batch(j):
-        if j == 0:  # RandomDataset(reset_seed_on_access=True): re-seed at the first batch of every epoch
-            np.random.seed(args.numpy_rand_seed)
-        n = min(args.mini_batch_size, data_size - j * args.mini_batch_size)
-        return reference_order_batch(m_den, ln_emb, n, args.num_indices_per_lookup,
-                                     args.num_indices_per_lookup_fixed, args.round_targets)
+        return datagen.collate_wrapper_random_offset([train_data[j]])
 
     loss_ws = np.fromstring(args.loss_weights, dtype=float, sep="-") if args.loss_function == "wbce" else None
     dlrm = DLRM_Net(m_spa, ln_emb, ln_bot, ln_top, arch_interaction_op=args.arch_interaction_op,
