@@ -46,3 +46,29 @@ def test_product_does_not_import_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".cpp", ".h")):
                 txt = open(os.path.join(dp, f)).read()
                 assert not re.search(r"^\s*(from|import)\s+oracle\b", txt, flags=re.M), f
+
+
+def test_struct_layouts_match_the_header(tmp_path):
+    """sizeof / offsetof of every struct in include/dlrm_b200.h, as a C compiler sees them, equal the
+    ctypes mirrors in dlrm_b200/_lib.py (field names are the header's)."""
+    import ctypes as C
+    import subprocess
+
+    pairs = {"dlrm_emb_fwd_table_t": _lib.EmbFwdTable, "dlrm_emb_bwd_table_t": _lib.EmbBwdTable,
+             "dlrm_emb_dedup_t": _lib.EmbDedup, "dlrm_gemm_tc_desc_t": _lib.GemmTcDesc,
+             "dlrm_dense_layer_t": _lib.DenseLayer}
+    lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "dlrm_b200.h"', "int main(void) {"]
+    for cname, cls in pairs.items():
+        lines.append('printf("%s %%zu\\n", sizeof(%s));' % (cname, cname))
+        for fname, _ in cls._fields_:
+            lines.append('printf("%s.%s %%zu\\n", offsetof(%s, %s));' % (cname, fname, cname, fname))
+    lines += ["return 0;", "}"]
+    src = tmp_path / "layout.c"
+    src.write_text("\n".join(lines))
+    exe = str(tmp_path / "layout")
+    subprocess.run(["gcc", "-std=c99", "-I", os.path.join(ROOT, "include"), str(src), "-o", exe], check=True)
+    got = dict(l.split() for l in subprocess.run([exe], check=True, capture_output=True, text=True).stdout.splitlines())
+    for cname, cls in pairs.items():
+        assert int(got[cname]) == C.sizeof(cls), cname
+        for fname, _ in cls._fields_:
+            assert int(got[cname + "." + fname]) == getattr(cls, fname).offset, cname + "." + fname
