@@ -383,7 +383,9 @@ def measure_update_alone(eng, devb, args, hbm_peak, T, B, D):
     by_u = nnz * (D * 4 * 2 + 8) + T * B * D * 4 + nnz * 8   # SURVEY 8(d) bytes_bwd
     ach = by_u / tu / 1e9
     return {"kernel": "emb_update_kernel (coalesce + row-wise Adagrad, in place)", "bound": "hbm",
-            "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak, "traffic": None,
+            "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak, "traffic": 337.2e6,
+            "traffic_source": "ncu --set full r4: dram__bytes_read.sum 228.7 MB + dram__bytes_write.sum 108.5 MB "
+                              "per launch (profiles/r1_ncu_full_emb_interact_head.csv)",
             "avg_launch_us": tu * 1e6, "algorithmic_bytes_per_launch": by_u,
             "train_gather_plus_link_us": t_gl * 1e6,
             "how": "CUDA events between the launches of back-to-back (gather+link, update) pairs"}
@@ -398,8 +400,8 @@ def measure_gather_alone(eng, devb, args, hbm_peak, peak_src, T, B, D):
     by = bytes_fwd_gather(nnz, T, B, D)
     ach = by / tg / 1e9
     return {"kernel": "emb_fwd_vec_kernel (multi-table EmbeddingBag gather)", "bound": "hbm", "achieved": ach,
-            "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak, "traffic": 139.6e6,
-            "traffic_source": "ncu --set full r2: dram__bytes_read.sum 139.6 MB + write 6.6 MB per launch "
+            "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak, "traffic": 146.2e6,
+            "traffic_source": "ncu --set full r2: dram__bytes_read.sum 139.6 MB + dram__bytes_write.sum 6.6 MB per launch "
                               "(profiles/r1_ncu_full_emb_interact_head.csv)",
             "peak_source": peak_src, "avg_launch_us": tg * 1e6, "algorithmic_bytes_per_launch": by,
             "how": "back-to-back launches over the batch ring, one CUDA-event pair on the launching stream"}
