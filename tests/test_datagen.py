@@ -108,27 +108,32 @@ def test_trace_profile_and_dist_file_roundtrip(tmp_path):
     assert [int(x) for x in G.read_trace_from_file(q)] == [3, 1, 2]
 
 
-def test_cli_batches_are_the_dataset_batches():
-    """The batches the CLI trained on when its loss curves were pinned (cli.reference_order_batch, drawn
-    sample by sample) are exactly what RandomDataset yields for the same flags."""
-    from dlrm_b200.cli import reference_order_batch
+@pytest.mark.parametrize("tag", ["A", "B"])
+def test_cli_batches_are_the_dataset_batches(tag):
+    """With the flags of the pinned CLI loss curves (tests/golden/cli_cfg0_*.flags, test_gpu_facade.py), the
+    loader the CLI builds yields exactly the batches of the sample-by-sample restatement
+    (cli.reference_order_batch) those curves were recorded with."""
+    from dlrm_b200.cli import build_parser, reference_order_batch
 
-    ln_emb = np.asarray([1000, 1000, 1000])
-    ds = G.RandomDataset(13, ln_emb, 2 * 128, 2, 128, 10, False, 1, True, reset_seed_on_access=True, rand_seed=123)
-    for j in range(2):
-        X, lS_o, lS_i, T = G.collate_wrapper_random_offset([ds[j]])
-        mine = (X, lS_o, lS_i, T)
-        if j == 0:
-            np.random.seed(123)
-            st = None
-        else:
-            np.random.set_state(st_after)
-        ref = reference_order_batch(13, ln_emb, 128, 10, False, True)
-        st_after = np.random.get_state()
-        assert torch.equal(mine[0], ref[0]) and torch.equal(mine[1], ref[1]) and torch.equal(mine[3], ref[3])
-        assert all(torch.equal(a, b) for a, b in zip(mine[2], ref[2]))
-        # continue the dataset's stream from the same point for the next batch
-        np.random.set_state(st_after)
+    flags = open(os.path.join(GOLD, "cli_cfg0_%s.flags" % tag)).read().split()
+    args = build_parser().parse_args(
+        ["--arch-sparse-feature-size=16", "--arch-embedding-size=1000-1000-1000",
+         "--arch-mlp-bot=13-512-256-64-16", "--arch-mlp-top=512-256-1", "--mini-batch-size=128",
+         "--data-generation=random", "--num-batches=6", "--print-freq=1", "--learning-rate=0.1",
+         "--numpy-rand-seed=727", "--use-gpu"] + flags)
+    ln_emb = np.fromstring(args.arch_embedding_size, dtype=int, sep="-")
+    train_data, train_loader, _, _ = G.make_random_data_and_loader(args, ln_emb, 13)
+    assert len(train_data) == 6
+    np.random.seed(1)                               # model initialisation would have moved the stream
+    got = [G.collate_wrapper_random_offset([train_data[j]]) for j in range(6)]
+    np.random.seed(args.numpy_rand_seed)            # what the CLI did at batch 0 of the epoch
+    want = [reference_order_batch(13, ln_emb, 128, args.num_indices_per_lookup,
+                                  args.num_indices_per_lookup_fixed, args.round_targets) for _ in range(6)]
+    for a, b in zip(got, want):
+        assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1]) and torch.equal(a[3], b[3])
+        assert len(a[2]) == len(b[2]) and all(torch.equal(x, y) for x, y in zip(a[2], b[2]))
+    first = next(iter(train_loader))                # the DataLoader path re-seeds at batch 0 as well
+    assert torch.equal(first[0], want[0][0]) and torch.equal(first[3], want[0][3])
 
 
 @pytest.mark.skipif(not os.path.isdir(REF), reason="live reference not present (GPU box)")
