@@ -80,7 +80,10 @@ def build_parser():
         else:
             p.add_argument(name, type=typ, default=default)
     p.add_argument("--arch-interaction-op", type=str, choices=["dot", "cat"], default="dot")
-    p.add_argument("--data-generation", type=str, choices=["random", "dataset", "internal"], default="random")
+    # the reference's choices (:941-945) plus "synthetic": its RandomDataset implements the trace-driven
+    # generator but its parser cannot select it
+    p.add_argument("--data-generation", type=str, choices=["random", "dataset", "internal", "synthetic"],
+                   default="random")
     # dlrm_b200 addition (not in the reference): GEMM back end
     p.add_argument("--gemm", type=str, default="tc", choices=["tc", "tc_bf16", "simt"])
     return p
