@@ -185,7 +185,6 @@ def run(argv=None):
         sys.exit("ERROR: arch-sparse-feature-size " + str(m_spa) + " does not match last dim of bottom mlp "
                  + str(m_den_out))
     nbatches = args.num_batches if args.num_batches > 0 else int(np.ceil(args.data_size / args.mini_batch_size))
-    data_size = nbatches * args.mini_batch_size if args.num_batches > 0 else args.data_size
 
     # RandomDataset(reset_seed_on_access=True): numpy is re-seeded at the first batch of every epoch, and
     # every batch is drawn in the reference's order (datagen.py; identical batches for identical flags)

@@ -28,7 +28,7 @@ from __future__ import annotations
 import bisect
 import sys
 from collections import deque
-from typing import List, Sequence, Tuple
+from typing import List, Tuple
 
 import numpy as np
 import torch

@@ -290,7 +290,6 @@ class DistEngine:
 
         e = self.eng
         self._barrier()       # every rank's interact_bwd stores have landed in my receive buffer
-        FD = e.F * self.D
         bdesc, _ = e._bwd_desc_chunk(sp, list(range(self.Tl)))
         _lib.check(e.lib.dlrm_b200_emb_bwd_update_p2p(bdesc, self.Tl, self.D, sp.batch, sp.idx_bytes,
                                                       int(sp.include_last), e.link.data_ptr(), self._peer_dT,
