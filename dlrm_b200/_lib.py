@@ -66,7 +66,7 @@ SYMBOLS = [
     "dlrm_b200_linear_fwd", "dlrm_b200_linear_dgrad", "dlrm_b200_linear_wgrad",
     "dlrm_b200_interact_fwd", "dlrm_b200_interact_bwd", "dlrm_b200_loss_fwd_bwd",
     "dlrm_b200_dense_update",
-    "dlrm_b200_gemm_tc_plan_create", "dlrm_b200_gemm_tc_plan_info", "dlrm_b200_gemm_tc_run",
+    "dlrm_b200_gemm_tc_plan_create", "dlrm_b200_gemm_tc_plan_info", "dlrm_b200_gemm_tc_run", "dlrm_b200_gemm_tc_run_group",
     "dlrm_b200_gemm_tc_plan_destroy", "dlrm_b200_split_bf16", "dlrm_b200_dense_update_pack",
 ]
 
@@ -112,6 +112,7 @@ def _declare(lib):
     lib.dlrm_b200_gemm_tc_plan_create.argtypes = [C.POINTER(GemmTcDesc), C.POINTER(vp)]
     lib.dlrm_b200_gemm_tc_plan_info.argtypes = [vp, C.POINTER(i32), C.POINTER(i32), C.POINTER(i32), C.POINTER(i32)]
     lib.dlrm_b200_gemm_tc_run.argtypes = [vp, vp]
+    lib.dlrm_b200_gemm_tc_run_group.argtypes = [C.POINTER(vp), i32, vp]
     lib.dlrm_b200_gemm_tc_plan_destroy.argtypes = [vp]
     lib.dlrm_b200_split_bf16.argtypes = [vp, i64, i64, i64, vp, vp, i64, vp]
     lib.dlrm_b200_dense_update_pack.argtypes = [C.POINTER(DenseLayer), i32, i32, f32, f32, vp]
@@ -183,6 +184,12 @@ class GemmTcPlan:
 
     def run(self, stream):
         check(lib().dlrm_b200_gemm_tc_run(self.handle, stream), "gemm_tc_run")
+
+    @staticmethod
+    def run_group(plans, stream):
+        """Launch up to 4 plans of one tile width as ONE kernel (bit-identical to running them in turn)."""
+        arr = (C.c_void_p * len(plans))(*[p.handle.value for p in plans])
+        check(lib().dlrm_b200_gemm_tc_run_group(arr, len(plans), stream), "gemm_tc_run_group")
 
     def __del__(self):
         try:

@@ -22,6 +22,7 @@
 // contiguous, e.g. dY^T read straight from dY): the UMMA descriptors and instruction descriptor
 // carry the majorness, so no transposed copy is needed for MN-major inputs.
 #include <cuda.h>
+#include <string.h>
 #include <cuda_bf16.h>
 
 #include "common.cuh"
@@ -141,6 +142,53 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
 #define TCB_MAP_AL (&tmAl)
 #define TCB_MAP_BH (&tmBh)
 #define TCB_MAP_BL (&tmBl)
+#include "gemm_tc_body.cuh"
+#undef TCB_BX
+#undef TCB_BY
+#undef TCB_BZ
+#undef TCB_MAP_AH
+#undef TCB_MAP_AL
+#undef TCB_MAP_BH
+#undef TCB_MAP_BL
+}
+
+// Several independent problems in ONE launch (same tile width): CTAs [cta_begin, next cta_begin) of the
+// linear grid belong to entry p and are numbered n tile fastest, then m tile, then k split -- the same
+// CTA program as above, so results are bit-identical to separate launches.  Meant for the weight-gradient
+// GEMMs of an MLP, which are mutually independent and individually too small to fill the GPU.
+constexpr int TC_MAX_GROUP = 4;
+
+struct TcGroupEntry {
+  CUtensorMap m[4];   // A_hi, A_lo, B_hi, B_lo
+  TcArgs a;
+  int stages;
+  int gx, gy, gz;
+  int cta_begin;
+};
+
+struct TcGroup {
+  TcGroupEntry e[TC_MAX_GROUP];
+  int n;
+};
+
+template <int BN>
+__global__ void __launch_bounds__(192, 1) gemm_tc_group_kernel(const __grid_constant__ TcGroup P) {
+  int p = 0;
+  while (p + 1 < P.n && (int)blockIdx.x >= P.e[p + 1].cta_begin) ++p;
+  const TcGroupEntry& E = P.e[p];
+  const TcArgs& g = E.a;
+  const int stages = E.stages;
+  const int local = (int)blockIdx.x - E.cta_begin;
+  const int tcb_bx = local % E.gx;
+  const int tcb_by = (local / E.gx) % E.gy;
+  const int tcb_bz = local / (E.gx * E.gy);
+#define TCB_BX tcb_bx
+#define TCB_BY tcb_by
+#define TCB_BZ tcb_bz
+#define TCB_MAP_AH (&E.m[0])
+#define TCB_MAP_AL (&E.m[1])
+#define TCB_MAP_BH (&E.m[2])
+#define TCB_MAP_BL (&E.m[3])
 #include "gemm_tc_body.cuh"
 #undef TCB_BX
 #undef TCB_BY
@@ -307,6 +355,51 @@ extern "C" int dlrm_b200_gemm_tc_run(void* plan, void* stream) {
   if (p->bn == 128) return launch_tc<128>(*p, st);
   if (p->bn == 64) return launch_tc<64>(*p, st);
   return launch_tc<32>(*p, st);
+}
+
+namespace dlrm {
+template <int BN>
+static int launch_tc_group(const TcGroup& G, unsigned total, size_t smem, cudaStream_t st) {
+  static bool configured = false;
+  if (!configured) {
+    DLRM_CUDA(cudaFuncSetAttribute(gemm_tc_group_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    configured = true;
+  }
+  (void)launch_chain(gemm_tc_group_kernel<BN>, dim3(total), dim3(192), smem, st, G);
+  DLRM_CHECK_LAUNCH("gemm_tc_group_kernel");
+  return 0;
+}
+}  // namespace dlrm
+
+extern "C" int dlrm_b200_gemm_tc_run_group(void* const* plans, int num_plans, void* stream) {
+  using namespace dlrm;
+  if (!plans || num_plans < 1 || num_plans > TC_MAX_GROUP)
+    return set_error("gemm_tc_run_group: num_plans=%d (1..%d)", num_plans, TC_MAX_GROUP);
+  TcGroup G;
+  memset(&G, 0, sizeof(G));
+  G.n = num_plans;
+  long long total = 0;
+  size_t smem = 0;
+  int bn = 0;
+  for (int i = 0; i < num_plans; ++i) {
+    const TcPlan* p = static_cast<const TcPlan*>(plans[i]);
+    if (!p) return set_error("gemm_tc_run_group: plan %d is NULL", i);
+    if (i == 0) bn = p->bn;
+    if (p->bn != bn) return set_error("gemm_tc_run_group: plans must share the tile width (%d vs %d)", p->bn, bn);
+    TcGroupEntry& e = G.e[i];
+    e.m[0] = p->tmAh; e.m[1] = p->tmAl; e.m[2] = p->tmBh; e.m[3] = p->tmBl;
+    e.a = p->args;
+    e.stages = p->stages;
+    e.gx = (int)p->grid.x; e.gy = (int)p->grid.y; e.gz = (int)p->grid.z;
+    e.cta_begin = (int)total;
+    total += (long long)p->grid.x * p->grid.y * p->grid.z;
+    smem = p->smem > smem ? p->smem : smem;
+  }
+  if (total <= 0 || total >= (1ll << 31)) return set_error("gemm_tc_run_group: %lld CTAs", total);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (bn == 32) return launch_tc_group<32>(G, (unsigned)total, smem, st);
+  if (bn == 64) return launch_tc_group<64>(G, (unsigned)total, smem, st);
+  return launch_tc_group<128>(G, (unsigned)total, smem, st);
 }
 
 extern "C" int dlrm_b200_gemm_tc_plan_destroy(void* plan) {

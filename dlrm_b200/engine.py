@@ -160,6 +160,7 @@ class Engine:
         # side streams: the gather runs beside the bottom MLP, the weight-gradient GEMMs and the
         # embedding update beside the dgrad chain (independent work; parallel branches in the graph)
         self.multi_stream = True
+        self.group_wgrad = os.environ.get("DLRM_GROUP_WGRAD") == "1"   # experimental, see _wgrad_group
         self.tc_smem_kb = (0, 0)    # (forward, backward) operand-ring budget of the tcgen05 GEMM plans, KB; 0 = 200
         self.s_emb = torch.cuda.Stream(device=self.device)
         self.s_wg = torch.cuda.Stream(device=self.device)
@@ -942,18 +943,39 @@ class Engine:
     def _tc_mlp_backward(self, which: str, B: int):
         """gz of the last tensor-core layer is ready on the current stream.  dgrads stay on it (the
         critical chain); every wgrad only feeds the final dense update and goes to the side stream."""
+        grouped = self._wgrad_group(which)
         for i in reversed(range(self.ntc[which])):
-            if self.multi_stream:
-                self._fork(self.s_wg)   # gz_i was produced by the previous launch on this stream
-                with torch.cuda.stream(self.s_wg):
+            if grouped is None:
+                if self.multi_stream:
+                    self._fork(self.s_wg)   # gz_i was produced by the previous launch on this stream
+                    with torch.cuda.stream(self.s_wg):
+                        self.tc_plans["wgrad"][(which, i)].run(_stream())
+                else:
                     self.tc_plans["wgrad"][(which, i)].run(_stream())
-            else:
-                self.tc_plans["wgrad"][(which, i)].run(_stream())
-            self.n_launch += 1
+                self.n_launch += 1
             pl = self.tc_plans["dgrad"].get((which, i))
             if pl is not None:
                 pl.run(_stream())
                 self.n_launch += 1
+        if grouped is not None:
+            # every gz of this MLP is final: all its weight gradients in one launch on the side stream
+            if self.multi_stream:
+                self._fork(self.s_wg)
+                with torch.cuda.stream(self.s_wg):
+                    _lib.GemmTcPlan.run_group(grouped, _stream())
+            else:
+                _lib.GemmTcPlan.run_group(grouped, _stream())
+            self.n_launch += 1
+
+    def _wgrad_group(self, which: str):
+        """The wgrad plans of one MLP if `group_wgrad` is on and they can share a launch (same tile width,
+        at most 4), else None.  EXPERIMENTAL (off by default): not yet measured on hardware."""
+        if not self.group_wgrad:
+            return None
+        plans = [self.tc_plans["wgrad"][(which, i)] for i in range(self.ntc[which])]
+        if not 1 <= len(plans) <= 4 or len({p.info()["tile_n"] for p in plans}) != 1:
+            return None
+        return plans
 
     def _tc_backward(self, X: torch.Tensor, sp: SparseInput, target: torch.Tensor, update=None):
         B = X.shape[0]

@@ -312,6 +312,10 @@ typedef struct {
 int dlrm_b200_gemm_tc_plan_create(const dlrm_gemm_tc_desc_t* desc /*[host]*/, void** plan);
 int dlrm_b200_gemm_tc_plan_info(void* plan, int* tile_n, int* stages, int* splits, int* ctas);
 int dlrm_b200_gemm_tc_run(void* plan, void* stream);
+/* Up to 4 independent plans of the same tile width in ONE launch (the weight-gradient GEMMs of an MLP:
+ * nn.Linear backward w.r.t. weight and bias for every layer, dlrm_s_pytorch.py:1613); results are
+ * bit-identical to running the plans one by one. */
+int dlrm_b200_gemm_tc_run_group(void* const* plans /*[host][num_plans]*/, int num_plans, void* stream);
 int dlrm_b200_gemm_tc_plan_destroy(void* plan);
 
 /* fp32 [M,N] (row stride ldx) -> (hi, lo) bf16 [M, ld_out]; lo may be NULL */
