@@ -66,8 +66,9 @@ SYMBOLS = [
     "dlrm_b200_linear_fwd", "dlrm_b200_linear_dgrad", "dlrm_b200_linear_wgrad",
     "dlrm_b200_interact_fwd", "dlrm_b200_interact_bwd", "dlrm_b200_loss_fwd_bwd",
     "dlrm_b200_dense_update",
-    "dlrm_b200_gemm_tc_plan_create", "dlrm_b200_gemm_tc_plan_info", "dlrm_b200_gemm_tc_run", "dlrm_b200_gemm_tc_run_group",
-    "dlrm_b200_gemm_tc_plan_destroy", "dlrm_b200_split_bf16", "dlrm_b200_dense_update_pack",
+    "dlrm_b200_gemm_tc_plan_create", "dlrm_b200_gemm_tc_plan_info", "dlrm_b200_gemm_tc_run",
+    "dlrm_b200_gemm_tc_plan_destroy", "dlrm_b200_gemm_chain_create", "dlrm_b200_gemm_chain_info",
+    "dlrm_b200_gemm_chain_run", "dlrm_b200_gemm_chain_destroy", "dlrm_b200_split_bf16", "dlrm_b200_dense_update_pack",
 ]
 
 
@@ -112,7 +113,10 @@ def _declare(lib):
     lib.dlrm_b200_gemm_tc_plan_create.argtypes = [C.POINTER(GemmTcDesc), C.POINTER(vp)]
     lib.dlrm_b200_gemm_tc_plan_info.argtypes = [vp, C.POINTER(i32), C.POINTER(i32), C.POINTER(i32), C.POINTER(i32)]
     lib.dlrm_b200_gemm_tc_run.argtypes = [vp, vp]
-    lib.dlrm_b200_gemm_tc_run_group.argtypes = [C.POINTER(vp), i32, vp]
+    lib.dlrm_b200_gemm_chain_create.argtypes = [C.POINTER(vp), C.POINTER(i32), C.POINTER(i32), i32, vp, i64, C.POINTER(vp)]
+    lib.dlrm_b200_gemm_chain_info.argtypes = [vp, C.POINTER(i32), C.POINTER(i32), C.POINTER(i32), C.POINTER(i32)]
+    lib.dlrm_b200_gemm_chain_run.argtypes = [vp, vp]
+    lib.dlrm_b200_gemm_chain_destroy.argtypes = [vp]
     lib.dlrm_b200_gemm_tc_plan_destroy.argtypes = [vp]
     lib.dlrm_b200_split_bf16.argtypes = [vp, i64, i64, i64, vp, vp, i64, vp]
     lib.dlrm_b200_dense_update_pack.argtypes = [C.POINTER(DenseLayer), i32, i32, f32, f32, vp]
@@ -185,16 +189,46 @@ class GemmTcPlan:
     def run(self, stream):
         check(lib().dlrm_b200_gemm_tc_run(self.handle, stream), "gemm_tc_run")
 
-    @staticmethod
-    def run_group(plans, stream):
-        """Launch up to 4 plans of one tile width as ONE kernel (bit-identical to running them in turn)."""
-        arr = (C.c_void_p * len(plans))(*[p.handle.value for p in plans])
-        check(lib().dlrm_b200_gemm_tc_run_group(arr, len(plans), stream), "gemm_tc_run_group")
-
     def __del__(self):
         try:
             if self.handle:
                 lib().dlrm_b200_gemm_tc_plan_destroy(self.handle)
+                self.handle = None
+        except Exception:
+            pass
+
+
+class GemmChain:
+    """A whole MLP chain (list of GemmTcPlan + producer/consumer dependencies) as ONE persistent launch
+    (csrc/gemm_chain.cu).  `counters` is a zeroed int32 device tensor owned by the caller."""
+
+    def __init__(self, plans, dep, dep_on_k, counters):
+        self.plans = list(plans)            # keep the plans (TMA descriptors are copied, buffers are not) alive
+        self.counters = counters
+        n = len(self.plans)
+        arr = (C.c_void_p * n)(*[p.handle.value for p in self.plans])
+        d = (C.c_int * n)(*[int(v) for v in dep])
+        k = (C.c_int * n)(*[int(v) for v in dep_on_k])
+        self.handle = C.c_void_p()
+        check(lib().dlrm_b200_gemm_chain_create(arr, d, k, n, counters.data_ptr(), counters.numel(),
+                                                C.byref(self.handle)), "gemm_chain_create")
+
+    @staticmethod
+    def counters_needed(plans):
+        return 2 + sum((int(p.desc.M) + 127) // 128 for p in plans)
+
+    def info(self):
+        a, b, c, e = C.c_int(), C.c_int(), C.c_int(), C.c_int()
+        check(lib().dlrm_b200_gemm_chain_info(self.handle, C.byref(a), C.byref(b), C.byref(c), C.byref(e)))
+        return dict(tasks=a.value, ctas=b.value, stages=c.value, smem=e.value)
+
+    def run(self, stream):
+        check(lib().dlrm_b200_gemm_chain_run(self.handle, stream), "gemm_chain_run")
+
+    def __del__(self):
+        try:
+            if self.handle:
+                lib().dlrm_b200_gemm_chain_destroy(self.handle)
                 self.handle = None
         except Exception:
             pass

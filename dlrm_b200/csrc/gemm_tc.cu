@@ -21,112 +21,11 @@
 // Operands may be K-major ([rows, K] with K contiguous) or MN-major ([K, rows] with rows
 // contiguous, e.g. dY^T read straight from dY): the UMMA descriptors and instruction descriptor
 // carry the majorness, so no transposed copy is needed for MN-major inputs.
-#include <cuda.h>
 #include <string.h>
-#include <cuda_bf16.h>
 
-#include "common.cuh"
+#include "gemm_tc_common.cuh"
 
 namespace dlrm {
-
-constexpr int TC_BM = 128;
-constexpr int TC_BK = 64;  // 64 bf16 = 128 bytes = one swizzle row
-
-struct TcArgs {
-  long long M, N, K;
-  int x3;
-  int a_mn, b_mn;  // operand majorness (0 = K-major, 1 = MN-major)
-  int kb_per_split, num_kb;
-  int act;
-  int mask_act;
-  const __nv_bfloat16* mask_hi;
-  const __nv_bfloat16* mask_lo;
-  long long ldmask;
-  float* out_f32;
-  long long ld_f32, slab_stride;
-  __nv_bfloat16* out_hi;
-  __nv_bfloat16* out_lo;
-  long long ld_out;
-  __nv_bfloat16* outT_hi;
-  __nv_bfloat16* outT_lo;
-  long long ld_outT;
-  float* out_col;
-  long long col_index, col_slab_stride;
-};
-
-// ------------------------------------------------------------------------------------------ PTX
-__device__ __forceinline__ uint32_t smem_u32(const void* p) {
-  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
-}
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-  // try_wait suspends for a bounded time per call; a protocol bug must trap, not hang the GPU
-  uint32_t ok = 0;
-  int tries = 0;
-  while (true) {
-    asm volatile(
-        "{\n\t.reg .pred P1;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, P1;\n\t}"
-        : "=r"(ok)
-        : "r"(bar), "r"(parity)
-        : "memory");
-    if (ok) break;
-    if (++tries > (1 << 24)) __trap();
-  }
-}
-__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int x, int y) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
-      "l"(map), "r"(bar), "r"(x), "r"(y)
-      : "memory");
-}
-__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
-                                          uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
-      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
-__device__ __forceinline__ void umma_commit(uint32_t bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
-        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
-        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-      : "r"(taddr)
-      : "memory");
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-}
-
-// UMMA shared-memory descriptor (cute::UMMA::SmemDescriptor): start>>4 [0,14), LBO>>4 [16,30),
-// SBO>>4 [32,46), version=1 [46,48), layout SWIZZLE_128B=2 [61,64).
-__device__ __forceinline__ uint64_t make_smem_desc(uint32_t addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
-  uint64_t d = 0;
-  d |= (uint64_t)((addr >> 4) & 0x3FFF);
-  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
-  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
-  d |= (uint64_t)1 << 46;
-  d |= (uint64_t)2 << 61;
-  return d;
-}
-
-__device__ __forceinline__ float apply_act_tc(float v, int act) {
-  if (act == DLRM_ACT_RELU) return fmaxf(v, 0.f);
-  if (act == DLRM_ACT_SIGMOID) return 1.0f / (1.0f + expf(-v));
-  return v;
-}
 
 // ------------------------------------------------------------------------------------------ kernel
 // smem per stage: A_hi [A_lo] B_hi [B_lo]; every tile 1024-byte aligned.
@@ -142,53 +41,6 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
 #define TCB_MAP_AL (&tmAl)
 #define TCB_MAP_BH (&tmBh)
 #define TCB_MAP_BL (&tmBl)
-#include "gemm_tc_body.cuh"
-#undef TCB_BX
-#undef TCB_BY
-#undef TCB_BZ
-#undef TCB_MAP_AH
-#undef TCB_MAP_AL
-#undef TCB_MAP_BH
-#undef TCB_MAP_BL
-}
-
-// Several independent problems in ONE launch (same tile width): CTAs [cta_begin, next cta_begin) of the
-// linear grid belong to entry p and are numbered n tile fastest, then m tile, then k split -- the same
-// CTA program as above, so results are bit-identical to separate launches.  Meant for the weight-gradient
-// GEMMs of an MLP, which are mutually independent and individually too small to fill the GPU.
-constexpr int TC_MAX_GROUP = 4;
-
-struct TcGroupEntry {
-  CUtensorMap m[4];   // A_hi, A_lo, B_hi, B_lo
-  TcArgs a;
-  int stages;
-  int gx, gy, gz;
-  int cta_begin;
-};
-
-struct TcGroup {
-  TcGroupEntry e[TC_MAX_GROUP];
-  int n;
-};
-
-template <int BN>
-__global__ void __launch_bounds__(192, 1) gemm_tc_group_kernel(const __grid_constant__ TcGroup P) {
-  int p = 0;
-  while (p + 1 < P.n && (int)blockIdx.x >= P.e[p + 1].cta_begin) ++p;
-  const TcGroupEntry& E = P.e[p];
-  const TcArgs& g = E.a;
-  const int stages = E.stages;
-  const int local = (int)blockIdx.x - E.cta_begin;
-  const int tcb_bx = local % E.gx;
-  const int tcb_by = (local / E.gx) % E.gy;
-  const int tcb_bz = local / (E.gx * E.gy);
-#define TCB_BX tcb_bx
-#define TCB_BY tcb_by
-#define TCB_BZ tcb_bz
-#define TCB_MAP_AH (&E.m[0])
-#define TCB_MAP_AL (&E.m[1])
-#define TCB_MAP_BH (&E.m[2])
-#define TCB_MAP_BL (&E.m[3])
 #include "gemm_tc_body.cuh"
 #undef TCB_BX
 #undef TCB_BY
@@ -234,13 +86,6 @@ static int make_map(CUtensorMap* map, const void* ptr, long long inner, long lon
   return 0;
 }
 
-struct TcPlan {
-  CUtensorMap tmAh, tmAl, tmBh, tmBl;
-  TcArgs args;
-  int bn, stages, splits;
-  size_t smem;
-  dim3 grid;
-};
 
 template <int BN>
 static int launch_tc(const TcPlan& p, cudaStream_t st) {
@@ -355,51 +200,6 @@ extern "C" int dlrm_b200_gemm_tc_run(void* plan, void* stream) {
   if (p->bn == 128) return launch_tc<128>(*p, st);
   if (p->bn == 64) return launch_tc<64>(*p, st);
   return launch_tc<32>(*p, st);
-}
-
-namespace dlrm {
-template <int BN>
-static int launch_tc_group(const TcGroup& G, unsigned total, size_t smem, cudaStream_t st) {
-  static bool configured = false;
-  if (!configured) {
-    DLRM_CUDA(cudaFuncSetAttribute(gemm_tc_group_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    configured = true;
-  }
-  (void)launch_chain(gemm_tc_group_kernel<BN>, dim3(total), dim3(192), smem, st, G);
-  DLRM_CHECK_LAUNCH("gemm_tc_group_kernel");
-  return 0;
-}
-}  // namespace dlrm
-
-extern "C" int dlrm_b200_gemm_tc_run_group(void* const* plans, int num_plans, void* stream) {
-  using namespace dlrm;
-  if (!plans || num_plans < 1 || num_plans > TC_MAX_GROUP)
-    return set_error("gemm_tc_run_group: num_plans=%d (1..%d)", num_plans, TC_MAX_GROUP);
-  TcGroup G;
-  memset(&G, 0, sizeof(G));
-  G.n = num_plans;
-  long long total = 0;
-  size_t smem = 0;
-  int bn = 0;
-  for (int i = 0; i < num_plans; ++i) {
-    const TcPlan* p = static_cast<const TcPlan*>(plans[i]);
-    if (!p) return set_error("gemm_tc_run_group: plan %d is NULL", i);
-    if (i == 0) bn = p->bn;
-    if (p->bn != bn) return set_error("gemm_tc_run_group: plans must share the tile width (%d vs %d)", p->bn, bn);
-    TcGroupEntry& e = G.e[i];
-    e.m[0] = p->tmAh; e.m[1] = p->tmAl; e.m[2] = p->tmBh; e.m[3] = p->tmBl;
-    e.a = p->args;
-    e.stages = p->stages;
-    e.gx = (int)p->grid.x; e.gy = (int)p->grid.y; e.gz = (int)p->grid.z;
-    e.cta_begin = (int)total;
-    total += (long long)p->grid.x * p->grid.y * p->grid.z;
-    smem = p->smem > smem ? p->smem : smem;
-  }
-  if (total <= 0 || total >= (1ll << 31)) return set_error("gemm_tc_run_group: %lld CTAs", total);
-  cudaStream_t st = static_cast<cudaStream_t>(stream);
-  if (bn == 32) return launch_tc_group<32>(G, (unsigned)total, smem, st);
-  if (bn == 64) return launch_tc_group<64>(G, (unsigned)total, smem, st);
-  return launch_tc_group<128>(G, (unsigned)total, smem, st);
 }
 
 extern "C" int dlrm_b200_gemm_tc_plan_destroy(void* plan) {

@@ -160,7 +160,10 @@ class Engine:
         # side streams: the gather runs beside the bottom MLP, the weight-gradient GEMMs and the
         # embedding update beside the dgrad chain (independent work; parallel branches in the graph)
         self.multi_stream = True
-        self.group_wgrad = os.environ.get("DLRM_GROUP_WGRAD") == "1"   # experimental, see _wgrad_group
+        # every MLP chain (forward layers; dgrad chain + weight gradients) as ONE persistent tile-dataflow
+        # launch (csrc/gemm_chain.cu) instead of one launch per layer; DLRM_CHAIN=0 restores per-layer launches
+        self.use_chain = os.environ.get("DLRM_CHAIN", "1") != "0"
+        self.tc_tile_n = {}          # optional (kind, which, i) -> tile_n override for the tcgen05 plans
         self.tc_smem_kb = (0, 0)    # (forward, backward) operand-ring budget of the tcgen05 GEMM plans, KB; 0 = 200
         self.s_emb = torch.cuda.Stream(device=self.device)
         self.s_wg = torch.cuda.Stream(device=self.device)
@@ -774,6 +777,8 @@ class Engine:
         bwd_kb = int(os.environ.get("DLRM_TC_BWD_SMEM_KB", self.tc_smem_kb[1]))
 
         def GP(_kb, **kw):
+            if "tile_n" not in kw:
+                kw["tile_n"] = int(os.environ.get("DLRM_CHAIN_TILE_N", "0"))   # experiment knob; 0 = auto
             _lib.set_tunable("gemm_smem_kb", _kb)
             try:
                 return _lib.GemmTcPlan(**kw)
@@ -825,6 +830,8 @@ class Engine:
                         B_hi=wh.data_ptr(), B_lo=wl.data_ptr(), ldb=Kp, b_mn_major=1,
                         M=B, N=K, K=N, mode_x3=x3, split_k=1,
                         out_f32=self.dR.data_ptr(), ld_f32=self.ldr)
+        if self.use_chain:
+            self._build_chains()
         self._pack_dirty = True
 
     def _split(self, x: torch.Tensor, ldx: int, M: int, N: int, hl):
@@ -877,9 +884,13 @@ class Engine:
         ln = self.ln_bot if which == "bot" else self.ln_top
         s = _stream()
         ntc = self.ntc[which]
-        for i in range(ntc):
-            self.tc_plans["fwd"][(which, i)].run(s)
+        if self.use_chain and ntc:
+            self.tc_chains[("fwd", which)].run(s)
             self.n_launch += 1
+        else:
+            for i in range(ntc):
+                self.tc_plans["fwd"][(which, i)].run(s)
+                self.n_launch += 1
         nl = len(ln) - 1
         if which == "top" and self.has_head:
             nl -= 1
@@ -941,41 +952,54 @@ class Engine:
         return p
 
     def _tc_mlp_backward(self, which: str, B: int):
-        """gz of the last tensor-core layer is ready on the current stream.  dgrads stay on it (the
-        critical chain); every wgrad only feeds the final dense update and goes to the side stream."""
-        grouped = self._wgrad_group(which)
+        """gz of the last tensor-core layer is ready on the current stream.  Chain mode: dgrads and weight
+        gradients of the whole MLP are ONE persistent launch.  Per-layer mode: dgrads stay on this stream
+        (the critical chain); every wgrad only feeds the final dense update and goes to the side stream."""
+        if self.use_chain:
+            self.tc_chains[("bwd", which)].run(_stream())
+            self.n_launch += 1
+            return
         for i in reversed(range(self.ntc[which])):
-            if grouped is None:
-                if self.multi_stream:
-                    self._fork(self.s_wg)   # gz_i was produced by the previous launch on this stream
-                    with torch.cuda.stream(self.s_wg):
-                        self.tc_plans["wgrad"][(which, i)].run(_stream())
-                else:
+            if self.multi_stream:
+                self._fork(self.s_wg)   # gz_i was produced by the previous launch on this stream
+                with torch.cuda.stream(self.s_wg):
                     self.tc_plans["wgrad"][(which, i)].run(_stream())
-                self.n_launch += 1
+            else:
+                self.tc_plans["wgrad"][(which, i)].run(_stream())
+            self.n_launch += 1
             pl = self.tc_plans["dgrad"].get((which, i))
             if pl is not None:
                 pl.run(_stream())
                 self.n_launch += 1
-        if grouped is not None:
-            # every gz of this MLP is final: all its weight gradients in one launch on the side stream
-            if self.multi_stream:
-                self._fork(self.s_wg)
-                with torch.cuda.stream(self.s_wg):
-                    _lib.GemmTcPlan.run_group(grouped, _stream())
-            else:
-                _lib.GemmTcPlan.run_group(grouped, _stream())
-            self.n_launch += 1
 
-    def _wgrad_group(self, which: str):
-        """The wgrad plans of one MLP if `group_wgrad` is on and they can share a launch (same tile width,
-        at most 4), else None.  EXPERIMENTAL (off by default): not yet measured on hardware."""
-        if not self.group_wgrad:
-            return None
-        plans = [self.tc_plans["wgrad"][(which, i)] for i in range(self.ntc[which])]
-        if not 1 <= len(plans) <= 4 or len({p.info()["tile_n"] for p in plans}) != 1:
-            return None
-        return plans
+    def _build_chains(self):
+        """Group the per-layer plans into persistent launches.  forward: layer i reads layer i-1's rows.
+        backward (order = claim order): dgrad_i (critical chain, reads dgrad_{i+1}'s rows), then wgrad_i
+        (reads gz_i = dgrad_{i+1}'s output over its k range = batch rows)."""
+        self.tc_chains, self._chain_ctr = {}, {}
+        for which in ("bot", "top"):
+            ntc = self.ntc[which]
+            if ntc == 0:
+                continue
+            plans = [self.tc_plans["fwd"][(which, i)] for i in range(ntc)]
+            self._make_chain(("fwd", which), plans, [-1] + list(range(ntc - 1)), [0] * ntc)
+            plans, dep, onk = [], [], []
+            last_dgrad = -1             # position (in this chain) of the dgrad that produced gz_i
+            for i in reversed(range(ntc)):
+                pl = self.tc_plans["dgrad"].get((which, i))
+                produced_by = last_dgrad
+                if pl is not None:
+                    plans.append(pl); dep.append(produced_by); onk.append(0)
+                    last_dgrad = len(plans) - 1
+                plans.append(self.tc_plans["wgrad"][(which, i)]); dep.append(produced_by); onk.append(1)
+                if pl is None:
+                    last_dgrad = -1
+            self._make_chain(("bwd", which), plans, dep, onk)
+
+    def _make_chain(self, key, plans, dep, onk):
+        ctr = torch.zeros(_lib.GemmChain.counters_needed(plans), dtype=torch.int32, device=self.device)
+        self._chain_ctr[key] = ctr
+        self.tc_chains[key] = _lib.GemmChain(plans, dep, onk, ctr)
 
     def _tc_backward(self, X: torch.Tensor, sp: SparseInput, target: torch.Tensor, update=None):
         B = X.shape[0]

@@ -312,11 +312,25 @@ typedef struct {
 int dlrm_b200_gemm_tc_plan_create(const dlrm_gemm_tc_desc_t* desc /*[host]*/, void** plan);
 int dlrm_b200_gemm_tc_plan_info(void* plan, int* tile_n, int* stages, int* splits, int* ctas);
 int dlrm_b200_gemm_tc_run(void* plan, void* stream);
-/* Up to 4 independent plans of the same tile width in ONE launch (the weight-gradient GEMMs of an MLP:
- * nn.Linear backward w.r.t. weight and bias for every layer, dlrm_s_pytorch.py:1613); results are
- * bit-identical to running the plans one by one. */
-int dlrm_b200_gemm_tc_run_group(void* const* plans /*[host][num_plans]*/, int num_plans, void* stream);
 int dlrm_b200_gemm_tc_plan_destroy(void* plan);
+
+/* A whole MLP chain in ONE persistent launch (apply_mlp: `layers(x)`, dlrm_s_pytorch.py:399-405, and its
+ * autograd: the dgrad chain with every weight-gradient GEMM beside it, :1613).  The plans' output tiles form
+ * one topologically ordered task list (plan order; inside a plan: n tile, m tile, k split); one CTA per SM
+ * claims tasks from a device-side queue and runs TMA -> tcgen05.mma -> epilogue with up to 4 accumulators
+ * in tensor memory, so the epilogue of a tile overlaps the MMAs of the next.  dep[i] >= 0 names the plan
+ * that produces plan i's A operand inside this launch: a task waits until every 128-row block of that
+ * producer covering its A rows (dep_on_k[i] = 0: the task's own m tile; = 1: the task's k range, i.e. a
+ * weight-gradient GEMM reducing over the batch) is complete (per-block counters, release/acquire at GPU
+ * scope + async-proxy fence before the TMA reads).  Results are bit-identical to running the plans one by
+ * one.  counters: caller-owned, zero-initialised int32[counters_len], counters_len >= 2 + sum of the
+ * plans' m tiles; the kernel leaves it zeroed.  Plans must outlive the chain. */
+int dlrm_b200_gemm_chain_create(void* const* plans /*[host][n]*/, const int* dep /*[host][n]*/,
+                                const int* dep_on_k /*[host][n]*/, int n, int32_t* counters,
+                                int64_t counters_len, void** chain);
+int dlrm_b200_gemm_chain_info(void* chain, int* tasks, int* ctas, int* stages, int* smem_bytes);
+int dlrm_b200_gemm_chain_run(void* chain, void* stream);
+int dlrm_b200_gemm_chain_destroy(void* chain);
 
 /* fp32 [M,N] (row stride ldx) -> (hi, lo) bf16 [M, ld_out]; lo may be NULL */
 int dlrm_b200_split_bf16(const float* X, int64_t ldx, int64_t M, int64_t N, void* hi, void* lo,
