@@ -42,7 +42,8 @@ class GemmTcDesc(C.Structure):
                 ("out_f32", C.c_void_p), ("ld_f32", C.c_int64), ("slab_stride", C.c_int64),
                 ("out_hi", C.c_void_p), ("out_lo", C.c_void_p), ("ld_out", C.c_int64),
                 ("outT_hi", C.c_void_p), ("outT_lo", C.c_void_p), ("ld_outT", C.c_int64),
-                ("out_col", C.c_void_p), ("col_index", C.c_int64), ("col_slab_stride", C.c_int64)]
+                ("out_col", C.c_void_p), ("col_index", C.c_int64), ("col_slab_stride", C.c_int64),
+                ("bias", C.c_void_p)]
 
 
 class DenseLayer(C.Structure):
@@ -68,7 +69,7 @@ SYMBOLS = [
     "dlrm_b200_dense_update",
     "dlrm_b200_gemm_tc_plan_create", "dlrm_b200_gemm_tc_plan_info", "dlrm_b200_gemm_tc_run",
     "dlrm_b200_gemm_tc_plan_destroy", "dlrm_b200_gemm_chain_create", "dlrm_b200_gemm_chain_info",
-    "dlrm_b200_gemm_chain_run", "dlrm_b200_gemm_chain_destroy", "dlrm_b200_split_bf16", "dlrm_b200_dense_update_pack",
+    "dlrm_b200_gemm_chain_run", "dlrm_b200_gemm_chain_destroy", "dlrm_b200_gemm_chain_set_trace", "dlrm_b200_split_bf16", "dlrm_b200_dense_update_pack",
 ]
 
 
@@ -116,6 +117,7 @@ def _declare(lib):
     lib.dlrm_b200_gemm_chain_create.argtypes = [C.POINTER(vp), C.POINTER(i32), C.POINTER(i32), i32, vp, i64, C.POINTER(vp)]
     lib.dlrm_b200_gemm_chain_info.argtypes = [vp, C.POINTER(i32), C.POINTER(i32), C.POINTER(i32), C.POINTER(i32)]
     lib.dlrm_b200_gemm_chain_run.argtypes = [vp, vp]
+    lib.dlrm_b200_gemm_chain_set_trace.argtypes = [vp, vp]
     lib.dlrm_b200_gemm_chain_destroy.argtypes = [vp]
     lib.dlrm_b200_gemm_tc_plan_destroy.argtypes = [vp]
     lib.dlrm_b200_split_bf16.argtypes = [vp, i64, i64, i64, vp, vp, i64, vp]
@@ -224,6 +226,12 @@ class GemmChain:
 
     def run(self, stream):
         check(lib().dlrm_b200_gemm_chain_run(self.handle, stream), "gemm_chain_run")
+
+    def set_trace(self, trace):
+        """trace: uint64/int64 device tensor [tasks, 8] (or None to switch tracing off)."""
+        self._trace = trace
+        check(lib().dlrm_b200_gemm_chain_set_trace(self.handle, trace.data_ptr() if trace is not None else None),
+              "gemm_chain_set_trace")
 
     def __del__(self):
         try:

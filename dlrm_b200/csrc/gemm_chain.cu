@@ -51,6 +51,9 @@ struct ChParams {
   uint32_t stage_bytes;
   int* ctr;           // [0] task queue, [1] exit count, [2...] completion counters
   int n_ctr;
+  // optional per-task timeline (globaltimer ns), 8 words per task: claim, deps ready, last TMA issued,
+  // first operands landed, last MMA issued, accumulator ready, epilogue + signal done, SM id
+  unsigned long long* trace;
 };
 
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
@@ -80,113 +83,6 @@ __device__ __forceinline__ ChTask ch_decode(const ChParams& P, int t) {
   return k;
 }
 
-// Epilogue of one tile: same per-element program as gemm_tc_body.cuh (tile width at run time).
-__device__ __forceinline__ void ch_epilogue(const TcArgs& g, int bn, int m0, int n0, int bz, uint32_t tmem_acc,
-                                            int quad, int lane) {
-  const long long m = (long long)m0 + quad * 32 + lane;
-  const bool m_ok = m < g.M;
-  float* of32 = g.out_f32 ? g.out_f32 + (long long)bz * g.slab_stride : nullptr;
-  float* ocol = g.out_col ? g.out_col + (long long)bz * g.col_slab_stride : nullptr;
-#pragma unroll 1
-  for (int c = 0; c < bn / 32; ++c) {
-    uint32_t r[32];
-    tmem_ld32(tmem_acc + ((uint32_t)(quad * 32) << 16) + (uint32_t)(c * 32), r);
-    const long long nb = (long long)n0 + c * 32;
-    if (nb >= g.N) break;
-    float v[32];
-#pragma unroll
-    for (int j = 0; j < 32; ++j) v[j] = apply_act_tc(__uint_as_float(r[j]), g.act);
-    const bool full = nb + 32 <= g.N;
-    if (g.mask_act != DLRM_ACT_NONE && m_ok) {
-      if (full && (g.ldmask & 7) == 0) {
-        __align__(16) __nv_bfloat16 yh[32], yl[32];
-        const uint4* ph = reinterpret_cast<const uint4*>(g.mask_hi + m * g.ldmask + nb);
-#pragma unroll
-        for (int q = 0; q < 4; ++q) reinterpret_cast<uint4*>(yh)[q] = ph[q];
-        if (g.mask_act == DLRM_ACT_RELU) {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = __bfloat162float(yh[j]) > 0.f ? v[j] : 0.f;
-        } else {
-          if (g.mask_lo) {
-            const uint4* pl = reinterpret_cast<const uint4*>(g.mask_lo + m * g.ldmask + nb);
-#pragma unroll
-            for (int q = 0; q < 4; ++q) reinterpret_cast<uint4*>(yl)[q] = pl[q];
-          }
-#pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            float y = __bfloat162float(yh[j]);
-            if (g.mask_lo) y += __bfloat162float(yl[j]);
-            v[j] *= (1.0f - y) * y;
-          }
-        }
-      } else {
-#pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          if (full || nb + j < g.N) {
-            const long long o = m * g.ldmask + nb + j;
-            float y = __bfloat162float(g.mask_hi[o]);
-            if (g.mask_act == DLRM_ACT_RELU) {
-              v[j] = y > 0.f ? v[j] : 0.f;
-            } else {
-              if (g.mask_lo) y += __bfloat162float(g.mask_lo[o]);
-              v[j] *= (1.0f - y) * y;
-            }
-          }
-        }
-      }
-    }
-    if (of32 && m_ok) {
-      float* p = of32 + m * g.ld_f32 + nb;
-      const bool colsplit = ocol != nullptr && g.col_index >= nb && g.col_index < nb + 32;
-      if (full && !colsplit && (g.ld_f32 & 3) == 0) {
-#pragma unroll
-        for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(p + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-      } else {
-#pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          if (nb + j < g.N) {
-            if (ocol && nb + j == g.col_index) ocol[m] = v[j];
-            else if (!ocol || nb + j < g.col_index) p[j] = v[j];
-          }
-        }
-      }
-    }
-    if (g.out_hi || g.outT_hi) {
-      __nv_bfloat16 hi[32], lo[32];
-#pragma unroll
-      for (int j = 0; j < 32; ++j) {
-        hi[j] = __float2bfloat16_rn(v[j]);
-        lo[j] = __float2bfloat16_rn(v[j] - __bfloat162float(hi[j]));
-      }
-      if (g.out_hi && m_ok) {
-        __nv_bfloat16* ph = g.out_hi + m * g.ld_out + nb;
-        __nv_bfloat16* pl = g.out_lo ? g.out_lo + m * g.ld_out + nb : nullptr;
-        if (full) {
-#pragma unroll
-          for (int j = 0; j < 32; j += 8) {
-            *reinterpret_cast<uint4*>(ph + j) = *reinterpret_cast<const uint4*>(&hi[j]);
-            if (pl) *reinterpret_cast<uint4*>(pl + j) = *reinterpret_cast<const uint4*>(&lo[j]);
-          }
-        } else {
-#pragma unroll
-          for (int j = 0; j < 32; ++j)
-            if (nb + j < g.N) { ph[j] = hi[j]; if (pl) pl[j] = lo[j]; }
-        }
-      }
-      if (g.outT_hi && m_ok) {
-#pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          if (full || nb + j < g.N) {
-            const long long o = (nb + j) * g.ld_outT + m;
-            g.outT_hi[o] = hi[j];
-            if (g.outT_lo) g.outT_lo[o] = lo[j];
-          }
-        }
-      }
-    }
-  }
-}
-
 __global__ void __launch_bounds__(192, 1) gemm_chain_kernel(const __grid_constant__ ChParams P) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -196,6 +92,7 @@ __global__ void __launch_bounds__(192, 1) gemm_chain_kernel(const __grid_constan
   // bars: full[stages] | empty[stages] | acc_full[4] | acc_empty[4] | task_full[4] | task_empty[4]
   int* ring = reinterpret_cast<int*>(bars + 2 * stages + 2 * CH_ACC_STAGES + 2 * CH_RING);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(ring + CH_RING);
+  uint8_t* epi_stage = smem + (size_t)stages * stage_bytes + 512;   // barriers + ring + slot < 512 B
 
   pdl_launch_dependents();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -246,6 +143,7 @@ __global__ void __launch_bounds__(192, 1) gemm_chain_kernel(const __grid_constan
         mbar_arrive(bar_task_full + 8 * slot);
         if (++slot == CH_RING) { slot = 0; tph ^= 1; }
         if (t >= P.total) break;
+        if (P.trace) P.trace[(size_t)t * 8 + 0] = globaltimer_ns();
         const int tnext = atomicAdd(P.ctr, 1);    // claimed one task ahead: the round trip hides behind this task
         const ChTask k = ch_decode(P, t);
         const ChProblem& Q = P.p[k.pi];
@@ -272,6 +170,7 @@ __global__ void __launch_bounds__(192, 1) gemm_chain_kernel(const __grid_constan
           }
           asm volatile("fence.proxy.async;" ::: "memory");   // producer's generic-proxy stores -> our TMA reads
         }
+        if (P.trace) P.trace[(size_t)t * 8 + 1] = globaltimer_ns();
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(bar_empty + 8 * stage, phase ^ 1);
           const uint32_t full = bar_full + 8 * stage;
@@ -299,6 +198,7 @@ __global__ void __launch_bounds__(192, 1) gemm_chain_kernel(const __grid_constan
           }
           if (++stage == stages) { stage = 0; phase ^= 1; }
         }
+        if (P.trace) P.trace[(size_t)t * 8 + 2] = globaltimer_ns();
         t = tnext;
       }
     }
@@ -330,6 +230,7 @@ __global__ void __launch_bounds__(192, 1) gemm_chain_kernel(const __grid_constan
         mbar_wait(bar_full + 8 * stage, phase);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         if (lane == 0) {
+          if (P.trace && kb == kb0) P.trace[(size_t)t * 8 + 3] = globaltimer_ns();
           const uint32_t sa_hi = smem_base + stage * stage_bytes;
           const uint32_t sa_lo = sa_hi + A_BYTES;
           const uint32_t sb_hi = sa_hi + (g.x3 ? 2u : 1u) * A_BYTES;
@@ -353,7 +254,10 @@ __global__ void __launch_bounds__(192, 1) gemm_chain_kernel(const __grid_constan
             accum = 1u;
           }
           umma_commit(bar_empty + 8 * stage);
-          if (kb == kb1 - 1) umma_commit(bar_acc_full + 8 * as);
+          if (kb == kb1 - 1) {
+            umma_commit(bar_acc_full + 8 * as);
+            if (P.trace) P.trace[(size_t)t * 8 + 4] = globaltimer_ns();
+          }
         }
         __syncwarp();
         if (++stage == stages) { stage = 0; phase ^= 1; }
@@ -376,7 +280,9 @@ __global__ void __launch_bounds__(192, 1) gemm_chain_kernel(const __grid_constan
       const ChProblem& Q = P.p[k.pi];
       mbar_wait(bar_acc_full + 8 * as, aph);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      ch_epilogue(Q.a, Q.bn, k.by * TC_BM, k.bx * Q.bn, k.bz, tmem_base + (uint32_t)(as * 128), quad, lane);
+      if (P.trace && warp == 2 && lane == 0) P.trace[(size_t)t * 8 + 5] = globaltimer_ns();
+      tc_epilogue_tile(Q.a, Q.bn, k.by * TC_BM, k.bx * Q.bn, k.bz, tmem_base + (uint32_t)(as * 128), quad, lane,
+                       epi_stage + (size_t)(warp - 2) * TC_EPI_WARP_BYTES);
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       __syncwarp();
       if (lane == 0) mbar_arrive(bar_acc_empty + 8 * as);
@@ -387,6 +293,12 @@ __global__ void __launch_bounds__(192, 1) gemm_chain_kernel(const __grid_constan
           asm volatile("fence.proxy.async;" ::: "memory");
           red_release_gpu_add(P.ctr + 2 + Q.ctr_base + k.by, 1);
         }
+      }
+      if (P.trace && warp == 2 && lane == 0) {
+        unsigned smid;
+        asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+        P.trace[(size_t)t * 8 + 6] = globaltimer_ns();
+        P.trace[(size_t)t * 8 + 7] = smid;
       }
       if (++as == CH_ACC_STAGES) { as = 0; aph ^= 1; }
     }
@@ -462,14 +374,14 @@ extern "C" int dlrm_b200_gemm_chain_create(void* const* plans, const int* dep, c
   P.total = (int)total;
   P.stage_bytes = stage_bytes;
   int budget_kb = get_tunable(TUNE_GEMM_SMEM_KB);
-  if (budget_kb <= 0 || budget_kb > 216) budget_kb = 216;
+  if (budget_kb <= 0 || budget_kb > 200) budget_kb = 200;
   int stages = (int)(((size_t)budget_kb * 1024) / stage_bytes);
   if (stages > 8) stages = 8;
   if (stages < 2) stages = 2;
   P.stages = stages;
   P.ctr = counters;
   P.n_ctr = (int)(2 + nctr);
-  c->smem = (size_t)stages * stage_bytes + (2 * stages + 2 * CH_ACC_STAGES + 2 * CH_RING) * 8 + CH_RING * 4 + 16 + 1024;
+  c->smem = (size_t)stages * stage_bytes + 512 + TC_EPI_BYTES + 1024;   // ring | barriers, task ring | epilogue staging
   int dev = 0, sms = 0;
   DLRM_CUDA(cudaGetDevice(&dev));
   DLRM_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
@@ -486,6 +398,13 @@ extern "C" int dlrm_b200_gemm_chain_info(void* chain, int* tasks, int* ctas, int
   if (ctas) *ctas = (int)c->grid;
   if (stages) *stages = c->P.stages;
   if (smem_bytes) *smem_bytes = (int)c->smem;
+  return 0;
+}
+
+extern "C" int dlrm_b200_gemm_chain_set_trace(void* chain, uint64_t* trace) {
+  using namespace dlrm;
+  if (!chain) return set_error("gemm_chain_set_trace: NULL chain");
+  static_cast<Chain*>(chain)->P.trace = reinterpret_cast<unsigned long long*>(trace);
   return 0;
 }
 

@@ -123,6 +123,7 @@ extern "C" int dlrm_b200_gemm_tc_plan_create(const dlrm_gemm_tc_desc_t* d, void*
   a.outT_hi = static_cast<__nv_bfloat16*>(d->outT_hi); a.outT_lo = static_cast<__nv_bfloat16*>(d->outT_lo);
   a.ld_outT = d->ld_outT;
   a.out_col = d->out_col; a.col_index = d->col_index; a.col_slab_stride = d->col_slab_stride;
+  a.bias = d->bias;
   if (a.mask_act != DLRM_ACT_NONE && !a.mask_hi) { delete p; return set_error("gemm_tc: mask_act without mask_hi"); }
   if (a.out_hi && (a.ld_out % 8)) { delete p; return set_error("gemm_tc: ld_out must be a multiple of 8"); }
   // tile width: keep >= ~64 CTAs when N is small
@@ -149,7 +150,7 @@ extern "C" int dlrm_b200_gemm_tc_plan_create(const dlrm_gemm_tc_desc_t* d, void*
   a.kb_per_split = (a.num_kb + splits - 1) / splits;
   splits = (a.num_kb + a.kb_per_split - 1) / a.kb_per_split;  // no empty split
   p->splits = splits;
-  if (splits > 1 && (a.out_hi || a.outT_hi || a.act != DLRM_ACT_NONE || a.mask_act != DLRM_ACT_NONE)) {
+  if (splits > 1 && (a.out_hi || a.outT_hi || a.act != DLRM_ACT_NONE || a.mask_act != DLRM_ACT_NONE || a.bias)) {
     delete p; return set_error("gemm_tc: split-K only supports fp32 slab outputs");
   }
   const size_t stage_bytes = (size_t)(a.x3 ? 2 : 1) * (TC_BM * TC_BK * 2 + bn * TC_BK * 2);
@@ -158,7 +159,7 @@ extern "C" int dlrm_b200_gemm_tc_plan_create(const dlrm_gemm_tc_desc_t* d, void*
   if (stages < 2) stages = 2;
   if (stages > a.kb_per_split) stages = a.kb_per_split < 2 ? 2 : a.kb_per_split;
   p->stages = stages;
-  p->smem = stages * stage_bytes + (2 * stages + 1) * 8 + 16 + 1024;
+  p->smem = stages * stage_bytes + 256 + TC_EPI_BYTES + 1024;   // ring | barriers (<= 256 B) | epilogue staging
   p->grid = dim3((unsigned)((d->N + bn - 1) / bn), (unsigned)mt, (unsigned)splits);
   int rc = 0;
   // operand maps.  K-major: tensor [rows, K]; MN-major: tensor [K, rows].

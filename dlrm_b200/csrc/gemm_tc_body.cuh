@@ -127,109 +127,8 @@
     const int quad = warp & 3;  // TMEM lane quadrant this warp may access
     mbar_wait(bar_base + 8 * (2 * stages), 0);
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    const long long m = (long long)m0 + quad * 32 + lane;
-    const bool m_ok = m < g.M;
-    float* of32 = g.out_f32 ? g.out_f32 + (long long)TCB_BZ * g.slab_stride : nullptr;
-    float* ocol = g.out_col ? g.out_col + (long long)TCB_BZ * g.col_slab_stride : nullptr;
-#pragma unroll 1
-    for (int c = 0; c < BN / 32; ++c) {
-      uint32_t r[32];
-      tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(c * 32), r);
-      const long long nb = (long long)n0 + c * 32;
-      if (nb >= g.N) break;
-      float v[32];
-#pragma unroll
-      for (int j = 0; j < 32; ++j) v[j] = apply_act_tc(__uint_as_float(r[j]), g.act);
-      const bool full = nb + 32 <= g.N;
-      if (g.mask_act != DLRM_ACT_NONE && m_ok) {
-        if (full && (g.ldmask & 7) == 0) {
-          // 32 bf16 of this row = 4 x 16-byte loads (hi), + 4 (lo) for sigmoid'
-          __align__(16) __nv_bfloat16 yh[32], yl[32];
-          const uint4* ph = reinterpret_cast<const uint4*>(g.mask_hi + m * g.ldmask + nb);
-#pragma unroll
-          for (int q = 0; q < 4; ++q) reinterpret_cast<uint4*>(yh)[q] = ph[q];
-          if (g.mask_act == DLRM_ACT_RELU) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = __bfloat162float(yh[j]) > 0.f ? v[j] : 0.f;
-          } else {
-            if (g.mask_lo) {
-              const uint4* pl = reinterpret_cast<const uint4*>(g.mask_lo + m * g.ldmask + nb);
-#pragma unroll
-              for (int q = 0; q < 4; ++q) reinterpret_cast<uint4*>(yl)[q] = pl[q];
-            }
-#pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              float y = __bfloat162float(yh[j]);
-              if (g.mask_lo) y += __bfloat162float(yl[j]);
-              v[j] *= (1.0f - y) * y;
-            }
-          }
-        } else {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            if (full || nb + j < g.N) {
-              const long long o = m * g.ldmask + nb + j;
-              float y = __bfloat162float(g.mask_hi[o]);
-              if (g.mask_act == DLRM_ACT_RELU) {
-                v[j] = y > 0.f ? v[j] : 0.f;
-              } else {
-                if (g.mask_lo) y += __bfloat162float(g.mask_lo[o]);
-                v[j] *= (1.0f - y) * y;
-              }
-            }
-          }
-        }
-      }
-      if (of32 && m_ok) {
-        float* p = of32 + m * g.ld_f32 + nb;
-        const bool colsplit = ocol != nullptr && g.col_index >= nb && g.col_index < nb + 32;
-        if (full && !colsplit && (g.ld_f32 & 3) == 0) {
-#pragma unroll
-          for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(p + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-        } else {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            if (nb + j < g.N) {
-              if (ocol && nb + j == g.col_index) ocol[m] = v[j];
-              else if (!ocol || nb + j < g.col_index) p[j] = v[j];
-            }
-          }
-        }
-      }
-      if (g.out_hi || g.outT_hi) {
-        __nv_bfloat16 hi[32], lo[32];
-#pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          hi[j] = __float2bfloat16_rn(v[j]);
-          lo[j] = __float2bfloat16_rn(v[j] - __bfloat162float(hi[j]));
-        }
-        if (g.out_hi && m_ok) {
-          __nv_bfloat16* ph = g.out_hi + m * g.ld_out + nb;
-          __nv_bfloat16* pl = g.out_lo ? g.out_lo + m * g.ld_out + nb : nullptr;
-          if (full) {
-#pragma unroll
-            for (int j = 0; j < 32; j += 8) {
-              *reinterpret_cast<uint4*>(ph + j) = *reinterpret_cast<const uint4*>(&hi[j]);
-              if (pl) *reinterpret_cast<uint4*>(pl + j) = *reinterpret_cast<const uint4*>(&lo[j]);
-            }
-          } else {
-#pragma unroll
-            for (int j = 0; j < 32; ++j)
-              if (nb + j < g.N) { ph[j] = hi[j]; if (pl) pl[j] = lo[j]; }
-          }
-        }
-        if (g.outT_hi && m_ok) {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            if (full || nb + j < g.N) {
-              const long long o = (nb + j) * g.ld_outT + m;
-              g.outT_hi[o] = hi[j];
-              if (g.outT_lo) g.outT_lo[o] = lo[j];
-            }
-          }
-        }
-      }
-    }
+    uint8_t* stage_warp = smem + (size_t)stages * stage_bytes + 256 + (size_t)(warp - 2) * TC_EPI_WARP_BYTES;
+    tc_epilogue_tile(g, BN, m0, n0, TCB_BZ, tmem_base, quad, lane, stage_warp);
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   }
   __syncthreads();

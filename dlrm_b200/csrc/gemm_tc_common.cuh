@@ -32,6 +32,7 @@ struct TcArgs {
   long long ld_outT;
   float* out_col;
   long long col_index, col_slab_stride;
+  const float* bias;   // optional fp32 [N], added to the accumulator before the activation
 };
 
 // ------------------------------------------------------------------------------------------ PTX
@@ -116,6 +117,187 @@ __device__ __forceinline__ float apply_act_tc(float v, int act) {
   return v;
 }
 
+
+// ------------------------------------------------------------------------------------------ epilogue
+// One accumulator tile (128 rows x bn columns in tensor memory) -> global memory, shared by the per-layer
+// kernel (gemm_tc.cu) and the persistent chain kernel (gemm_chain.cu).
+//
+// tcgen05.ld hands every thread ONE ROW (32 consecutive columns per load).  Storing from that layout makes
+// each warp-wide 16-byte store hit 32 different rows (32 half-written sectors per instruction); measured with
+// the chain kernel's per-task timeline (tools/chain_timeline.py, profiles/r2_chain_timeline_before.txt) that
+// cost 10-19 us per 128 x 128 tile -- more than the tile's MMAs.  Here every 32 x 32 chunk is transposed
+// through a per-warp shared-memory tile (padded rows: conflict-free 16-byte accesses) so that a warp store
+// covers whole row segments: 8 rows x 64 B for the bf16 (hi, lo) operands, 4 rows x 128 B for fp32; the
+// activation-gradient mask is read the same way.  Chunks that are ragged (N tail, the diverted bias-gradient
+// column) or whose rows are not 16-byte aligned use element-wise but still row-contiguous accesses.
+constexpr int TC_EPI_ROW_F32 = 36;                 // floats per staged fp32 row (32 + 4 pad)
+constexpr int TC_EPI_ROW_BF16 = 40;                // bf16 per staged bf16 row (32 + 8 pad)
+constexpr int TC_EPI_WARP_BYTES = 32 * TC_EPI_ROW_F32 * 4;   // 4608 B per epilogue warp
+constexpr int TC_EPI_BYTES = 4 * TC_EPI_WARP_BYTES;
+
+// 32 x 32 bf16 chunk, one row per thread in `mine` -> global rows [mrow0, mrow0 + 32) x columns [nb, nb + 32)
+__device__ __forceinline__ void tc_epi_store_bf16(const __nv_bfloat16 (&mine)[32], __nv_bfloat16* dst, long long ld,
+                                                  long long mrow0, long long nb, long long M, long long N, bool vec,
+                                                  int lane, __nv_bfloat16* sb) {
+#pragma unroll
+  for (int q = 0; q < 4; ++q)
+    *reinterpret_cast<uint4*>(sb + lane * TC_EPI_ROW_BF16 + q * 8) = reinterpret_cast<const uint4*>(mine)[q];
+  __syncwarp();
+  if (vec) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {     // 8 rows x 64 B per warp store
+      const int row = i * 8 + (lane >> 2), seg = lane & 3;
+      if (mrow0 + row < M)
+        *reinterpret_cast<uint4*>(dst + (mrow0 + row) * ld + nb + seg * 8) =
+            *reinterpret_cast<const uint4*>(sb + row * TC_EPI_ROW_BF16 + seg * 8);
+    }
+  } else {
+    const long long col = nb + lane;
+    for (int row = 0; row < 32; ++row) {
+      if (mrow0 + row >= M) break;
+      if (col < N) dst[(mrow0 + row) * ld + col] = sb[row * TC_EPI_ROW_BF16 + lane];
+    }
+  }
+  __syncwarp();
+}
+
+__device__ __forceinline__ void tc_epilogue_tile(const TcArgs& g, int bn, int m0, int n0, int bz, uint32_t tmem_acc,
+                                                 int quad, int lane, uint8_t* stage_warp) {
+  const long long mrow0 = (long long)m0 + quad * 32;   // first row of this warp
+  const long long m = mrow0 + lane;
+  const bool m_ok = m < g.M;
+  float* of32 = g.out_f32 ? g.out_f32 + (long long)bz * g.slab_stride : nullptr;
+  float* ocol = g.out_col ? g.out_col + (long long)bz * g.col_slab_stride : nullptr;
+  float* sf = reinterpret_cast<float*>(stage_warp);
+  __nv_bfloat16* sb = reinterpret_cast<__nv_bfloat16*>(stage_warp);
+  const bool f32_vec = of32 && (g.ld_f32 & 3) == 0 && (reinterpret_cast<uintptr_t>(of32) & 15) == 0;
+  const bool bf_vec = g.out_hi && (g.ld_out & 7) == 0 && (reinterpret_cast<uintptr_t>(g.out_hi) & 15) == 0 &&
+                      (!g.out_lo || (reinterpret_cast<uintptr_t>(g.out_lo) & 15) == 0);
+  const bool mask_vec = g.mask_act != DLRM_ACT_NONE && (g.ldmask & 7) == 0 &&
+                        (reinterpret_cast<uintptr_t>(g.mask_hi) & 15) == 0 &&
+                        (!g.mask_lo || (reinterpret_cast<uintptr_t>(g.mask_lo) & 15) == 0);
+#pragma unroll 1
+  for (int c = 0; c < bn / 32; ++c) {
+    uint32_t r[32];
+    tmem_ld32(tmem_acc + ((uint32_t)(quad * 32) << 16) + (uint32_t)(c * 32), r);
+    const long long nb = (long long)n0 + c * 32;
+    if (nb >= g.N) break;
+    float v[32];
+    const bool full = nb + 32 <= g.N;
+    if (g.bias) {     // nn.Linear bias (broadcast over rows: every lane reads the same 32 values -> one L1 line)
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        const float bj = (full || nb + j < g.N) ? __ldg(g.bias + nb + j) : 0.f;
+        v[j] = apply_act_tc(__uint_as_float(r[j]) + bj, g.act);
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) v[j] = apply_act_tc(__uint_as_float(r[j]), g.act);
+    }
+    // ---------------------------------------------------------------- activation-gradient mask
+    if (g.mask_act != DLRM_ACT_NONE) {
+      if (full && mask_vec) {
+        for (int pass = 0; pass < (g.mask_act == DLRM_ACT_SIGMOID && g.mask_lo ? 2 : 1); ++pass) {
+          const __nv_bfloat16* src = pass ? g.mask_lo : g.mask_hi;
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {       // 8 rows x 64 B per warp load
+            const int row = i * 8 + (lane >> 2), seg = lane & 3;
+            uint4 t = make_uint4(0, 0, 0, 0);
+            if (mrow0 + row < g.M) t = *reinterpret_cast<const uint4*>(src + (mrow0 + row) * g.ldmask + nb + seg * 8);
+            *reinterpret_cast<uint4*>(sb + row * TC_EPI_ROW_BF16 + seg * 8) = t;
+          }
+          __syncwarp();
+          __align__(16) __nv_bfloat16 y[32];
+#pragma unroll
+          for (int q = 0; q < 4; ++q)
+            reinterpret_cast<uint4*>(y)[q] = *reinterpret_cast<const uint4*>(sb + lane * TC_EPI_ROW_BF16 + q * 8);
+          __syncwarp();
+          if (g.mask_act == DLRM_ACT_RELU) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = __bfloat162float(y[j]) > 0.f ? v[j] : 0.f;
+          } else if (!g.mask_lo) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) { const float yy = __bfloat162float(y[j]); v[j] *= (1.0f - yy) * yy; }
+          } else if (pass == 0) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) r[j] = __float_as_uint(__bfloat162float(y[j]));   // keep hi, add lo next pass
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              const float yy = __uint_as_float(r[j]) + __bfloat162float(y[j]);
+              v[j] *= (1.0f - yy) * yy;
+            }
+          }
+        }
+      } else if (m_ok) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          if (full || nb + j < g.N) {
+            const long long o = m * g.ldmask + nb + j;
+            float y = __bfloat162float(g.mask_hi[o]);
+            if (g.mask_act == DLRM_ACT_RELU) {
+              v[j] = y > 0.f ? v[j] : 0.f;
+            } else {
+              if (g.mask_lo) y += __bfloat162float(g.mask_lo[o]);
+              v[j] *= (1.0f - y) * y;
+            }
+          }
+        }
+      }
+    }
+    // ---------------------------------------------------------------- fp32 output (+ diverted column)
+    if (of32) {
+#pragma unroll
+      for (int q = 0; q < 8; ++q)
+        *reinterpret_cast<float4*>(sf + lane * TC_EPI_ROW_F32 + q * 4) = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+      __syncwarp();
+      const bool colsplit = ocol != nullptr && g.col_index >= nb && g.col_index < nb + 32;
+      if (full && !colsplit && f32_vec && (!ocol || nb + 32 <= g.col_index)) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {         // 4 rows x 128 B per warp store
+          const int row = i * 4 + (lane >> 3), seg = lane & 7;
+          if (mrow0 + row < g.M)
+            *reinterpret_cast<float4*>(of32 + (mrow0 + row) * g.ld_f32 + nb + seg * 4) =
+                *reinterpret_cast<const float4*>(sf + row * TC_EPI_ROW_F32 + seg * 4);
+        }
+      } else {
+        const long long col = nb + lane;      // one row per store: 32 consecutive floats
+        const bool to_col = ocol && col == g.col_index;
+        const bool to_out = col < g.N && (!ocol || col < g.col_index);
+        for (int row = 0; row < 32; ++row) {
+          if (mrow0 + row >= g.M) break;
+          const float x = sf[row * TC_EPI_ROW_F32 + lane];
+          if (to_col) ocol[mrow0 + row] = x;
+          else if (to_out) of32[(mrow0 + row) * g.ld_f32 + col] = x;
+        }
+      }
+      __syncwarp();
+    }
+    // ---------------------------------------------------------------- (hi, lo) bf16 operand outputs
+    if (g.out_hi || g.outT_hi) {
+      __align__(16) __nv_bfloat16 hi[32], lo[32];
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        hi[j] = __float2bfloat16_rn(v[j]);
+        lo[j] = __float2bfloat16_rn(v[j] - __bfloat162float(hi[j]));
+      }
+      if (g.out_hi) {
+        tc_epi_store_bf16(hi, g.out_hi, g.ld_out, mrow0, nb, g.M, g.N, full && bf_vec, lane, sb);
+        if (g.out_lo) tc_epi_store_bf16(lo, g.out_lo, g.ld_out, mrow0, nb, g.M, g.N, full && bf_vec, lane, sb);
+      }
+      if (g.outT_hi && m_ok) {                // transposed copy: consecutive lanes = consecutive rows = contiguous
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          if (full || nb + j < g.N) {
+            const long long o = (nb + j) * g.ld_outT + m;
+            g.outT_hi[o] = hi[j];
+            if (g.outT_lo) g.outT_lo[o] = lo[j];
+          }
+        }
+      }
+    }
+  }
+}
 
 struct TcPlan {
   CUtensorMap tmAh, tmAl, tmBh, tmBl;

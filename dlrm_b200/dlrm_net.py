@@ -67,7 +67,11 @@ class _DLRMForward(torch.autograd.Function):
     @staticmethod
     def forward(ctx, net, sp, train, dense_x, *params):
         eng = net._engine
-        linked = bool(train) and net._fused_opt is not None   # training forward: gather also links
+        # The per-row occurrence lists of the sort-free coalesce (head[] / link[]) are built by
+        # optimizer.step() itself, never here: a grad-enabled forward that is NOT followed by a step (the
+        # reference's inference() loop, a skipped step, two forwards before one backward) would otherwise
+        # leave stale list heads behind for the next update to follow.
+        linked = False
         p = eng.forward(dense_x, sp, link=linked)
         ctx.net, ctx.sp, ctx.x, ctx.nparams, ctx.linked = net, sp, dense_x, len(params), linked
         return p.clone()
@@ -78,6 +82,10 @@ class _DLRMForward(torch.autograd.Function):
         eng.backward_from_output_grad(ctx.x, ctx.sp, gp.contiguous())
         grads: List[Optional[torch.Tensor]] = []
         if net._fused_opt is not None:
+            if net._pending is not None:
+                raise RuntimeError("dlrm_b200: backward() called twice before optimizer.step(): gradient "
+                                   "accumulation is not supported by the fused optimizers (the second "
+                                   "micro-batch would overwrite the first)")
             net._pending = (ctx.sp, ctx.linked)          # consumed by the fused optimizer's step()
             return (None, None, None, None) + (None,) * ctx.nparams
         grads += net._materialise_sparse_grads(ctx.sp)

@@ -794,10 +794,12 @@ class Engine:
                 ih, il, Kp = self.tc_in[which][i]
                 wh, wl, _ = self.tc_W[which][i]
                 gh, gl, Np = self.tc_gz[which][i]
-                # ---- forward: Y = act([X | 1] [W | b]^T)
+                # ---- forward: Y = act(X W^T + b): bias added in fp32 in the epilogue (the constant-1 column of
+                # the activations only serves the weight-gradient GEMM: a K of 512 stays 8 k-blocks, not 9)
                 kw = dict(A_hi=ih.data_ptr(), A_lo=il.data_ptr(), lda=Kp, a_mn_major=0,
                           B_hi=wh.data_ptr(), B_lo=wl.data_ptr(), ldb=Kp, b_mn_major=0,
-                          M=B, N=N, K=K + 1, mode_x3=x3, split_k=1, act=self._act(which, i))
+                          M=B, N=N, K=K, mode_x3=x3, split_k=1, act=self._act(which, i),
+                          bias=self.b[which][i].data_ptr())
                 if i + 1 < ntc:
                     oh, ol, Kp2 = self.tc_in[which][i + 1]
                     kw.update(out_hi=oh.data_ptr(), out_lo=ol.data_ptr(), ld_out=Kp2)
@@ -1058,7 +1060,8 @@ class Engine:
                 upd()
         self._tc_mlp_backward("bot", B)
         if self.multi_stream:
-            self._join(self.s_wg)
+            if not self.use_chain:
+                self._join(self.s_wg)
             if update is not None and has_emb and getattr(self, "_join_update", True):
                 self._join(self.s_emb)
 

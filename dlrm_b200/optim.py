@@ -38,6 +38,7 @@ class _Fused(torch.optim.Optimizer):
         self.net._engine.ensure_optimizer_state(self._name)
 
     def zero_grad(self, set_to_none: bool = True):
+        self.net._pending = None      # discards a backward() whose step() was skipped
         for g in self.param_groups:
             for p in g["params"]:
                 p.grad = None

@@ -287,7 +287,8 @@ int dlrm_b200_dense_update(float* param, const float* grad, float* state /*NULL 
  * Operands are (hi, lo) bf16 pairs of fp32 values (hi = bf16(x), lo = bf16(x - hi)); mode_x3
  * computes hi*hi + hi*lo + lo*hi (fp32-grade), otherwise hi*hi only.  An operand is K-major
  * ([rows, K], ld = row stride) or MN-major ([K, rows]); ld in elements, multiple of 8.
- * The bias is folded into the GEMM: activations carry a constant-1 column, weights a bias column.
+ * Bias: forward layers add `bias` (fp32) in the epilogue; the weight-gradient GEMMs get the bias gradient
+ * for free from a constant-1 column of the activations ([dW | db] = gz^T [X | 1]).
  * Epilogue (all optional): act(); multiply by act'(y), y = mask_hi + mask_lo [M, ldmask];
  * fp32 store (split-K: one slab per split, reduced by dense_update_pack); one column diverted to
  * out_col (bias gradient); (hi, lo) bf16 stores in normal [M, ld_out] and transposed [N, ld_outT]
@@ -307,6 +308,7 @@ typedef struct {
   void* out_hi; void* out_lo; int64_t ld_out;
   void* outT_hi; void* outT_lo; int64_t ld_outT;
   float* out_col; int64_t col_index; int64_t col_slab_stride;
+  const float* bias;  /* optional fp32 [N] added to the accumulator before act (nn.Linear bias in fp32) */
 } dlrm_gemm_tc_desc_t;
 
 int dlrm_b200_gemm_tc_plan_create(const dlrm_gemm_tc_desc_t* desc /*[host]*/, void** plan);
@@ -329,6 +331,10 @@ int dlrm_b200_gemm_chain_create(void* const* plans /*[host][n]*/, const int* dep
                                 const int* dep_on_k /*[host][n]*/, int n, int32_t* counters,
                                 int64_t counters_len, void** chain);
 int dlrm_b200_gemm_chain_info(void* chain, int* tasks, int* ctas, int* stages, int* smem_bytes);
+/* Optional per-task timeline for tools/chain_timeline.py: trace = device uint64[8 * tasks] (globaltimer ns: task
+ * claimed, dependencies ready, last TMA issued, first operands landed, last MMA issued, accumulator ready,
+ * epilogue + signal done; word 7 = SM id), or NULL to switch it off (default). */
+int dlrm_b200_gemm_chain_set_trace(void* chain, uint64_t* trace);
 int dlrm_b200_gemm_chain_run(void* chain, void* stream);
 int dlrm_b200_gemm_chain_destroy(void* chain);
 

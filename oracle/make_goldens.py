@@ -23,16 +23,23 @@ import torch
 REF = os.environ.get("DLRM_REFERENCE", "/root/reference")
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
-sys.path.insert(0, REF)
+# the repo root holds its own dlrm_s_pytorch.py (the drop-in CLI shim): the REFERENCE must come first
 sys.path.insert(0, ROOT)
+sys.path.insert(0, REF)
+for _m in ("dlrm_s_pytorch", "dlrm_data_pytorch"):
+    sys.modules.pop(_m, None)          # never reuse an already-imported shim
 _print = print  # extend_distributed overrides builtins.print on import
 
 import dlrm_data_pytorch as dp  # noqa: E402
 import dlrm_s_pytorch as R  # noqa: E402
 
+assert os.path.realpath(os.path.dirname(R.__file__)) == os.path.realpath(REF), \
+    "dlrm_s_pytorch resolved to %s, not to the reference" % R.__file__
+assert hasattr(R, "DLRM_Net")
+
 from oracle import dlrm_numpy as O  # noqa: E402
 
-OUT = os.path.join(ROOT, "tests", "golden")
+OUT = os.environ.get("DLRM_GOLDEN_OUT", os.path.join(ROOT, "tests", "golden"))
 
 
 def build_ref(m_spa, ln_emb, ln_bot, ln_top, params, loss, itself=False, thr=0.0, op="dot",
@@ -203,10 +210,24 @@ def embbag_order_check():
     _print("EmbeddingBag(sum) == sequential fp32 order: bit-exact (D=2,16,64,128)")
 
 
-def main():
+def main(only=None):
+    """only: iterable of fixture names to (re)generate (default: all)."""
     os.makedirs(OUT, exist_ok=True)
     torch.manual_seed(0)
     embbag_order_check()
+    global case
+    _case = case
+
+    def case(name, *a, **kw):  # noqa: F811
+        if only is None or name in only:
+            _case(name, *a, **kw)
+    try:
+        _main_cases(case)
+    finally:
+        case = _case
+
+
+def _main_cases(case):
     # reference's own test arch (dlrm_s_pytorch.py:908-914 defaults; test/dlrm_s_test.sh)
     case("tiny_default", 2, [4, 3, 2], [4, 3, 2], [4, 2, 1], B=5, lmax=3, loss="mse", seed=11)
     # CFG0 (BASELINE.json configs[0])
@@ -224,4 +245,4 @@ def main():
 
 
 if __name__ == "__main__":
-    main()
+    main(only=set(sys.argv[1:]) or None)

@@ -31,11 +31,12 @@ def pad_cols(t: torch.Tensor, mult=8):
     return out
 
 
-def run_case(M, N, K, x3, a_mn, b_mn, tile_n=0, split_k=1, act=0, mask=0, outs="f32", seed=0):
+def run_case(M, N, K, x3, a_mn, b_mn, tile_n=0, split_k=1, act=0, mask=0, outs="f32", seed=0, bias=0, ldf_exact=0):
     """Returns (name, max_rel_err, tolerance, ok, detail)."""
     from dlrm_b200 import _lib
 
-    name = f"M{M} N{N} K{K} x3={x3} a_mn={a_mn} b_mn={b_mn} tn={tile_n} sk={split_k} act={act} mask={mask} {outs}"
+    name = (f"M{M} N{N} K{K} x3={x3} a_mn={a_mn} b_mn={b_mn} tn={tile_n} sk={split_k} act={act} mask={mask} {outs}"
+            + (" bias" if bias else "") + (" ldf=N" if ldf_exact else ""))
     g = torch.Generator(device="cpu").manual_seed(seed)
     A = torch.randn(M, K, generator=g)
     B = torch.randn(N, K, generator=g)
@@ -59,7 +60,14 @@ def run_case(M, N, K, x3, a_mn, b_mn, tile_n=0, split_k=1, act=0, mask=0, outs="
     else:
         ref = Ah.double() @ Bh.double().t()
         ref3 = ref
+    bvec = None
+    if bias:
+        bvec = torch.randn(N, generator=g)
+        ref, ref3 = ref + bvec.double()[None, :], ref3 + bvec.double()[None, :]
+        dbias = bvec.to(DEV)
     scale = (A.double().abs() @ B.double().abs().t()).clamp_min(1e-30)
+    if bias:
+        scale = scale + bvec.double().abs()[None, :]
     ymask = None
     if mask:
         ymask = torch.rand(M, N, generator=g) - 0.3 if mask == 1 else torch.rand(M, N, generator=g)
@@ -72,8 +80,10 @@ def run_case(M, N, K, x3, a_mn, b_mn, tile_n=0, split_k=1, act=0, mask=0, outs="
               M=M, N=N, K=K, mode_x3=x3, split_k=split_k, tile_n=tile_n, act=act, mask_act=mask)
     if mask:
         kw.update(mask_hi=dmh.data_ptr(), mask_lo=dml.data_ptr(), ldmask=dmh.stride(0))
+    if bias:
+        kw.update(bias=dbias.data_ptr())
     nslab = max(split_k, 1)
-    ldf = (N + 3) // 4 * 4
+    ldf = N if ldf_exact else (N + 3) // 4 * 4
     of32 = torch.full((nslab, M, ldf), float("nan"), device=DEV)
     ocol = torch.full((nslab, M), float("nan"), device=DEV)
     ldo = (N + 7) // 8 * 8
@@ -173,6 +183,16 @@ def all_cases():
         ]
     for tn in (32, 64, 128):
         cases.append(dict(M=384, N=256, K=1024, x3=1, a_mn=0, b_mn=0, tile_n=tn, outs="f32"))
+    # epilogue paths: fp32 bias, ragged rows / columns, fp32 rows that are not 16-byte aligned
+    cases += [
+        dict(M=2048, N=512, K=13, x3=1, a_mn=0, b_mn=0, act=1, outs="f32 bf", bias=1),
+        dict(M=300, N=96, K=134, x3=1, a_mn=0, b_mn=0, act=1, outs="f32 bf", bias=1),
+        dict(M=2048, N=256, K=512, x3=1, a_mn=0, b_mn=0, act=2, outs="f32 bf", bias=1),
+        dict(M=77, N=479, K=192, x3=1, a_mn=0, b_mn=1, outs="f32", ldf_exact=1),
+        dict(M=1024, N=480, K=2048, x3=1, a_mn=1, b_mn=1, split_k=4, outs="f32 col", ldf_exact=1),
+        dict(M=130, N=70, K=64, x3=1, a_mn=0, b_mn=1, mask=1, outs="f32 bf T"),
+        dict(M=130, N=70, K=64, x3=0, a_mn=0, b_mn=1, mask=2, outs="bf"),
+    ]
     return cases
 
 

@@ -143,3 +143,43 @@ def test_cli_loss_curve_matches_reference_cli(tag, gemm):
     got = [float(m.group(1)) for m in re.finditer(r"Finished training it \d+/6 of epoch 0, .* loss ([0-9.]+)", r.stdout)]
     assert len(got) == 6, r.stdout
     np.testing.assert_allclose(got, want, rtol=0, atol=2e-5)
+
+
+def test_eval_forward_with_grad_enabled_between_training_steps():
+    """The reference's inference() loop runs the model WITHOUT no_grad (dlrm_s_pytorch.py:759-899).  A
+    grad-enabled forward on another batch that is never followed by step() must not disturb the next
+    training step (round-1 advisor finding: stale per-row list heads)."""
+    from dlrm_b200 import optim as fused
+
+    g = Golden("cfg0")
+    net = _net(g, "tc")
+    opt = fused.RWSAdagrad(net.parameters(), lr=float(g["rwsadagrad_lr"]))
+    losses = []
+    for s in range(g.nsteps):
+        Xe, oe, ie, Te = _batch(g, g.nsteps)            # "evaluation" batch, grad enabled, no step
+        _ = net(Xe, oe, ie)
+        _ = net(Xe, oe, ie)
+        X, lS_o, lS_i, T = _batch(g, s)
+        E = net.loss_fn(net(X, lS_o, lS_i), T.to(DEV))
+        losses.append(float(E.item()))
+        opt.zero_grad()
+        E.backward()
+        opt.step()
+    np.testing.assert_allclose(losses, g["rwsadagrad_losses"], rtol=0, atol=3e-4)
+    assert int(net._engine.head.abs().sum().item()) == 0     # list heads are clean between steps
+    for k in range(g.T):
+        np.testing.assert_allclose(net._engine.momentum[int(net._engine.row_base[k]):int(net._engine.row_base[k + 1])]
+                                   .cpu().numpy(), g[f"rwsadagrad_mom{k}"], rtol=2e-3, atol=1e-7)
+
+
+def test_gradient_accumulation_fails_loudly():
+    from dlrm_b200 import optim as fused
+
+    g = Golden("cfg0")
+    net = _net(g, "tc")
+    opt = fused.SGD(net.parameters(), lr=0.1)
+    X, lS_o, lS_i, T = _batch(g, 0)
+    opt.zero_grad()
+    net.loss_fn(net(X, lS_o, lS_i), T.to(DEV)).backward()
+    with pytest.raises(RuntimeError, match="accumulation"):
+        net.loss_fn(net(X, lS_o, lS_i), T.to(DEV)).backward()
