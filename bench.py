@@ -1,26 +1,34 @@
 #!/usr/bin/env python
-"""bench.py -- samples/s of the DLRM fwd+bwd+optimizer hot path on N B200s (contract in the task
-statement).  One "step" = one pass of the hot path (forward, loss, backward, fused row-wise-Adagrad
-embedding update, dense update) over one synthetic batch.
+"""bench.py -- samples/s of the DLRM fwd+bwd+optimizer hot path on N B200s (contract in the task statement).
+One "step" = one pass of the hot path (index exchange, forward, loss, backward, fused row-wise-Adagrad embedding
+update, dense update) over one synthetic batch.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload cfg2|cfg1]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload cfg3|cfg2|cfg1]
 
-Workload at N=1: BASELINE.json configs[2] ("cfg2": 26 tables x 1e6 rows x dim 128, bot 13-512-256-128,
-top 479-1024-512-256-1, batch 2048, --data-generation=random distribution, fwd+bwd+RWSAdagrad);
-`--workload cfg1` times the forward only (configs[1]).  N>1: the same model with tables sharded
-table-wise, per-GPU batch fixed at 2048 (weak scaling).
+Workloads (BASELINE.json configs)
+  cfg3 (default, every N): MLPerf-DLRM synthetic -- the config the headline metric is quoted on: 26 tables of the
+        Criteo-Terabyte sizes (204 M rows x dim 128 = 104.5 GB fp32, fits one B200), multi-hot bags of fixed length
+        L_k (214 lookups per sample), bot 13-512-256-128, top 479-1024-1024-512-256-1, batch 8192 PER GPU (global
+        65536 at 8 GPUs: weak scaling), fwd+bwd+RWSAdagrad.  Tables are placed by dlrm_b200/placement.py
+        (cost-balanced, the L=100 / L=27 tables row-split over all ranks).
+  cfg2: 26 x 1e6 x 128 tables, random bags of <= 10 indices, bot 13-512-256-128, top 479-1024-512-256-1, batch
+        2048 per GPU (round 1's headline);  cfg1: cfg2's model, forward only.
 
-Timing hygiene: a ring of >= 16 distinct pre-generated batches (their touched rows, 138 MB per batch,
-exceed the 126 MB L2 many times over) -> "inputs larger than L2"; CUDA events on the launching
-stream; max over ranks; nvidia-smi clocks sampled during the timed region.
+Every N (1 included) runs the same sharded engine (one process per GPU; N = 1 is a 1-rank group).  Timing:
+a ring of >= 8 distinct pre-generated batches (their touched rows exceed the 126 MB L2 many times over: "inputs
+larger than L2"); CUDA events on the launching stream; max over ranks; nvidia-smi clocks sampled during the
+timed region.  `value`: the packed batches already sit in HBM.  `e2e`: packed pinned host batches -> one H2D
+copy per step (copy stream, double-buffered) -> step -> loss D2H.
 """
 import argparse
 import json
 import os
+import socket
 import subprocess
 import sys
 import threading
 import time
+import types
 
 import numpy as np
 import torch
@@ -28,15 +36,30 @@ import torch
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-CFG = dict(m_spa=128, rows=1_000_000, T=26, ln_bot=[13, 512, 256, 128], top_tail=[1024, 512, 256, 1],
-           B=2048, lmax=10)
+CFG2 = dict(m_spa=128, rows=[1_000_000] * 26, ln_bot=[13, 512, 256, 128], top_tail=[1024, 512, 256, 1], B=2048,
+            lmax=10, hot=None)
 
 
-def model_dims(T=CFG["T"]):
-    D = CFG["m_spa"]
-    ln_emb = [CFG["rows"]] * T
-    ln_top = [D + (T + 1) * T // 2] + CFG["top_tail"]
-    return D, ln_emb, CFG["ln_bot"], ln_top
+def workload(name):
+    from dlrm_b200 import mlperf as M
+
+    if name == "cfg3":
+        return dict(m_spa=M.DIM, rows=list(M.TABLE_ROWS), ln_bot=list(M.LN_BOT), top_tail=list(M.TOP_TAIL), B=8192,
+                    lmax=None, hot=list(M.MULTI_HOT))
+    return dict(CFG2)
+
+
+def model_dims(W):
+    D, T = W["m_spa"], len(W["rows"])
+    return D, W["rows"], W["ln_bot"], [D + (T + 1) * T // 2] + W["top_tail"]
+
+
+def lookups_per_sample(W):
+    """Expected embedding rows read per sample and table (the placement cost)."""
+    if W["hot"] is not None:
+        return [float(h) for h in W["hot"]]
+    # round(max(1, u*min(R, lmax))) draws, de-duplicated: ~5.05 at R = 1e6, lmax = 10 (SURVEY 8d)
+    return [5.05 if r >= 1000 else min(float(r), 5.0) for r in W["rows"]]
 
 
 # ------------------------------------------------------------------------------ clocks
@@ -90,71 +113,86 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
-# ------------------------------------------------------------------------------ CPU baseline
-def cpu_baseline(train=True, budget_s=20.0, threads=None):
-    """The torch-CPU port of the oracle (same ATen ops as the reference's CPU path), timed on the
-    host cores on a bounded sample of the same workload."""
+# ------------------------------------------------------------------------------ CPU arm
+def cpu_arm(args, W, budget_s=20.0, threads=None):
+    """The reference's CPU implementation of the path on the host cores, on a bounded sample of the workload:
+    the UNMODIFIED reference (oracle/_ref, vendored by build(); kind "reference") when present, else its torch-CPU
+    port (oracle/torch_cpu_port.py; kind "port").  Tables larger than `cap` rows are capped (host RAM / init time);
+    the bag structure, the MLPs and the optimizer are the workload's."""
+    from oracle import live_reference as LR
     from oracle.torch_cpu_port import CpuDLRM, RowWiseAdagradCPU, time_cpu_steps
+    from dlrm_b200 import mlperf as M
     from dlrm_b200.data import make_batch
+
+    train = args.workload != "cfg1"
+    D, rows, ln_bot, ln_top = model_dims(W)
+    cap = 1_000_000
+    rows_c = [min(int(r), cap) for r in rows]
+    Bc = 2048
+    R, where = LR.load()
+    kind = "reference" if R is not None else "port"
+    if R is not None:
+        model, opt = LR.build_model(R, D, rows_c, ln_bot, ln_top, "bce")
+    else:
+        model = CpuDLRM(D, rows_c, ln_bot, ln_top, loss="bce")
+        opt = RowWiseAdagradCPU(model.parameters(), lr=0.01)
+    batches = []
+    for s in range(4):
+        if W["hot"] is not None:
+            idx = M.multi_hot_batch(99, s, rows_c, W["hot"], 0, Bc, dtype=np.int64)
+            X, T = M.dense_and_targets(99, s, 0, Bc)
+            lS_i = [torch.from_numpy(a.reshape(-1)) for a in idx]
+            lS_o = [torch.arange(Bc, dtype=torch.int64) * int(h) for h in W["hot"]]
+            batches.append((torch.from_numpy(X), lS_o, lS_i, torch.from_numpy(T)))
+        else:
+            hb = make_batch(np.random.default_rng(99 + s), rows_c, Bc, 13, W["lmax"], pin=False)
+            X, lS_o, lS_i, T = hb.reference_format()
+            batches.append((X, [o for o in lS_o], lS_i, T))
+    if R is not None:      # the reference stacks the offsets (collate_wrapper_random_offset)
+        batches = [(X, torch.stack(list(o)), i, T) for X, o, i, T in batches]
+
+    def run(n):
+        return time_cpu_steps(model, opt, batches, n, train)
 
     if threads:
         torch.set_num_threads(threads)
-    D, ln_emb, ln_bot, ln_top = model_dims()
-    rows = CFG["rows"]
-    note = ""
-    try:
-        model = CpuDLRM(D, ln_emb, ln_bot, ln_top, loss="bce")
-    except (RuntimeError, MemoryError):  # host RAM too small for 13.3 GB of tables
-        rows = 100_000
-        ln_emb = [rows] * CFG["T"]
-        model = CpuDLRM(D, ln_emb, ln_bot, ln_top, loss="bce")
-        note = " (rows capped at 1e5: host RAM)"
-    opt = RowWiseAdagradCPU(model.parameters(), lr=0.01)
-    rng = np.random.default_rng(99)
-    batches = [make_batch(rng, ln_emb, CFG["B"], 13, CFG["lmax"], pin=False).reference_format()
-               for _ in range(4)]
-    batches = [(X, [o for o in lS_o], lS_i, T) for X, lS_o, lS_i, T in batches]
-    time_cpu_steps(model, opt, batches, 2, train)  # warm-up
-    # "all the host threads it can use": torch's default is one thread per core, which is NOT the
-    # fastest setting for this sparse, sync-heavy path -- probe a few counts and keep the best.
+    run(2)  # warm-up
+    # "all the host threads it can use": one thread per core is NOT the fastest setting for this sparse,
+    # sync-heavy path -- probe a few counts and keep the best
     ncpu = os.cpu_count() or 1
-    best = (None, float("inf"))
+    best = (torch.get_num_threads(), float("inf"))
     if not threads:
         for th in sorted({t for t in (8, 16, 32, 64, ncpu) if t <= ncpu}):
             torch.set_num_threads(th)
-            time_cpu_steps(model, opt, batches, 1, train)
-            tt = time_cpu_steps(model, opt, batches, 2, train) / 2
+            run(1)
+            tt = run(2) / 2
             if tt < best[1]:
                 best = (th, tt)
         torch.set_num_threads(best[0])
     cores = torch.get_num_threads()
-    t1 = time_cpu_steps(model, opt, batches, 3, train) / 3
-    n = int(max(5, min(200, budget_s / max(t1, 1e-4))))
-    dt = time_cpu_steps(model, opt, batches, n, train)
-    sps = n * CFG["B"] / dt
-    return {"value": sps, "unit": "samples/s", "cores": cores, "kind": "port",
-            "sample": "%d steps of batch %d, %s, 26x%dx128 tables%s, torch %s CPU, %d threads "
-                      "(best of 8/16/32/64/all on a %d-cpu host)" % (
-                n, CFG["B"], "fwd+bwd+RWSAdagrad" if train else "fwd only", rows, note,
-                torch.__version__, cores, ncpu),
+    t1 = run(2) / 2
+    n = int(max(3, min(200, budget_s / max(t1, 1e-4))))
+    dt = run(n)
+    return {"value": n * Bc / dt, "unit": "samples/s", "cores": cores, "kind": kind,
+            "sample": "%d steps of batch %d (%s), %s, tables capped at %d rows (host RAM / init time), %s, torch %s "
+                      "CPU, %d threads (best of 8/16/32/64/all on a %d-cpu host)" % (
+                          n, Bc, args.workload, "fwd+bwd+RWSAdagrad" if train else "fwd only", cap,
+                          "unmodified reference dlrm_s_pytorch.DLRM_Net + optim/rwsadagrad.py" if R is not None
+                          else "torch-CPU port of the reference path", torch.__version__, cores, ncpu),
             "ms_per_step": 1e3 * dt / n}
 
 
-def reference_arm(args):
-    """`--impl reference`: the reference's CPU implementation of the path (its torch-CPU port: the
-    Python reference cannot travel to the GPU box), all host threads, same config/metric."""
+def reference_arm(args, W):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     train = args.workload != "cfg1"
-    per_step_budget = 1.0
-    cb = cpu_baseline(train, budget_s=max(5.0, per_step_budget * (args.steps + args.warmup)))
+    cb = cpu_arm(args, W, budget_s=max(5.0, min(120.0, 1.0 * (args.steps + args.warmup))))
     line = {
         "impl": "reference", "metric": metric_name(train), "value": cb["value"], "unit": "samples/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": cb["ms_per_step"],
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "fp32",
-        "data": "synthetic", "config": config_dict(args, 1),
-        "cpu_baseline": cb,
+        "data": "synthetic", "config": config_dict(args, W, 1), "cpu_baseline": cb,
         "e2e": {"value": cb["value"], "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line))
@@ -164,138 +202,238 @@ def metric_name(train):
     return "samples/sec (fwd+bwd) MLPerf-DLRM synthetic" if train else "samples/sec (fwd) MLPerf-DLRM synthetic"
 
 
-def config_dict(args, n):
-    return {"workload": "cfg2: 26x1e6x128 tables, bot 13-512-256-128, top 479-1024-512-256-1, "
-                        "batch 2048/GPU, random data Lmax=10, fwd+bwd+RWSAdagrad" if args.workload != "cfg1"
-            else "cfg1: same model, forward only",
-            "global_batch": CFG["B"] * n, "parallelism": "table-wise x%d + dp%d" % (n, n) if n > 1 else "single",
-            "l2_policy": "ring of %d distinct batches (inputs larger than L2)" % args.ring,
-            "gemm": args.gemm}
+def config_dict(args, W, n):
+    desc = {"cfg3": "cfg3: MLPerf-DLRM synthetic, 26 Criteo-Terabyte-sized tables (204.18 M rows x 128, 104.5 GB fp32), "
+                    "multi-hot L_k sum 214, bot 13-512-256-128, top 479-1024-1024-512-256-1, batch 8192/GPU, "
+                    "fwd+bwd+RWSAdagrad",
+            "cfg2": "cfg2: 26x1e6x128 tables, bot 13-512-256-128, top 479-1024-512-256-1, batch 2048/GPU, random data "
+                    "Lmax=10, fwd+bwd+RWSAdagrad",
+            "cfg1": "cfg1: cfg2's model, forward only"}[args.workload]
+    return {"workload": desc, "global_batch": W["B"] * n,
+            "parallelism": ("placement.plan (cost-balanced table-wise + row-split) x%d + dp%d" % (n, n)) if n > 1 else "single",
+            "l2_policy": "ring of %d distinct batches (inputs larger than L2)" % args.ring, "gemm": args.gemm}
 
 
 # ------------------------------------------------------------------------------ our arm
-def bytes_fwd_gather(nnz, T, B, D):
-    """rows read + indices + offsets + pooled output written."""
-    return nnz * D * 4 + nnz * 8 + T * B * 8 + T * B * D * 4
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
 
 
-def ours(args):
-    from dlrm_b200.data import DeviceBatch, make_batch
-    from dlrm_b200.engine import Engine, GraphedTrainStep
+def parity_check(de_cls, dev, gemm):
+    """Two RWSAdagrad steps of tests/golden/cfg0.npz (recorded from the LIVE reference, single process, whole
+    batch) through the SAME sharded engine, placement policy and exchange as the timed run: max errors of the loss
+    curve, the logits after the steps, the touched table rows and the row-wise accumulators.  The batch (128) is
+    split over the ranks; 3 tables on N ranks forces row-split shards for N > 2."""
+    import torch.distributed as dist
+    from dlrm_b200 import placement as P, sharding as S
+    from dlrm_b200.engine import sparse_from_reference
 
-    n = args.gpus
-    if n > 1:
-        from dlrm_b200 import dist as ddist
+    z = np.load(os.path.join(ROOT, "tests", "golden", "cfg0.npz"))
+    rank, world = dist.get_rank(), dist.get_world_size()
+    D, ln_emb = int(z["m_spa"]), [int(v) for v in z["ln_emb"]]
+    ln_bot, ln_top = [int(v) for v in z["ln_bot"]], [int(v) for v in z["ln_top"]]
+    Bg, T = int(z["B"]), len(ln_emb)
+    B = Bg // world
+    pl = P.plan(ln_emb, [5.0] * T, world, force_split=[0] if world <= 2 else [])
+    de = de_cls(D, ln_emb, ln_bot, ln_top, local_batch=B, device=dev, gemm=gemm, exchange="p2p", placement=pl,
+                loss=str(z["loss"]))
+    params = dict(emb=[z["emb%d" % k] for k in range(T)],
+                  bot=[(z["botW%d" % i], z["botb%d" % i]) for i in range(len(ln_bot) - 1)],
+                  top=[(z["topW%d" % i], z["topb%d" % i]) for i in range(len(ln_top) - 1)], v_W_l=None)
+    de.eng.load_params(S.slice_params(params, pl, rank))
+    lr = float(z["rwsadagrad_lr"])
+    nsteps = int(z["nsteps"])
+    sl = slice(rank * B, (rank + 1) * B)
+    losses = []
 
-        return ddist.bench_main(args, CFG, metric_name, config_dict, ClockSampler)
-    torch.cuda.set_device(0)
-    dev = "cuda:0"
+    def batch(s):
+        per_table = [(torch.from_numpy(z["b%d_off" % s][k]), torch.from_numpy(z["b%d_idx%d" % (s, k)])) for k in range(T)]
+        st = S.local_streams(per_table, pl, rank)
+        sp = sparse_from_reference([o for o, _ in st], [i for _, i in st], dev)
+        X = torch.from_numpy(z["b%d_X" % s][sl].copy()).to(dev)
+        Tt = torch.from_numpy(z["b%d_T" % s][sl].copy()).to(dev)
+        return X, sp, Tt
+
+    for s in range(nsteps):
+        X, sp, Tt = batch(s)
+        l = de.train_step(X, sp, Tt, lr, "rwsadagrad").clone()
+        if world > 1:
+            dist.all_reduce(l, op=dist.ReduceOp.AVG)
+        losses.append(float(l.item()))
+    X, sp, Tt = batch(nsteps)
+    p = de.forward(X, sp).cpu().numpy()
+    err = {"loss": float(np.abs(np.array(losses) - z["rwsadagrad_losses"]).max()),
+           "p_after": float(np.abs(p - z["rwsadagrad_p_after"][sl]).max()), "rows_p999": 0.0, "momentum": 0.0}
+    for j, s_ in enumerate(pl.of_rank(rank)):
+        k = s_.table
+        rows, vals = z["rwsadagrad_emb%d_rows" % k], z["rwsadagrad_emb%d_vals" % k]
+        m = (rows >= s_.row_lo) & (rows < s_.row_hi)
+        if m.any():
+            got = de.eng.table(j).cpu().numpy()[rows[m] - s_.row_lo]
+            err["rows_p999"] = max(err["rows_p999"], float(np.quantile(np.abs(got - vals[m]), 0.999)))
+        mom = de.eng.momentum[int(de.eng.row_base[j]):int(de.eng.row_base[j + 1])].cpu().numpy()
+        ref = z["rwsadagrad_mom%d" % k][s_.row_lo:s_.row_hi]
+        err["momentum"] = max(err["momentum"], float(np.abs(mom - ref).max() / max(float(np.abs(ref).max()), 1e-30)))
+    t = torch.tensor([err["loss"], err["p_after"], err["rows_p999"], err["momentum"]], device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    err = dict(zip(("loss", "p_after", "rows_p999", "momentum_rel"), [float(v) for v in t.tolist()]))
+    err.update(golden="tests/golden/cfg0.npz (live reference, 2 RWSAdagrad steps, global batch 128)",
+               split_tables=pl.split_tables(), ok=bool(err["loss"] < 1e-4 and err["p_after"] < 1e-3))
+    return err      # the (tiny) engine stays alive: its buffers are mapped into the peers
+
+
+def ours(args, W):
+    import torch.distributed as dist
+    from dlrm_b200 import dist as ddist, placement as P
+    from dlrm_b200.data import DeviceBatch
+    from dlrm_b200.engine import GraphedTrainStep
+
+    if "RANK" not in os.environ:       # N = 1 without a launcher: a 1-rank group
+        os.environ.update(RANK="0", WORLD_SIZE="1", LOCAL_RANK="0", MASTER_ADDR="127.0.0.1",
+                          MASTER_PORT=str(_free_port()))
+    rank, world = ddist.init_distributed("nccl")
+    local = int(os.environ.get("LOCAL_RANK", str(rank)))
+    dev = "cuda:%d" % local
+    torch.cuda.set_device(local)
     train = args.workload != "cfg1"
-    D, ln_emb, ln_bot, ln_top = model_dims()
-    B, T = CFG["B"], CFG["T"]
-    eng = Engine(D, ln_emb, ln_bot, ln_top, loss="bce", sigmoid_top=len(ln_top) - 2, device=dev,
-                 max_batch=B, gemm=args.gemm)
-    eng.init_params(0)
-    eng.ensure_optimizer_state("rwsadagrad")
-    rng = np.random.default_rng(1234)
-    host = [make_batch(rng, ln_emb, B, 13, CFG["lmax"]) for _ in range(args.ring)]
-    devb = []
-    for hb in host:
-        db = DeviceBatch(hb.layout, dev)
-        db.load(hb, non_blocking=False)
-        devb.append(db)
-    torch.cuda.synchronize()
+    D, rows, ln_bot, ln_top = model_dims(W)
+    B, T = W["B"], len(rows)
+    cost = lookups_per_sample(W)
+    check = None
+    if not args.no_check and train:
+        check = parity_check(ddist.DistEngine, dev, args.gemm)
+    pl = P.plan(rows, cost, world)
+    de = ddist.DistEngine(D, rows, ln_bot, ln_top, local_batch=B, device=dev, gemm=args.gemm, exchange="p2p",
+                          placement=pl)
+    de.eng.init_params(100 + rank)
+    if world > 1:
+        de.sync_dense_params_from_rank0()
+    de.eng.ensure_optimizer_state("rwsadagrad")
     lr = 0.01
-    # K consecutive steps per CUDA graph (the embedding update of step j overlaps the bottom MLP of step
-    # j+1 on a side stream); two sets of K static staging buffers so the H2D of the next K batches can
-    # run while the current graph executes.
-    Kp = 1
-    if train and not args.no_pipeline:
-        if args.pipeline >= 1 and args.steps % args.pipeline == 0:
-            Kp = args.pipeline
-    sets = [[DeviceBatch(host[0].layout, dev) for _ in range(Kp)] for _ in range(2)]
-    for st_set in sets:
-        for st in st_set:
-            st.load(host[0], non_blocking=False)
-    use_graph = not args.no_graph
-    from dlrm_b200.engine import GraphedTrainSteps
+    nsets = 2
+    fixed = W["hot"] is not None
+    # ---- inputs: a ring of packed pinned host batches (this rank's share) + their device copies
+    if fixed:
+        mh = ddist.MultiHotExchange(de, W["hot"], 13, nsets)
+        host = [mh.fill_host(mh.host_buffer(), 1234, i, rows) for i in range(args.ring)]
+        devr = [h.to(dev) for h in host]
+        stages = [types.SimpleNamespace(sparse=mh.sparse[k], X=mh.X[k], target=mh.target[k]) for k in range(nsets)]
 
+        def pre(k):
+            return lambda: mh.exchange(k)
+
+        def load_dev(k, i):
+            mh.stage[k].copy_(devr[i % args.ring], non_blocking=True)
+
+        def load_host(k, i):
+            return mh.upload(k, host[i % args.ring])
+    else:
+        hostb = [ddist.make_sharded_batch(1000 + i, rows, rank, world, B, 13, W["lmax"], placement=pl)
+                 for i in range(args.ring)]
+        devb = []
+        for hb, X, Tt in hostb:
+            db = DeviceBatch(hb.layout, dev)
+            db.load(hb, non_blocking=False)
+            devb.append((db, X.to(dev), Tt.to(dev)))
+        sdb = [DeviceBatch(hostb[0][0].layout, dev) for _ in range(nsets)]
+        for s_ in sdb:
+            s_.load(hostb[0][0], non_blocking=False)
+        stages = [types.SimpleNamespace(sparse=sdb[k].sparse, X=devb[0][1].clone(), target=devb[0][2].clone())
+                  for k in range(nsets)]
+
+        def pre(k):
+            return None
+
+        def load_dev(k, i):
+            db, Xd, Td = devb[i % args.ring]
+            n = db.layout.used(db.nnz)
+            sdb[k].buf[:n].copy_(db.buf[:n], non_blocking=True)
+            stages[k].X.copy_(Xd, non_blocking=True)
+            stages[k].target.copy_(Td, non_blocking=True)
+
+        def load_host(k, i):
+            hb, Xh, Th = hostb[i % args.ring]
+            n = sdb[k].load(hb)
+            stages[k].X.copy_(Xh, non_blocking=True)
+            stages[k].target.copy_(Th, non_blocking=True)
+            return n + Xh.numel() * 4 + Th.numel() * 4
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
     graphs = None
-    if use_graph:
-        if train:
-            graphs = [GraphedTrainSteps(eng, st_set, lr, "rwsadagrad") for st_set in sets]
-        else:
-            graphs = [GraphedTrainStep(eng, st_set[0], lr, "rwsadagrad", train=False) for st_set in sets]
+    if not args.no_graph:
+        graphs = [GraphedTrainStep(de.eng, stages[k], lr, "rwsadagrad", train=train, pre=pre(k)) for k in range(nsets)]
 
-    def run_set(si):
-        """Kp steps on the batches currently in staging set si; returns a tensor holding a loss / output."""
+    def run_set(k):
         if graphs is not None:
-            return graphs[si].replay()
-        out = None
-        for j, st in enumerate(sets[si]):
-            if train:
-                out = eng.train_step(st.X, st.sparse, st.target, lr, "rwsadagrad", join_update=(j == Kp - 1))
-            else:
-                out = eng.forward(st.X, st.sparse)
-        return out
+            return graphs[k].replay()
+        p = pre(k)
+        if p is not None:
+            p()
+        if train:
+            return de.eng.train_step(stages[k].X, stages[k].sparse, stages[k].target, lr, "rwsadagrad")
+        return de.eng.forward(stages[k].X, stages[k].sparse)
 
-    def resident_round(i):
-        # inputs already resident in HBM: device-to-device copies of the packed batches into the
-        # graph's static buffers (2.7 MB each), then Kp steps
-        for j, st in enumerate(sets[0]):
-            src = devb[(i * Kp + j) % args.ring]
-            nbytes = src.layout.used(src.nnz)
-            st.buf[:nbytes].copy_(src.buf[:nbytes], non_blocking=True)
-        run_set(0)
+    def sync_all():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
 
-    rounds, wrounds = args.steps // Kp, max((args.warmup + Kp - 1) // Kp, 1)
-    for w in range(wrounds):
-        resident_round(w)
-    torch.cuda.synchronize()
-    sampler = ClockSampler(0)
-    sampler.start()
-    time.sleep(0.25)
+    def resident_step(i):
+        k = i % nsets
+        load_dev(k, i)
+        return run_set(k)
+
+    for w in range(args.warmup):
+        resident_step(w)
+    sync_all()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.25)
+    sync_all()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    torch.cuda.synchronize()
     t0 = time.time()
-    launches0 = eng.n_launch
+    n0 = de.eng.n_launch
     ev0.record()
-    for r in range(rounds):
-        resident_round(wrounds + r)
+    for r in range(args.steps):
+        resident_step(args.warmup + r)
     ev1.record()
-    torch.cuda.synchronize()
+    sync_all()
     t1 = time.time()
-    launches = eng.n_launch - launches0
-    clocks = sampler.stop(t0, t1)
-    ms = ev0.elapsed_time(ev1) / args.steps
-    value = B / (ms * 1e-3)
+    launches = de.eng.n_launch - n0
+    ms = torch.tensor([ev0.elapsed_time(ev1) / args.steps], device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms = float(ms.item())
 
-    # ---- e2e: host buffers; H2D of the packed batches + D2H of the loss inside the timed region
+    # ---- e2e: host buffers; H2D of the packed batch + D2H of the loss inside the timed region
     copy_stream = torch.cuda.Stream()
     loss_host = torch.zeros(1).pin_memory()
     main = torch.cuda.current_stream()
     h2d = 0
 
-    def load_set(si, base):
+    def e2e_loop(nsteps, base):
         nonlocal h2d
-        for j, st in enumerate(sets[si]):
-            h2d += st.load(host[(base + j) % args.ring])
-
-    def e2e_loop(nrounds, base):
-        ready = [torch.cuda.Event(), torch.cuda.Event()]
-        freed = [torch.cuda.Event(), torch.cuda.Event()]
+        ready = [torch.cuda.Event() for _ in range(nsets)]
+        freed = [torch.cuda.Event() for _ in range(nsets)]
         for f in freed:
             f.record(main)
         with torch.cuda.stream(copy_stream):
             copy_stream.wait_event(freed[0])
-            load_set(0, base)
+            h2d += load_host(0, base)
             ready[0].record(copy_stream)
-        for r in range(nrounds):
-            cur, nxt = r & 1, (r + 1) & 1
-            if r + 1 < nrounds:
+        for r in range(nsteps):
+            cur, nxt = r % nsets, (r + 1) % nsets
+            if r + 1 < nsteps:
                 with torch.cuda.stream(copy_stream):
                     copy_stream.wait_event(freed[nxt])
-                    load_set(nxt, base + (r + 1) * Kp)
+                    h2d += load_host(nxt, base + r + 1)
                     ready[nxt].record(copy_stream)
             main.wait_event(ready[cur])
             out = run_set(cur)
@@ -303,136 +441,159 @@ def ours(args):
             freed[cur].record(main)
         main.synchronize()
 
-    e2e_loop(wrounds, 0)
+    e2e_loop(max(args.warmup // 2, 2), 0)
     h2d = 0
-    torch.cuda.synchronize()
+    sync_all()
     ev0.record()
-    e2e_loop(rounds, wrounds * Kp)
+    e2e_loop(args.steps, 5)
     ev1.record()
-    torch.cuda.synchronize()
-    ms_e2e = ev0.elapsed_time(ev1) / args.steps
-    e2e = {"value": B / (ms_e2e * 1e-3), "unit": "samples/s", "h2d_bytes_per_step": int(h2d / args.steps),
-           "d2h_bytes_per_step": 4.0 / Kp, "ms_per_step": ms_e2e,
-           "note": "packed pinned batches -> one cudaMemcpyAsync each on a copy stream (double-buffered sets of "
-                   "%d) -> one CUDA-graph launch per %d steps; loss read back after every launch" % (Kp, Kp)}
+    sync_all()
+    ms2 = torch.tensor([ev0.elapsed_time(ev1) / args.steps], device=dev)
+    if world > 1:
+        dist.all_reduce(ms2, op=dist.ReduceOp.MAX)
+    ms2 = float(ms2.item())
+    # per-rank gather bytes (balance of the placement)
+    gb = torch.tensor([de.gather_bytes_per_step(cost)], device=dev, dtype=torch.float64)
+    gbs = [torch.zeros_like(gb) for _ in range(world)]
+    if world > 1:
+        dist.all_gather(gbs, gb)
+    else:
+        gbs = [gb]
+    gbs = [float(g.item()) for g in gbs]
 
-    # ---- rooflines of the HBM-bound kernels, timed with CUDA events on the launching stream
-    peaks = {}
-    try:
-        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as fh:
-            peaks = json.load(fh)
-    except Exception:
-        pass
-    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
-    peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s"
-    roof = measure_gather_alone(eng, devb, args, hbm_peak, peak_src, T, B, D)
-    roof_upd = measure_update_alone(eng, devb, args, hbm_peak, T, B, D) if train else None
+    roof = roof_upd = cb = None
+    if rank == 0 and world == 1:
+        peaks = {}
+        try:
+            with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as fh:
+                peaks = json.load(fh)
+        except Exception:
+            pass
+        hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+        peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s"
+        roof, roof_upd = measure_rooflines(de, stages, load_dev, pre, args, W, cost, hbm_peak, peak_src, train)
+        if not args.no_cpu:
+            cb = cpu_arm(args, W, budget_s=args.cpu_budget)
+    if rank == 0:
+        clocks = sampler.stop(t0, t1)
+        Bg = B * world
+        line = {
+            "metric": metric_name(train), "value": Bg / (ms * 1e-3), "unit": "samples/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None,
+            "dtype": {"simt": "fp32", "tc": "fp32 (bf16x3 split on tcgen05, fp32 accumulate)", "tc_bf16": "bf16"}[args.gemm],
+            "data": "synthetic", "config": config_dict(args, W, world),
+            "roofline": roof, "roofline_update": roof_upd, "cpu_baseline": cb,
+            "e2e": {"value": Bg / (ms2 * 1e-3), "unit": "samples/s", "h2d_bytes_per_step": int(h2d / args.steps),
+                    "d2h_bytes_per_step": 4, "ms_per_step": ms2,
+                    "note": "per rank: ONE packed pinned buffer with ITS samples (dense, targets, int32 indices of all "
+                            "tables) -> one H2D copy on a copy stream (double-buffered) -> index exchange over NVLink + "
+                            "step in one CUDA graph -> loss read back" if fixed else
+                            "per rank: packed pinned sparse batch (its tables, global batch) + dense slice, H2D every "
+                            "step, loss read back"},
+            "gpu_launches": int(launches), "exchange": "p2p (peer-mapped stores over NVLink, own barriers)",
+            "cuda_graph": graphs is not None,
+            "placement": {"split_tables": pl.split_tables(), "imbalance": pl.imbalance(),
+                          "gather_bytes_per_rank_per_step": gbs,
+                          "gather_bytes_max_over_min": max(gbs) / max(min(gbs), 1.0)},
+            "parity_check": check, "clocks": clocks,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+    dist.destroy_process_group()
 
-    cb = cpu_baseline(train, budget_s=args.cpu_budget) if not args.no_cpu else None
-    line = {
-        "metric": metric_name(train), "value": value, "unit": "samples/s", "n_gpus": 1, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None,
-        "dtype": {"simt": "fp32", "tc": "fp32 (bf16x3 split on tcgen05, fp32 accumulate)", "tc_bf16": "bf16"}[args.gemm],
-        "data": "synthetic", "config": config_dict(args, 1),
-        "roofline": roof, "roofline_update": roof_upd, "cpu_baseline": cb, "e2e": e2e,
-        "gpu_launches": int(launches), "cuda_graph": bool(use_graph), "steps_per_graph": Kp, "clocks": clocks,
-    }
-    print(json.dumps(line))
 
+def measure_rooflines(de, stages, load_dev, pre, args, W, cost, hbm_peak, peak_src, train):
+    """The HBM-bound kernels timed with CUDA events on the launching stream (N = 1): the forward gather alone
+    (back-to-back launches over the batch ring) and, for training, (gather+link, update) pairs."""
+    eng = de.eng
+    D, B, T = eng.D, de.Bg, len(W["rows"])
+    n = max(min(args.steps, 64), 16)
+    k = 0
+    pk = pre(k)
 
-def _time_loop(fn, n, ring):
-    """n back-to-back calls between ONE pair of CUDA events on the launching stream (the launch queue
-    stays full, so host launch gaps are not counted)."""
+    def prep(i):
+        load_dev(k, i)
+        if pk is not None:
+            pk()
+
     for i in range(3):
-        fn(ring[i % len(ring)])
+        prep(i)
+        eng.emb_forward(stages[k].sparse)
     torch.cuda.synchronize()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for i in range(n):
-        fn(ring[i % len(ring)])
-    e1.record()
-    torch.cuda.synchronize()
-    return e0.elapsed_time(e1) * 1e-3 / n
-
-
-def measure_update_alone(eng, devb, args, hbm_peak, T, B, D):
-    """Training-mode gather (+link) and the fused coalesce + row-wise Adagrad update, timed with CUDA
-    events between the launches of back-to-back (gather+link, update) pairs: each kernel is long enough
-    (>= 35 us) to hide the host's launch latency of the next one, so the intervals hold no idle gaps."""
-    FD = eng.F * eng.D
-    out = eng.Tbuf.view(-1)[eng.D:]
-    eng.dT.normal_()
-    eng.head.zero_()
-    n = max(args.steps, 32)
+    # gather alone: the index refresh (D2D + exchange) sits between the timed launches, so bracket each launch
     evs = []
-    for i in range(n + 3):
-        db = devb[i % len(devb)]
-        e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+    for i in range(n):
+        prep(i)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        eng.emb_forward(db.sparse, out, FD, eng.D, link=True)
+        eng.emb_forward(stages[k].sparse)
+        eng.reduce_partials(de.B)
         e1.record()
-        eng.emb_update(db.sparse, eng.dT.view(-1)[eng.D:], FD, eng.D, "rwsadagrad", 1e-6)
-        e2.record()
-        if i >= 3:
-            evs.append((e0, e1, e2))
+        evs.append((e0, e1))
     torch.cuda.synchronize()
-    t_gl = float(np.mean([a.elapsed_time(b) for a, b, _ in evs])) * 1e-3
-    tu = float(np.mean([b.elapsed_time(c) for _, b, c in evs])) * 1e-3
-    nnz = float(np.mean([d.nnz for d in devb]))
-    by_u = nnz * (D * 4 * 2 + 8) + T * B * D * 4 + nnz * 8   # SURVEY 8(d) bytes_bwd
-    ach = by_u / tu / 1e9
-    return {"kernel": "emb_update_kernel (coalesce + row-wise Adagrad, in place)", "bound": "hbm",
-            "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak, "traffic": 337.2e6,
-            "traffic_source": "ncu --set full r4: dram__bytes_read.sum 228.7 MB + dram__bytes_write.sum 108.5 MB "
-                              "per launch (profiles/r1_ncu_full_emb_interact_head.csv)",
-            "avg_launch_us": tu * 1e6, "algorithmic_bytes_per_launch": by_u,
-            "train_gather_plus_link_us": t_gl * 1e6,
-            "how": "CUDA events between the launches of back-to-back (gather+link, update) pairs"}
-
-
-def measure_gather_alone(eng, devb, args, hbm_peak, peak_src, T, B, D):
-    FD = eng.F * eng.D
-    out = eng.Tbuf.view(-1)[eng.D:]
-    n = max(args.steps, 32)
-    tg = _time_loop(lambda db: eng.emb_forward(db.sparse, out, FD, eng.D), n, devb)
-    nnz = float(np.mean([d.nnz for d in devb]))
-    by = bytes_fwd_gather(nnz, T, B, D)
+    tg = float(np.median([a.elapsed_time(b) for a, b in evs])) * 1e-3
+    nnz = float(sum(cost)) * B
+    idx_b = 4 if W["hot"] is not None else 8
+    by = nnz * D * 4 + nnz * idx_b + T * B * idx_b + T * B * D * 4      # SURVEY 8(d): rows + indices + offsets + pooled out
     ach = by / tg / 1e9
-    return {"kernel": "emb_fwd_vec_kernel (multi-table EmbeddingBag gather)", "bound": "hbm", "achieved": ach,
-            "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak, "traffic": 146.2e6,
-            "traffic_source": "ncu --set full r2: dram__bytes_read.sum 139.6 MB + dram__bytes_write.sum 6.6 MB per launch "
-                              "(profiles/r1_ncu_full_emb_interact_head.csv)",
-            "peak_source": peak_src, "avg_launch_us": tg * 1e6, "algorithmic_bytes_per_launch": by,
-            "how": "back-to-back launches over the batch ring, one CUDA-event pair on the launching stream"}
+    roof = {"kernel": "emb_fwd_vec_kernel (multi-table EmbeddingBag gather, forward)", "bound": "hbm", "achieved": ach,
+            "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak, "traffic": None,
+            "traffic_source": "see profiles/ (ncu --set full capture of this round)", "peak_source": peak_src,
+            "avg_launch_us": tg * 1e6, "algorithmic_bytes_per_launch": by,
+            "how": "CUDA events around each gather launch on the launching stream, median of %d over the batch ring" % n}
+    roof_upd = None
+    if train:
+        eng.dT.normal_()
+        eng.head.zero_()
+        evs = []
+        for i in range(n + 3):
+            prep(i)
+            e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+            e0.record()
+            eng.emb_forward(stages[k].sparse, link=True)
+            eng.reduce_partials(de.B)
+            e1.record()
+            eng.emb_update(stages[k].sparse, optimizer="rwsadagrad", lr=1e-6)
+            e2.record()
+            if i >= 3:
+                evs.append((e0, e1, e2))
+        torch.cuda.synchronize()
+        t_gl = float(np.median([a.elapsed_time(b) for a, b, _ in evs])) * 1e-3
+        tu = float(np.median([b.elapsed_time(c) for _, b, c in evs])) * 1e-3
+        by_u = nnz * (D * 4 * 2 + 8) + T * B * D * 4 + nnz * idx_b      # SURVEY 8(d) bytes_bwd (unique rows ~ nnz)
+        achu = by_u / tu / 1e9
+        roof_upd = {"kernel": "emb_update_kernel (+ emb_small_*: coalesce + row-wise Adagrad, in place)", "bound": "hbm",
+                    "achieved": achu, "peak": hbm_peak, "unit": "GB/s", "frac": achu / hbm_peak, "traffic": None,
+                    "avg_launch_us": tu * 1e6, "algorithmic_bytes_per_launch": by_u,
+                    "train_gather_plus_link_us": t_gl * 1e6,
+                    "train_gather": {"achieved": by / t_gl / 1e9, "frac": by / t_gl / 1e9 / hbm_peak},
+                    "how": "CUDA events between the launches of (gather+link, update) pairs, medians"}
+    return roof, roof_upd
 
 
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=200)
-    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="cfg2", choices=["cfg2", "cfg1"])
-    ap.add_argument("--ring", type=int, default=16)
-    ap.add_argument("--gemm", default="tc", choices=["tc", "tc_bf16", "simt"])
+    ap.add_argument("--workload", default="cfg3", choices=["cfg3", "cfg2", "cfg1"])
+    ap.add_argument("--ring", type=int, default=8)
+    ap.add_argument("--gemm", default="tc", choices=["tc", "tc_bf16"])
     ap.add_argument("--no-graph", action="store_true")
-    ap.add_argument("--pipeline", type=int, default=1,
-                    help="training steps per CUDA graph (cross-step overlap of the embedding update; measured "
-                         "neutral at CFG2 -- the step is bound by the sum of kernel work, not by its critical path)")
-    ap.add_argument("--no-pipeline", action="store_true")
-    ap.add_argument("--exchange", default="auto", choices=["auto", "p2p", "nccl"],
-                    help="N>1: pooled-vector / gradient exchange fused into the kernels over NVLink peer memory (p2p), or "
-                         "NCCL all-to-all; auto = p2p when every GPU pair has peer access, else nccl")
+    ap.add_argument("--no-check", action="store_true", help="skip the pre-run parity check against the live-reference golden")
     ap.add_argument("--cpu-budget", type=float, default=15.0)
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
+    W = workload(args.workload)
     if args.impl == "reference":
-        return reference_arm(args)
+        return reference_arm(args, W)
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; dlrm_b200 has no CPU path (use --impl reference for the CPU arm)")
-    ours(args)
+    ours(args, W)
 
 
 if __name__ == "__main__":

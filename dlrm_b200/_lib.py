@@ -14,18 +14,20 @@ LOSS_MSE, LOSS_BCE, LOSS_WBCE = 0, 1, 2
 OPT_SGD, OPT_RWSADAGRAD = 0, 1
 GEMM_SIMT_FP32, GEMM_TC_BF16X3, GEMM_TC_BF16 = 0, 1, 2
 TUNE = dict(emb_bags_per_group=0, emb_unroll=1, emb_block=2, upd_block=3, gemm_splitk=4, gemm_smem_kb=5,
-            head_rows=6, interact_bwd_cols=7, pdl=8)
+            head_rows=6, interact_bwd_cols=7, pdl=8, chain_order=9)
 
 
 class EmbFwdTable(C.Structure):
     _fields_ = [("weight", C.c_void_p), ("indices", C.c_void_p), ("offsets", C.c_void_p),
-                ("row_weights", C.c_void_p), ("nnz", C.c_int64), ("rows", C.c_int64), ("ld", C.c_int64)]
+                ("row_weights", C.c_void_p), ("nnz", C.c_int64), ("rows", C.c_int64), ("ld", C.c_int64),
+                ("out_off", C.c_int64), ("out_stride", C.c_int64), ("row_lo", C.c_int64), ("row_n", C.c_int64)]
 
 
 class EmbBwdTable(C.Structure):
     _fields_ = [("weight", C.c_void_p), ("momentum", C.c_void_p), ("head", C.c_void_p),
                 ("indices", C.c_void_p), ("offsets", C.c_void_p), ("nnz", C.c_int64),
-                ("rows", C.c_int64), ("pair_base", C.c_int64), ("ld", C.c_int64), ("mom_stride", C.c_int64)]
+                ("rows", C.c_int64), ("pair_base", C.c_int64), ("ld", C.c_int64), ("mom_stride", C.c_int64),
+                ("use_dy_off", C.c_int64), ("dy_off", C.c_int64), ("row_lo", C.c_int64), ("row_n", C.c_int64)]
 
 
 class EmbDedup(C.Structure):
@@ -57,7 +59,7 @@ _lib = None
 
 # every symbol include/dlrm_b200.h declares (tests check the .so exports all of them)
 SYMBOLS = [
-    "dlrm_b200_abi_version", "dlrm_b200_last_error", "dlrm_b200_device_info",
+    "dlrm_b200_abi_version", "dlrm_b200_last_error", "dlrm_b200_device_info", "dlrm_b200_check_device_errors",
     "dlrm_b200_emb_bag_fwd", "dlrm_b200_emb_bag_fwd_train", "dlrm_b200_emb_bwd_link",
     "dlrm_b200_emb_bwd_update", "dlrm_b200_head_scratch_bytes", "dlrm_b200_head_fused",
     "dlrm_b200_interact_fwd_ex", "dlrm_b200_interact_bwd_ex", "dlrm_b200_interact_bwd_p2p", "dlrm_b200_act_bwd",
@@ -69,7 +71,9 @@ SYMBOLS = [
     "dlrm_b200_dense_update",
     "dlrm_b200_gemm_tc_plan_create", "dlrm_b200_gemm_tc_plan_info", "dlrm_b200_gemm_tc_run",
     "dlrm_b200_gemm_tc_plan_destroy", "dlrm_b200_gemm_chain_create", "dlrm_b200_gemm_chain_info",
-    "dlrm_b200_gemm_chain_run", "dlrm_b200_gemm_chain_destroy", "dlrm_b200_gemm_chain_set_trace", "dlrm_b200_split_bf16", "dlrm_b200_dense_update_pack",
+    "dlrm_b200_gemm_chain_run", "dlrm_b200_gemm_chain_destroy", "dlrm_b200_gemm_chain_set_trace",
+    "dlrm_b200_emb_bwd_small_scratch_bytes", "dlrm_b200_emb_bwd_small_update", "dlrm_b200_emb_reduce_partials",
+    "dlrm_b200_block_copy", "dlrm_b200_gen_multihot", "dlrm_b200_split_bf16", "dlrm_b200_dense_update_pack",
 ]
 
 
@@ -78,6 +82,7 @@ def _declare(lib):
     lib.dlrm_b200_abi_version.restype = i32
     lib.dlrm_b200_last_error.restype = C.c_char_p
     lib.dlrm_b200_set_tunable.argtypes = [i32, i32]
+    lib.dlrm_b200_check_device_errors.argtypes = [vp]
     lib.dlrm_b200_device_info.argtypes = [i32, C.POINTER(i32), C.POINTER(i32), C.POINTER(i32)]
     lib.dlrm_b200_emb_bag_fwd.argtypes = [C.POINTER(EmbFwdTable), i32, i32, i64, i32, i32, vp, i64, i64, vp]
     lib.dlrm_b200_emb_bag_fwd_train.argtypes = [C.POINTER(EmbFwdTable), C.POINTER(EmbBwdTable), i32, i32, i64, i32,
@@ -106,8 +111,8 @@ def _declare(lib):
     lib.dlrm_b200_linear_dgrad.argtypes = [vp, i64, vp, i64, vp, i64, i32, vp, i64, i64, i64, i64, i32, vp]
     lib.dlrm_b200_linear_wgrad.argtypes = [vp, i64, vp, i64, vp, i64, vp, i64, i64, i64, i32, vp]
     lib.dlrm_b200_interact_fwd.argtypes = [vp, i64, vp, i64, i64, i32, i32, i32, vp]
-    lib.dlrm_b200_interact_bwd_p2p.argtypes = [vp, i64, vp, i64, C.POINTER(vp), C.POINTER(i64), i64, i32, i32, i32, i32,
-                                               vp, vp, i64, vp]
+    lib.dlrm_b200_interact_bwd_p2p.argtypes = [vp, i64, vp, i64, C.POINTER(vp), C.POINTER(i64), C.POINTER(i32), i64, i32,
+                                               i32, i32, i32, vp, vp, i64, vp]
     lib.dlrm_b200_interact_bwd.argtypes = [vp, i64, vp, i64, vp, i64, i64, i32, i32, i32, i32, vp]
     lib.dlrm_b200_loss_fwd_bwd.argtypes = [vp, vp, vp, i64, i32, f32, i32, vp, vp, vp, vp]
     lib.dlrm_b200_dense_update.argtypes = [vp, vp, vp, i64, i32, f32, f32, vp]
@@ -118,13 +123,20 @@ def _declare(lib):
     lib.dlrm_b200_gemm_chain_info.argtypes = [vp, C.POINTER(i32), C.POINTER(i32), C.POINTER(i32), C.POINTER(i32)]
     lib.dlrm_b200_gemm_chain_run.argtypes = [vp, vp]
     lib.dlrm_b200_gemm_chain_set_trace.argtypes = [vp, vp]
+    lib.dlrm_b200_emb_bwd_small_scratch_bytes.argtypes = [i64, i32, i64]
+    lib.dlrm_b200_emb_bwd_small_update.argtypes = [C.POINTER(EmbBwdTable), i32, i32, i64, i32, i32, vp, C.POINTER(vp), i32,
+                                                   i64, i64, i32, f32, f32, vp, i64, vp]
+    lib.dlrm_b200_emb_reduce_partials.argtypes = [vp, vp, i64, i64, i32, C.POINTER(i32), C.POINTER(i32), i32, vp]
+    lib.dlrm_b200_block_copy.argtypes = [C.POINTER(vp), C.POINTER(vp), C.POINTER(i64), i32, vp]
+    lib.dlrm_b200_gen_multihot.argtypes = [C.POINTER(vp), C.POINTER(i64), C.POINTER(i32), C.POINTER(i32), i32, i32,
+                                           C.c_uint64, C.c_uint64, i64, i64, vp, vp, i32, vp]
     lib.dlrm_b200_gemm_chain_destroy.argtypes = [vp]
     lib.dlrm_b200_gemm_tc_plan_destroy.argtypes = [vp]
     lib.dlrm_b200_split_bf16.argtypes = [vp, i64, i64, i64, vp, vp, i64, vp]
     lib.dlrm_b200_dense_update_pack.argtypes = [C.POINTER(DenseLayer), i32, i32, f32, f32, vp]
     for name in SYMBOLS:
         fn = getattr(lib, name)
-        if name == "dlrm_b200_head_scratch_bytes":
+        if name in ("dlrm_b200_head_scratch_bytes", "dlrm_b200_emb_bwd_small_scratch_bytes"):
             fn.restype = i64
         elif name != "dlrm_b200_last_error":
             fn.restype = i32

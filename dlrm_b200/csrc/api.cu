@@ -21,6 +21,23 @@ int set_error(const char* fmt, ...) {
 
 int get_tunable(int id) { return (id >= 0 && id < TUNE_COUNT) ? g_tunables[id] : 0; }
 
+static unsigned* g_err_word[64] = {nullptr};
+
+unsigned* err_word_device() {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+  if (!g_err_word[dev]) {
+    // the only allocation this library ever makes: 4 bytes per device, outside any stream capture
+    cudaStreamCaptureMode mode = cudaStreamCaptureModeRelaxed;
+    cudaThreadExchangeStreamCaptureMode(&mode);
+    unsigned* p = nullptr;
+    if (cudaMalloc(&p, 256) == cudaSuccess && cudaMemset(p, 0, 256) == cudaSuccess) g_err_word[dev] = p;
+    cudaThreadExchangeStreamCaptureMode(&mode);
+    (void)cudaGetLastError();
+  }
+  return g_err_word[dev];
+}
+
 int simt_linear_fwd(const float*, long long, const float*, long long, const float*, float*, long long,
                     long long, long long, long long, int, cudaStream_t);
 int simt_linear_dgrad(const float*, long long, const float*, long long, const float*, long long, int,
@@ -36,6 +53,23 @@ extern "C" const char* dlrm_b200_last_error(void) { return dlrm::err_buf(); }
 extern "C" int dlrm_b200_set_tunable(int id, int value) {
   if (id < 0 || id >= dlrm::TUNE_COUNT) return dlrm::set_error("set_tunable: id=%d", id);
   dlrm::g_tunables[id] = value;
+  return 0;
+}
+
+extern "C" int dlrm_b200_check_device_errors(void* stream) {
+  using namespace dlrm;
+  unsigned* w = err_word_device();
+  if (!w) return 0;
+  unsigned h = 0;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  DLRM_CUDA(cudaMemcpyAsync(&h, w, sizeof(h), cudaMemcpyDeviceToHost, st));
+  DLRM_CUDA(cudaStreamSynchronize(st));
+  if (h) {
+    DLRM_CUDA(cudaMemsetAsync(w, 0, sizeof(h), st));
+    if (h & 1u) return set_error("an embedding index was outside its table (index out of range in self; the access was "
+                                 "redirected to row 0 / skipped, no memory outside the tables was touched)");
+    return set_error("device error word = 0x%x", h);
+  }
   return 0;
 }
 

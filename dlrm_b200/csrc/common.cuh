@@ -12,6 +12,9 @@ namespace dlrm {
 char* err_buf();
 int set_error(const char* fmt, ...);
 int get_tunable(int id);
+// One 4-byte device error word per GPU (allocated on first use, never freed): bit 0 = an embedding index was
+// outside its table.  Kernels only set bits; dlrm_b200_check_device_errors() reads and clears it.
+unsigned* err_word_device();
 
 enum Tunable {
   TUNE_EMB_BAGS_PER_GROUP = 0,  // bags processed back to back by one lane group
@@ -23,6 +26,7 @@ enum Tunable {
   TUNE_HEAD_ROWS = 6,           // samples per CTA in the fused head (16 or 32; 0 = default)
   TUNE_INTERACT_BWD_COLS = 7,   // 1 = one column per thread (first kernel), else float2 columns
   TUNE_PDL = 8,                 // programmatic dependent launch on the dense chain: 0/1 = on, 2 = off
+  TUNE_CHAIN_ORDER = 9,         // gemm_chain task order: 0 = m-tile major across layers, 1 = layer by layer
   TUNE_COUNT = 16
 };
 

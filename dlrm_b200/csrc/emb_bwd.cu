@@ -32,6 +32,10 @@ struct EmbBwdTable {
   long long pair_base;
   long long ld;          // row stride of w in floats
   long long mom_stride;  // elements between consecutive rows' accumulators
+  long long dy_off;      // the dY row of (bag, this table) is dy_row(bag) + dy_off
+  long long rows;        // rows of the whole table
+  long long row_lo;      // this shard stores rows [row_lo, row_lo + row_n) at local index (row - row_lo);
+  long long row_n;       //   occurrences of other rows belong to another shard and are ignored
 };
 
 struct EmbBwdParams {
@@ -88,9 +92,10 @@ __global__ void __launch_bounds__(256) emb_link_kernel(const __grid_constant__ E
       const long long mid = (lo + hi + 1) >> 1;
       if ((long long)off[mid] <= j) lo = mid; else hi = mid - 1;
     }
-    const long long r = idx[j];
+    const long long r = (long long)idx[j] - tb.row_lo;
     const long long pos = tb.pair_base + j;
-    const int prev = atomicExch(tb.head + r, (int)(pos + 1));
+    const bool mine = tb.head != nullptr && (unsigned long long)r < (unsigned long long)tb.row_n;
+    const int prev = mine ? atomicExch(tb.head + r, (int)(pos + 1)) : 0;
     P.link[pos] = make_int2(prev, (int)lo);
   }
 }
@@ -228,16 +233,21 @@ __global__ void __launch_bounds__(256, NV == 1 ? 3 : 1) emb_update_kernel(const 
     int my_head = 0;
     int2 my_link = make_int2(0, 0);
     bool my_susp = true;
+    bool mine = false;
     if (valid) {
       const EmbBwdTable& tb = P.t[k];
-      my_r = static_cast<const idx_t*>(tb.idx)[pos - tb.pair_base];
-      my_link = P.link[pos];
-      if (P.flags) my_susp = P.flags[pos] != 0;
-      // an unflagged occurrence is the only one of its row: it owns the row, head[] is never touched
-      my_head = my_susp ? tb.head[my_r] : (int)(pos + 1);
-      if (!my_susp) my_link.x = 0;
+      my_r = (long long)static_cast<const idx_t*>(tb.idx)[pos - tb.pair_base] - tb.row_lo;
+      // rows of another shard, and tables updated by the small-table path (head == null), are not ours
+      mine = tb.head != nullptr && (unsigned long long)my_r < (unsigned long long)tb.row_n;
+      if (mine) {
+        my_link = P.link[pos];
+        if (P.flags) my_susp = P.flags[pos] != 0;
+        // an unflagged occurrence is the only one of its row: it owns the row, head[] is never touched
+        my_head = my_susp ? tb.head[my_r] : (int)(pos + 1);
+        if (!my_susp) my_link.x = 0;
+      }
     }
-    const unsigned owners = __ballot_sync(0xffffffffu, valid && my_head == (int)(pos + 1));
+    const unsigned owners = __ballot_sync(0xffffffffu, mine && my_head == (int)(pos + 1));
     const unsigned susp_mask = __ballot_sync(0xffffffffu, my_susp);
     for (int u0 = 0; u0 < 32; u0 += PF) {
       if (((owners >> u0) & ((1u << PF) - 1u)) == 0u) continue;
@@ -252,7 +262,7 @@ __global__ void __launch_bounds__(256, NV == 1 ? 3 : 1) emb_update_kernel(const 
         if ((owners >> src) & 1u) {
           const EmbBwdTable& tb = P.t[ku];
           const float* wrow = tb.w + r * tb.ld;
-          const float* grow = dy_row(P, bag) + (long long)ku * P.dy_stride_table;
+          const float* grow = dy_row(P, bag) + tb.dy_off;
 #pragma unroll
           for (int v = 0; v < NV; ++v)
             if (col_ok[v]) {
@@ -272,7 +282,7 @@ __global__ void __launch_bounds__(256, NV == 1 ? 3 : 1) emb_update_kernel(const 
         if (!((owners >> src) & 1u)) continue;
         const EmbBwdTable& tb = P.t[ku];
         float* wrow = tb.w + r * tb.ld;
-        const long long dyk_off = (long long)ku * P.dy_stride_table;
+        const long long dyk_off = tb.dy_off;
         Pack<W> w[NV], g[NV];
 #pragma unroll
         for (int v = 0; v < NV; ++v) { w[v] = wpf[u][v]; g[v] = gpf[u][v]; }
@@ -354,7 +364,7 @@ static int fill_params(EmbBwdParams& P, const dlrm_emb_bwd_table_t* tables, int 
     return set_error("%s: num_tables=%d out of range [0,%d]", who, num_tables,
                      DLRM_B200_MAX_TABLES_PER_CALL);
   for (int k = 0; k < num_tables; ++k) {
-    if (!tables[k].head || !tables[k].offsets || (!tables[k].indices && tables[k].nnz > 0))
+    if (!tables[k].offsets || (!tables[k].indices && tables[k].nnz > 0))
       return set_error("%s: table %d has a NULL pointer", who, k);
     if (tables[k].pair_base + tables[k].nnz > 0x7ffffffeLL)
       return set_error("%s: more than 2^31-2 index occurrences in one call", who);
@@ -367,6 +377,10 @@ static int fill_params(EmbBwdParams& P, const dlrm_emb_bwd_table_t* tables, int 
     P.t[k].pair_base = tables[k].pair_base;
     P.t[k].ld = tables[k].ld;   // 0 -> dim, resolved by the update entry point
     P.t[k].mom_stride = tables[k].mom_stride > 0 ? tables[k].mom_stride : 1;
+    P.t[k].dy_off = 0;          // resolved by the update entry point
+    P.t[k].rows = tables[k].rows > 0 ? tables[k].rows : 0x7fffffffffffffffLL;
+    P.t[k].row_lo = tables[k].row_n > 0 ? tables[k].row_lo : 0;
+    P.t[k].row_n = tables[k].row_n > 0 ? tables[k].row_n : P.t[k].rows;
   }
   return 0;
 }
@@ -430,6 +444,8 @@ static int emb_update_impl(const dlrm_emb_bwd_table_t* tables, int num_tables, i
     dY = peer_dY[0];
   }
   for (int k = 0; k < num_tables; ++k) {
+    P.t[k].dy_off = tables[k].use_dy_off ? tables[k].dy_off : (int64_t)k * dy_stride_table;
+    vec = vec && (P.t[k].dy_off % 4 == 0);
     if (!tables[k].weight) return set_error("emb_bwd_update: table %d weight NULL", k);
     if (optimizer == DLRM_OPT_RWSADAGRAD && !tables[k].momentum)
       return set_error("emb_bwd_update: table %d momentum NULL", k);

@@ -19,9 +19,14 @@ struct EmbFwdTable {
   const void* off;
   const float* rw;
   long long nnz;
-  int* head;            // training: per-row list heads of this table (see emb_bwd.cu), else null
+  int* head;            // training: per-row list heads of this table (see emb_bwd.cu); null = do not link
   long long pair_base;  // training: first slot of this table in link[]
   long long ld;         // row stride in floats
+  long long out_off;    // pooled row of bag b goes to out_row(b) [+ b_local * out_stride] + out_off
+  long long out_stride; // elements between consecutive samples of THIS table's output
+  long long rows;       // rows of the whole table: an index outside [0, rows) is an error
+  long long row_lo;     // this shard stores rows [row_lo, row_lo + row_n) at local index (row - row_lo)
+  long long row_n;
 };
 
 struct EmbFwdParams {
@@ -40,6 +45,7 @@ struct EmbFwdParams {
   long long peer_batch;
   unsigned* filter;   // training with a duplicate filter: count instead of linking
   int filter_log2;
+  unsigned* err;      // device error word: bit 0 = an index was outside its table
 };
 
 // training: either thread the occurrence onto its row's list (returns the previous head) or, with a
@@ -53,12 +59,19 @@ __device__ __forceinline__ int note_occurrence(const EmbFwdParams& P, const EmbF
   return atomicExch(tb.head + row, (int)(tb.pair_base + pos_local + 1));
 }
 
-__device__ __forceinline__ float* out_row(const EmbFwdParams& P, long long b) {
+// Where the pooled row of (table tb, global bag b) goes: buffer of the rank that owns the sample (peer-mapped
+// on a sharded run), sample-local row, per-table offset/stride (whole tables land in feature slot 1+t of the
+// interaction operand, row-split shards in their slab of the partial-sum area behind it).
+__device__ __forceinline__ float* out_ptr(const EmbFwdParams& P, const EmbFwdTable& tb, long long b) {
   if (P.peer_batch > 0) {
     const int dst = (int)(b / P.peer_batch);
-    return P.peer_out[dst] + (b - dst * P.peer_batch) * P.stride_sample;
+    return P.peer_out[dst] + (b - dst * P.peer_batch) * tb.out_stride + tb.out_off;
   }
-  return P.out + b * P.stride_sample;
+  return P.out + b * tb.out_stride + tb.out_off;
+}
+
+__device__ __forceinline__ void flag_bad_index(const EmbFwdParams& P) {
+  if (P.err) atomicOr(P.err, 1u);
 }
 
 
@@ -105,9 +118,13 @@ __global__ void __launch_bounds__(256, (G == 32 && NV == 1) ? 4 : 1) emb_fwd_vec
     int start = __shfl_sync(gmask, my_bound, 0, G);
     int end = __shfl_sync(gmask, my_bound, 1, G);
     // first index chunk of bag 0 (+ fused link: the atomic's result is only stored after the rows)
+    // an index outside the table is reported through the error word and read as row 0 (never out of bounds)
     long long my_row = (start + gl < end) ? (long long)idx[start + gl] : 0;
+    bool bad = (unsigned long long)my_row >= (unsigned long long)tb.rows;   // never linked, never updated
+    if (bad) { flag_bad_index(P); my_row = 0; }
     int my_prev = 0;
-    if (LINK && start + gl < end) my_prev = note_occurrence(P, tb, my_row, start + gl);
+    const bool link_tb = LINK && tb.head != nullptr;
+    if (link_tb && start + gl < end && !bad) my_prev = note_occurrence(P, tb, my_row, start + gl);
 
     for (int s = 0; s < nb; ++s) {
       // prefetch boundaries + first index chunk of the next bag
@@ -117,7 +134,9 @@ __global__ void __launch_bounds__(256, (G == 32 && NV == 1) ? 4 : 1) emb_fwd_vec
         nstart = end;
         nend = __shfl_sync(gmask, my_bound, s + 2, G);
         next_row = (nstart + gl < nend) ? (long long)idx[nstart + gl] : 0;
-        if (LINK && nstart + gl < nend)
+        bad = (unsigned long long)next_row >= (unsigned long long)tb.rows;
+        if (bad) { flag_bad_index(P); next_row = 0; }
+        if (link_tb && nstart + gl < nend && !bad)
           next_prev = note_occurrence(P, tb, next_row, nstart + gl);
       }
       float4 acc[NV];
@@ -127,7 +146,9 @@ __global__ void __launch_bounds__(256, (G == 32 && NV == 1) ? 4 : 1) emb_fwd_vec
       for (int j0 = start; j0 < end; j0 += G) {
         if (j0 != start) {
           my_row = (j0 + gl < end) ? (long long)idx[j0 + gl] : 0;
-          if (LINK && j0 + gl < end) my_prev = note_occurrence(P, tb, my_row, j0 + gl);
+          bad = (unsigned long long)my_row >= (unsigned long long)tb.rows;
+          if (bad) { flag_bad_index(P); my_row = 0; }
+          my_prev = (link_tb && j0 + gl < end && !bad) ? note_occurrence(P, tb, my_row, j0 + gl) : 0;
         }
         const int n = min(G, end - j0);
         for (int jj = 0; jj < n; jj += U) {
@@ -165,10 +186,10 @@ __global__ void __launch_bounds__(256, (G == 32 && NV == 1) ? 4 : 1) emb_fwd_vec
             }
           }
         }
-        if (LINK && j0 + gl < end)
+        if (link_tb && j0 + gl < end)
           P.link[tb.pair_base + j0 + gl] = make_int2(my_prev, (int)(b0 + s));
       }
-      float* op = out_row(P, b0 + s) + (long long)table * P.stride_table + gl * 4;
+      float* op = out_ptr(P, tb, b0 + s) + gl * 4;
 #pragma unroll
       for (int v = 0; v < NV; ++v) {
         if (gl * 4 + v * G * 4 < D) *reinterpret_cast<float4*>(op + v * G * 4) = acc[v];
@@ -178,6 +199,89 @@ __global__ void __launch_bounds__(256, (G == 32 && NV == 1) ? 4 : 1) emb_fwd_vec
       my_row = next_row;
       my_prev = next_prev;
     }
+  }
+}
+
+// Row-split shard: this rank stores rows [row_lo, row_lo + row_n) of the table and pools, for EVERY bag of the
+// global batch, only the indices that fall into its range (a partial sum; the N partials of a bag are added on the
+// rank that owns the sample).  The indices of a 32-wide chunk that are "mine" are compacted with a ballot so
+// that up to U row loads stay in flight however sparse the hits are (L = 100 over 8 shards: ~4 of 32).
+template <int G, int NV, int U, typename idx_t, bool WEIGHTED, bool LINK>
+__global__ void __launch_bounds__(256) emb_fwd_shard_kernel(const __grid_constant__ EmbFwdParams P, int num_tables) {
+  const int D = P.dim;
+  constexpr int GROUPS_PER_WARP = 32 / G;
+  const int lane = threadIdx.x & 31;
+  const int gl = lane % G;
+  const int grp = lane / G;
+  const unsigned gbits = (G == 32) ? 0xffffffffu : ((1u << G) - 1u);
+  const unsigned gmask = gbits << (grp * G);
+  const EmbFwdTable& tb = P.t[blockIdx.y];
+  const idx_t* __restrict__ idx = static_cast<const idx_t*>(tb.idx);
+  const idx_t* __restrict__ off = static_cast<const idx_t*>(tb.off);
+  const float* __restrict__ W = tb.w;
+  const bool link_tb = LINK && tb.head != nullptr;
+  const int S = P.bags_per_group;
+  const long long b0 = (((long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * GROUPS_PER_WARP + grp) * S;
+  for (int s = 0; s < S; ++s) {
+    const long long b = b0 + s;
+    if (b >= P.batch) return;
+    const long long start = (long long)off[b];
+    const long long end = bag_end<idx_t>(off, b, P.batch, tb.nnz, P.include_last);
+    float4 acc[NV];
+#pragma unroll
+    for (int v = 0; v < NV; ++v) acc[v] = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (long long j0 = start; j0 < end; j0 += G) {
+      const bool valid = j0 + gl < end;
+      const long long rg = valid ? (long long)idx[j0 + gl] : -1;
+      const long long lr = rg - tb.row_lo;
+      const bool mine = valid && (unsigned long long)lr < (unsigned long long)tb.row_n;
+      if (valid && !mine && (unsigned long long)rg >= (unsigned long long)tb.rows) flag_bad_index(P);
+      if (link_tb && mine)      // occurrences of other shards' rows are never looked at by the update
+        P.link[tb.pair_base + j0 + gl] = make_int2(note_occurrence(P, tb, lr, j0 + gl), (int)b);
+      unsigned live = (__ballot_sync(gmask, mine) >> (grp * G)) & gbits;
+      while (live) {
+        float4 val[U][NV];
+        float wgt[U];
+        bool on[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          on[u] = live != 0u;
+          const int src = on[u] ? __ffs(live) - 1 : 0;
+          live &= live - 1u;                      // clears the lowest set bit (0 stays 0)
+          const long long r = __shfl_sync(gmask, lr, src, G);
+          if (on[u]) {
+            const float* rp = W + r * tb.ld + gl * 4;
+#pragma unroll
+            for (int v = 0; v < NV; ++v)
+              if (gl * 4 + v * G * 4 < D) val[u][v] = ldg_stream_f4(rp + v * G * 4);
+            if (WEIGHTED) wgt[u] = __ldg(tb.rw + r);
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          if (on[u]) {
+#pragma unroll
+            for (int v = 0; v < NV; ++v) {
+              if (WEIGHTED) {
+                acc[v].x = fmaf(wgt[u], val[u][v].x, acc[v].x);
+                acc[v].y = fmaf(wgt[u], val[u][v].y, acc[v].y);
+                acc[v].z = fmaf(wgt[u], val[u][v].z, acc[v].z);
+                acc[v].w = fmaf(wgt[u], val[u][v].w, acc[v].w);
+              } else {
+                acc[v].x += val[u][v].x;
+                acc[v].y += val[u][v].y;
+                acc[v].z += val[u][v].z;
+                acc[v].w += val[u][v].w;
+              }
+            }
+          }
+        }
+      }
+    }
+    float* op = out_ptr(P, tb, b) + gl * 4;
+#pragma unroll
+    for (int v = 0; v < NV; ++v)
+      if (gl * 4 + v * G * 4 < D) *reinterpret_cast<float4*>(op + v * G * 4) = acc[v];
   }
 }
 
@@ -196,27 +300,36 @@ __global__ void emb_fwd_scalar_kernel(const __grid_constant__ EmbFwdParams P) {
   const long long end = bag_end<idx_t>(off, b, P.batch, tb.nnz, P.include_last);
   float acc = 0.f;
   for (long long j = start; j < end; ++j) {
-    const long long r = idx[j];
-    if (LINK && d == 0) P.link[tb.pair_base + j] = make_int2(note_occurrence(P, tb, r, j), (int)b);
+    const long long rg = idx[j];
+    const long long r = rg - tb.row_lo;
+    const bool mine = (unsigned long long)r < (unsigned long long)tb.row_n;
+    if (!mine && (unsigned long long)rg >= (unsigned long long)tb.rows && d == 0) flag_bad_index(P);
+    if (LINK && tb.head && d == 0) P.link[tb.pair_base + j] = make_int2(mine ? note_occurrence(P, tb, r, j) : 0, (int)b);
+    if (!mine) continue;
     const float x = tb.w[r * tb.ld + d];
     acc = WEIGHTED ? fmaf(tb.rw[r], x, acc) : acc + x;
   }
-  out_row(P, b)[(long long)blockIdx.y * P.stride_table + d] = acc;
+  out_ptr(P, tb, b)[d] = acc;
 }
 
 template <int G, int NV, int U, typename idx_t, bool WEIGHTED, bool LINK>
-static int launch_vec(const EmbFwdParams& P, int num_tables, cudaStream_t st) {
+static int launch_vec(const EmbFwdParams& P, int num_tables, bool shard, cudaStream_t st) {
   const int block = 256;
   const long long groups_per_block = (long long)(block / 32) * (32 / G);
   const long long groups = (P.batch + P.bags_per_group - 1) / P.bags_per_group;
   dim3 grid((unsigned)((groups + groups_per_block - 1) / groups_per_block), (unsigned)num_tables);
+  if (shard) {
+    emb_fwd_shard_kernel<G, NV, U, idx_t, WEIGHTED, LINK><<<grid, block, 0, st>>>(P, num_tables);
+    DLRM_CHECK_LAUNCH("emb_fwd_shard_kernel");
+    return 0;
+  }
   emb_fwd_vec_kernel<G, NV, U, idx_t, WEIGHTED, LINK><<<grid, block, 0, st>>>(P, num_tables);
   DLRM_CHECK_LAUNCH("emb_fwd_vec_kernel");
   return 0;
 }
 
 template <typename idx_t, bool WEIGHTED, bool LINK>
-static int dispatch(const EmbFwdParams& Pin, int num_tables, bool vec_ok, cudaStream_t st) {
+static int dispatch(const EmbFwdParams& Pin, int num_tables, bool vec_ok, bool shard, cudaStream_t st) {
   EmbFwdParams P = Pin;
   const int D = P.dim;
   if (vec_ok) {
@@ -226,8 +339,8 @@ static int dispatch(const EmbFwdParams& Pin, int num_tables, bool vec_ok, cudaSt
 #define VEC(G, NV)                                                                   \
   do {                                                                               \
     P.bags_per_group = S < (G) ? S : (G)-1;                                          \
-    if ((G) >= 8 && u8) return launch_vec<G, NV, 8, idx_t, WEIGHTED, LINK>(P, num_tables, st); \
-    return launch_vec<G, NV, ((G) >= 4 ? 4 : (G)), idx_t, WEIGHTED, LINK>(P, num_tables, st);  \
+    if ((G) >= 8 && u8) return launch_vec<G, NV, 8, idx_t, WEIGHTED, LINK>(P, num_tables, shard, st); \
+    return launch_vec<G, NV, ((G) >= 4 ? 4 : (G)), idx_t, WEIGHTED, LINK>(P, num_tables, shard, st);  \
   } while (0)
     if (D == 16) VEC(4, 1);  // dim 4 / 8: scalar kernel (a group must hold S+1 bag bounds)
     if (D == 32) VEC(8, 1);
@@ -263,7 +376,7 @@ static int emb_fwd_impl(const dlrm_emb_fwd_table_t* tables, const dlrm_emb_bwd_t
     return set_error("emb_bag_fwd: batch=%lld too large", (long long)batch);
   if (train && !link) return set_error("emb_bag_fwd_train: link is NULL");
   EmbFwdParams P;
-  bool weighted = false, any_unweighted = false;
+  bool weighted = false, any_unweighted = false, any_shard = false;
   bool vec_ok = (dim % 4 == 0) && dim <= 512 && (peer_out || aligned16(out)) && out_stride_sample % 4 == 0 &&
                 out_stride_table % 4 == 0;
   for (int k = 0; k < num_tables; ++k) {
@@ -275,12 +388,23 @@ static int emb_fwd_impl(const dlrm_emb_fwd_table_t* tables, const dlrm_emb_bwd_t
     P.t[k].ld = tables[k].ld > 0 ? tables[k].ld : dim;
     if (P.t[k].ld < dim) return set_error("emb_bag_fwd: table %d: ld=%lld < dim", k, (long long)tables[k].ld);
     vec_ok = vec_ok && (P.t[k].ld % 4 == 0);
-    P.t[k].head = train ? train[k].head : nullptr;
+    P.t[k].head = train ? train[k].head : nullptr;   // train[k].head == NULL: this table is not linked
     P.t[k].pair_base = train ? train[k].pair_base : 0;
+    // per-table output routing (0 = the call-level layout out[b, k, :])
+    P.t[k].out_stride = tables[k].out_stride > 0 ? tables[k].out_stride : out_stride_sample;
+    P.t[k].out_off = tables[k].out_stride > 0 ? tables[k].out_off : (int64_t)k * out_stride_table;
+    vec_ok = vec_ok && (P.t[k].out_stride % 4 == 0) && (P.t[k].out_off % 4 == 0);
+    // row range of a shard; rows <= 0: unchecked (legacy callers)
+    P.t[k].rows = tables[k].rows > 0 ? tables[k].rows : 0x7fffffffffffffffLL;
+    P.t[k].row_lo = tables[k].row_n > 0 ? tables[k].row_lo : 0;
+    P.t[k].row_n = tables[k].row_n > 0 ? tables[k].row_n : P.t[k].rows;
+    if (P.t[k].row_lo < 0 || (tables[k].rows > 0 && P.t[k].row_lo + P.t[k].row_n > tables[k].rows))
+      return set_error("emb_bag_fwd: table %d: row range [%lld, +%lld) outside %lld rows", k,
+                       (long long)P.t[k].row_lo, (long long)P.t[k].row_n, (long long)tables[k].rows);
+    any_shard = any_shard || P.t[k].row_lo != 0 || P.t[k].row_n != P.t[k].rows;
     if (!tables[k].weight || !tables[k].offsets || (!tables[k].indices && tables[k].nnz > 0))
       return set_error("emb_bag_fwd: table %d has a NULL pointer", k);
     if (tables[k].nnz > 0x7ffffffeLL) return set_error("emb_bag_fwd: table %d: nnz >= 2^31 per call", k);
-    if (train && !train[k].head) return set_error("emb_bag_fwd_train: table %d head is NULL", k);
     if (train && train[k].pair_base + tables[k].nnz > 0x7ffffffeLL)
       return set_error("emb_bag_fwd_train: more than 2^31-2 index occurrences");
     if (tables[k].row_weights) weighted = true; else any_unweighted = true;
@@ -298,6 +422,7 @@ static int emb_fwd_impl(const dlrm_emb_fwd_table_t* tables, const dlrm_emb_bwd_t
   P.link = reinterpret_cast<int2*>(link);
   P.filter = nullptr;
   P.filter_log2 = 0;
+  P.err = err_word_device();
   if (train && dedup && dedup->filter) {
     if (dedup->log2_size < 10 || dedup->log2_size > 30)
       return set_error("emb_bag_fwd_train: dedup log2_size=%d out of range [10,30]", dedup->log2_size);
@@ -321,10 +446,10 @@ static int emb_fwd_impl(const dlrm_emb_fwd_table_t* tables, const dlrm_emb_bwd_t
   cudaStream_t st = static_cast<cudaStream_t>(stream);
 #define DISPATCH(IDX)                                                                          \
   do {                                                                                         \
-    if (train) return weighted ? dispatch<IDX, true, true>(P, num_tables, vec_ok, st)          \
-                               : dispatch<IDX, false, true>(P, num_tables, vec_ok, st);        \
-    return weighted ? dispatch<IDX, true, false>(P, num_tables, vec_ok, st)                    \
-                    : dispatch<IDX, false, false>(P, num_tables, vec_ok, st);                  \
+    if (train) return weighted ? dispatch<IDX, true, true>(P, num_tables, vec_ok, any_shard, st)          \
+                               : dispatch<IDX, false, true>(P, num_tables, vec_ok, any_shard, st);        \
+    return weighted ? dispatch<IDX, true, false>(P, num_tables, vec_ok, any_shard, st)                    \
+                    : dispatch<IDX, false, false>(P, num_tables, vec_ok, any_shard, st);                  \
   } while (0)
   if (idx_bytes == 8) DISPATCH(long long);
   DISPATCH(int);

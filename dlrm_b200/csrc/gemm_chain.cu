@@ -45,8 +45,19 @@ struct ChProblem {
   int signal;         // some later problem depends on this one
 };
 
+// Task order.  A group of consecutive single-split problems with the same number of m tiles (the layers of a
+// forward MLP, the dgrad chain) is enumerated M-TILE MAJOR: (m, problem, n tile).  Layer l+1 of m tile 0 is then
+// claimed right after layer l of m tile 0 and can start as soon as those few tiles are done, while other CTAs
+// work on the next m tiles: the layers pipeline across the batch instead of running as one wave per layer.
+// Any other problem is a group of its own, enumerated (k split, m, n).
+struct ChGroup {
+  int task_begin, p0, np, per_m;
+};
+
 struct ChParams {
   ChProblem p[CH_MAX_PROBLEMS];
+  ChGroup grp[CH_MAX_PROBLEMS];
+  int ngroups;
   int n, total, stages;
   uint32_t stage_bytes;
   int* ctr;           // [0] task queue, [1] exit count, [2...] completion counters
@@ -73,17 +84,31 @@ struct ChTask {
 };
 __device__ __forceinline__ ChTask ch_decode(const ChParams& P, int t) {
   ChTask k;
-  k.pi = 0;
-  while (k.pi + 1 < P.n && t >= P.p[k.pi + 1].task_begin) ++k.pi;
-  const ChProblem& Q = P.p[k.pi];
-  const int local = t - Q.task_begin;
-  k.bx = local % Q.gx;
-  k.by = (local / Q.gx) % Q.gy;
-  k.bz = local / (Q.gx * Q.gy);
+  int gi = 0;
+  while (gi + 1 < P.ngroups && t >= P.grp[gi + 1].task_begin) ++gi;
+  const ChGroup& G = P.grp[gi];
+  const int local = t - G.task_begin;
+  if (G.np == 1) {
+    const ChProblem& Q = P.p[G.p0];
+    k.pi = G.p0;
+    k.bx = local % Q.gx;
+    k.by = (local / Q.gx) % Q.gy;
+    k.bz = local / (Q.gx * Q.gy);
+  } else {
+    k.by = local / G.per_m;
+    int r = local - k.by * G.per_m;
+    k.pi = G.p0;
+    while (r >= P.p[k.pi].gx) { r -= P.p[k.pi].gx; ++k.pi; }
+    k.bx = r;
+    k.bz = 0;
+  }
   return k;
 }
 
-__global__ void __launch_bounds__(192, 1) gemm_chain_kernel(const __grid_constant__ ChParams P) {
+constexpr int CH_EPI_WARPS = 8;     // two per TMEM lane quadrant: the epilogue is issue-latency bound per warp
+constexpr int CH_THREADS = 64 + 32 * CH_EPI_WARPS;
+
+__global__ void __launch_bounds__(CH_THREADS, 1) gemm_chain_kernel(const __grid_constant__ ChParams P) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int stages = P.stages;
@@ -111,11 +136,11 @@ __global__ void __launch_bounds__(192, 1) gemm_chain_kernel(const __grid_constan
     }
     for (int s = 0; s < CH_ACC_STAGES; ++s) {
       mbar_init(bar_acc_full + 8 * s, 1);
-      mbar_init(bar_acc_empty + 8 * s, 4);     // lane 0 of each epilogue warp
+      mbar_init(bar_acc_empty + 8 * s, CH_EPI_WARPS);     // lane 0 of each epilogue warp
     }
     for (int s = 0; s < CH_RING; ++s) {
       mbar_init(bar_task_full + 8 * s, 1);
-      mbar_init(bar_task_empty + 8 * s, 5);    // MMA warp + 4 epilogue warps
+      mbar_init(bar_task_empty + 8 * s, 1 + CH_EPI_WARPS);    // MMA warp + epilogue warps
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -265,8 +290,9 @@ __global__ void __launch_bounds__(192, 1) gemm_chain_kernel(const __grid_constan
       if (++as == CH_ACC_STAGES) { as = 0; aph ^= 1; }
     }
   } else {
-    // ------------------------------------------------------------------ epilogue (warps 2..5)
-    const int quad = warp & 3;
+    // ------------------------------------------------------------------ epilogue (warps 2..9)
+    const int quad = warp & 3;            // TMEM lane quadrant this warp may access
+    const int half = (warp - 2) >> 2;     // which of the quadrant's two warps: even / odd 32-column chunks
     int slot = 0, as = 0;
     uint32_t tph = 0, aph = 0;
     while (true) {
@@ -282,14 +308,16 @@ __global__ void __launch_bounds__(192, 1) gemm_chain_kernel(const __grid_constan
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       if (P.trace && warp == 2 && lane == 0) P.trace[(size_t)t * 8 + 5] = globaltimer_ns();
       tc_epilogue_tile(Q.a, Q.bn, k.by * TC_BM, k.bx * Q.bn, k.bz, tmem_base + (uint32_t)(as * 128), quad, lane,
-                       epi_stage + (size_t)(warp - 2) * TC_EPI_WARP_BYTES);
+                       epi_stage + (size_t)(warp - 2) * TC_EPI_WARP_BYTES, half, CH_EPI_WARPS / 4);
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       __syncwarp();
       if (lane == 0) mbar_arrive(bar_acc_empty + 8 * as);
       if (Q.signal) {
-        __threadfence();                                    // this thread's stores are visible GPU-wide
-        asm volatile("bar.sync 1, 128;" ::: "memory");      // ... and so are those of the other 127
+        // grid-sync idiom: every epilogue thread has issued its stores (barrier), then ONE thread makes them
+        // visible GPU-wide (cumulative fence) and publishes the tile with a release reduction
+        asm volatile("bar.sync 1, %0;" ::"n"(32 * CH_EPI_WARPS) : "memory");
         if (warp == 2 && lane == 0) {
+          __threadfence();
           asm volatile("fence.proxy.async;" ::: "memory");
           red_release_gpu_add(P.ctr + 2 + Q.ctr_base + k.by, 1);
         }
@@ -368,6 +396,27 @@ extern "C" int dlrm_b200_gemm_chain_create(void* const* plans, const int* dep, c
     const uint32_t sb = (uint32_t)((Q.a.x3 ? 2 : 1) * (TC_BM * TC_BK * 2 + Q.bn * TC_BK * 2));
     stage_bytes = sb > stage_bytes ? sb : stage_bytes;
   }
+  // groups (see ChGroup): maximal runs of single-split problems with equal m tiles, m-tile major
+  {
+    int gi = 0, i = 0;
+    long long t0 = 0;
+    const bool mmajor = get_tunable(TUNE_CHAIN_ORDER) != 1;
+    while (i < n) {
+      int j = i + 1;
+      // only row-linked problems (a task depends on ITS m tile of the producer) may be interleaved by m tile:
+      // a problem that reduces over the batch (dep_on_k) needs ALL m tiles of its producer first
+      if (mmajor && P.p[i].gz == 1 && !P.p[i].dep_on_k)
+        while (j < n && P.p[j].gz == 1 && !P.p[j].dep_on_k && P.p[j].gy == P.p[i].gy) ++j;
+      ChGroup& G = P.grp[gi++];
+      G.task_begin = (int)t0; G.p0 = i; G.np = j - i; G.per_m = 0;
+      for (int q = i; q < j; ++q) {
+        G.per_m += P.p[q].gx;
+        t0 += (long long)P.p[q].gx * P.p[q].gy * P.p[q].gz;
+      }
+      i = j;
+    }
+    P.ngroups = gi;
+  }
   if (total <= 0 || total >= (1ll << 30)) { delete c; return set_error("gemm_chain_create: %lld tasks", total); }
   if (counters_len < 2 + nctr) { delete c; return set_error("gemm_chain_create: counters_len=%lld < %lld", (long long)counters_len, 2 + nctr); }
   P.n = n;
@@ -381,7 +430,7 @@ extern "C" int dlrm_b200_gemm_chain_create(void* const* plans, const int* dep, c
   P.stages = stages;
   P.ctr = counters;
   P.n_ctr = (int)(2 + nctr);
-  c->smem = (size_t)stages * stage_bytes + 512 + TC_EPI_BYTES + 1024;   // ring | barriers, task ring | epilogue staging
+  c->smem = (size_t)stages * stage_bytes + 512 + CH_EPI_WARPS * TC_EPI_WARP_BYTES + 1024;   // ring | barriers, task ring | staging
   int dev = 0, sms = 0;
   DLRM_CUDA(cudaGetDevice(&dev));
   DLRM_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
@@ -417,7 +466,7 @@ extern "C" int dlrm_b200_gemm_chain_run(void* chain, void* stream) {
     DLRM_CUDA(cudaFuncSetAttribute(gemm_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     configured = true;
   }
-  (void)launch_chain(gemm_chain_kernel, dim3(c->grid), dim3(192), c->smem, static_cast<cudaStream_t>(stream), c->P);
+  (void)launch_chain(gemm_chain_kernel, dim3(c->grid), dim3(CH_THREADS), c->smem, static_cast<cudaStream_t>(stream), c->P);
   DLRM_CHECK_LAUNCH("gemm_chain_kernel");
   return 0;
 }

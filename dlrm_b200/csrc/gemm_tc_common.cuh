@@ -130,9 +130,9 @@ __device__ __forceinline__ float apply_act_tc(float v, int act) {
 // covers whole row segments: 8 rows x 64 B for the bf16 (hi, lo) operands, 4 rows x 128 B for fp32; the
 // activation-gradient mask is read the same way.  Chunks that are ragged (N tail, the diverted bias-gradient
 // column) or whose rows are not 16-byte aligned use element-wise but still row-contiguous accesses.
-constexpr int TC_EPI_ROW_F32 = 36;                 // floats per staged fp32 row (32 + 4 pad)
+constexpr int TC_EPI_ROW_F32 = 20;                 // floats per staged fp32 half-row (16 + 4 pad)
 constexpr int TC_EPI_ROW_BF16 = 40;                // bf16 per staged bf16 row (32 + 8 pad)
-constexpr int TC_EPI_WARP_BYTES = 32 * TC_EPI_ROW_F32 * 4;   // 4608 B per epilogue warp
+constexpr int TC_EPI_WARP_BYTES = 32 * TC_EPI_ROW_BF16 * 2;  // 2560 B per epilogue warp (fp32: two 16-column passes)
 constexpr int TC_EPI_BYTES = 4 * TC_EPI_WARP_BYTES;
 
 // 32 x 32 bf16 chunk, one row per thread in `mine` -> global rows [mrow0, mrow0 + 32) x columns [nb, nb + 32)
@@ -153,57 +153,86 @@ __device__ __forceinline__ void tc_epi_store_bf16(const __nv_bfloat16 (&mine)[32
     }
   } else {
     const long long col = nb + lane;
-    for (int row = 0; row < 32; ++row) {
-      if (mrow0 + row >= M) break;
-      if (col < N) dst[(mrow0 + row) * ld + col] = sb[row * TC_EPI_ROW_BF16 + lane];
-    }
+    const int nrow = (int)min(32ll, M - mrow0);
+    if (col < N)
+      for (int row = 0; row < nrow; ++row) dst[(mrow0 + row) * ld + col] = sb[row * TC_EPI_ROW_BF16 + lane];
   }
   __syncwarp();
 }
 
+// c0 / cstep: this warp handles the 32-column chunks c0, c0 + cstep, ... (two warps per TMEM lane quadrant split
+// the chunks of a tile between them in the chain kernel; the per-layer kernel passes 0, 1).
 __device__ __forceinline__ void tc_epilogue_tile(const TcArgs& g, int bn, int m0, int n0, int bz, uint32_t tmem_acc,
-                                                 int quad, int lane, uint8_t* stage_warp) {
+                                                 int quad, int lane, uint8_t* stage_warp, int c0 = 0, int cstep = 1) {
+  // Every field is copied into a register ONCE: `g` lives in kernel-parameter space (indexed at run time in the
+  // chain kernel) and the tcgen05 / mbarrier asm statements clobber memory, so reading g.act or g.bias inside the
+  // element loops costs a constant-bank load + a branch PER ELEMENT (measured: 3-7 us per 32 x 32 chunk).
+  const long long M = g.M, N = g.N;
+  const int act = g.act, mask_act = g.mask_act;
+  const __nv_bfloat16* const mask_hi = g.mask_hi;
+  const __nv_bfloat16* const mask_lo = g.mask_lo;
+  const long long ldmask = g.ldmask, ld_f32 = g.ld_f32, ld_out = g.ld_out, ld_outT = g.ld_outT;
+  __nv_bfloat16* const out_hi = g.out_hi;
+  __nv_bfloat16* const out_lo = g.out_lo;
+  __nv_bfloat16* const outT_hi = g.outT_hi;
+  __nv_bfloat16* const outT_lo = g.outT_lo;
+  const float* const bias = g.bias;
+  const long long col_index = g.col_index;
+  float* const of32 = g.out_f32 ? g.out_f32 + (long long)bz * g.slab_stride : nullptr;
+  float* const ocol = g.out_col ? g.out_col + (long long)bz * g.col_slab_stride : nullptr;
+
   const long long mrow0 = (long long)m0 + quad * 32;   // first row of this warp
   const long long m = mrow0 + lane;
-  const bool m_ok = m < g.M;
-  float* of32 = g.out_f32 ? g.out_f32 + (long long)bz * g.slab_stride : nullptr;
-  float* ocol = g.out_col ? g.out_col + (long long)bz * g.col_slab_stride : nullptr;
+  const bool m_ok = m < M;
   float* sf = reinterpret_cast<float*>(stage_warp);
   __nv_bfloat16* sb = reinterpret_cast<__nv_bfloat16*>(stage_warp);
-  const bool f32_vec = of32 && (g.ld_f32 & 3) == 0 && (reinterpret_cast<uintptr_t>(of32) & 15) == 0;
-  const bool bf_vec = g.out_hi && (g.ld_out & 7) == 0 && (reinterpret_cast<uintptr_t>(g.out_hi) & 15) == 0 &&
-                      (!g.out_lo || (reinterpret_cast<uintptr_t>(g.out_lo) & 15) == 0);
-  const bool mask_vec = g.mask_act != DLRM_ACT_NONE && (g.ldmask & 7) == 0 &&
-                        (reinterpret_cast<uintptr_t>(g.mask_hi) & 15) == 0 &&
-                        (!g.mask_lo || (reinterpret_cast<uintptr_t>(g.mask_lo) & 15) == 0);
+  const bool f32_vec = of32 && (ld_f32 & 3) == 0 && (reinterpret_cast<uintptr_t>(of32) & 15) == 0;
+  const bool bf_vec = out_hi && (ld_out & 7) == 0 && (reinterpret_cast<uintptr_t>(out_hi) & 15) == 0 &&
+                      (!out_lo || (reinterpret_cast<uintptr_t>(out_lo) & 15) == 0);
+  const bool mask_vec = mask_act != DLRM_ACT_NONE && (ldmask & 7) == 0 &&
+                        (reinterpret_cast<uintptr_t>(mask_hi) & 15) == 0 &&
+                        (!mask_lo || (reinterpret_cast<uintptr_t>(mask_lo) & 15) == 0);
+  const bool bias_vec = bias && (reinterpret_cast<uintptr_t>(bias) & 15) == 0;
 #pragma unroll 1
-  for (int c = 0; c < bn / 32; ++c) {
+  for (int c = c0; c < bn / 32; c += cstep) {
+    const long long nb = (long long)n0 + c * 32;
+    if (nb >= N) break;
     uint32_t r[32];
     tmem_ld32(tmem_acc + ((uint32_t)(quad * 32) << 16) + (uint32_t)(c * 32), r);
-    const long long nb = (long long)n0 + c * 32;
-    if (nb >= g.N) break;
     float v[32];
-    const bool full = nb + 32 <= g.N;
-    if (g.bias) {     // nn.Linear bias (broadcast over rows: every lane reads the same 32 values -> one L1 line)
+    const bool full = nb + 32 <= N;
 #pragma unroll
-      for (int j = 0; j < 32; ++j) {
-        const float bj = (full || nb + j < g.N) ? __ldg(g.bias + nb + j) : 0.f;
-        v[j] = apply_act_tc(__uint_as_float(r[j]) + bj, g.act);
+    for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+    if (bias) {       // nn.Linear bias: the same 32 values for every row -> 8 broadcast 16-byte loads
+      if (full && bias_vec) {
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          const float4 b4 = __ldg(reinterpret_cast<const float4*>(bias + nb) + q);
+          v[4 * q] += b4.x; v[4 * q + 1] += b4.y; v[4 * q + 2] += b4.z; v[4 * q + 3] += b4.w;
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] += (nb + j < N) ? __ldg(bias + nb + j) : 0.f;
       }
-    } else {
+    }
+    if (act == DLRM_ACT_RELU) {
 #pragma unroll
-      for (int j = 0; j < 32; ++j) v[j] = apply_act_tc(__uint_as_float(r[j]), g.act);
+      for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+    } else if (act == DLRM_ACT_SIGMOID) {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) v[j] = 1.0f / (1.0f + expf(-v[j]));
     }
     // ---------------------------------------------------------------- activation-gradient mask
-    if (g.mask_act != DLRM_ACT_NONE) {
+    if (mask_act != DLRM_ACT_NONE) {
       if (full && mask_vec) {
-        for (int pass = 0; pass < (g.mask_act == DLRM_ACT_SIGMOID && g.mask_lo ? 2 : 1); ++pass) {
-          const __nv_bfloat16* src = pass ? g.mask_lo : g.mask_hi;
+        const int passes = (mask_act == DLRM_ACT_SIGMOID && mask_lo) ? 2 : 1;
+        for (int pass = 0; pass < passes; ++pass) {
+          const __nv_bfloat16* src = pass ? mask_lo : mask_hi;
 #pragma unroll
           for (int i = 0; i < 4; ++i) {       // 8 rows x 64 B per warp load
             const int row = i * 8 + (lane >> 2), seg = lane & 3;
             uint4 t = make_uint4(0, 0, 0, 0);
-            if (mrow0 + row < g.M) t = *reinterpret_cast<const uint4*>(src + (mrow0 + row) * g.ldmask + nb + seg * 8);
+            if (mrow0 + row < M) t = *reinterpret_cast<const uint4*>(src + (mrow0 + row) * ldmask + nb + seg * 8);
             *reinterpret_cast<uint4*>(sb + row * TC_EPI_ROW_BF16 + seg * 8) = t;
           }
           __syncwarp();
@@ -212,10 +241,10 @@ __device__ __forceinline__ void tc_epilogue_tile(const TcArgs& g, int bn, int m0
           for (int q = 0; q < 4; ++q)
             reinterpret_cast<uint4*>(y)[q] = *reinterpret_cast<const uint4*>(sb + lane * TC_EPI_ROW_BF16 + q * 8);
           __syncwarp();
-          if (g.mask_act == DLRM_ACT_RELU) {
+          if (mask_act == DLRM_ACT_RELU) {
 #pragma unroll
             for (int j = 0; j < 32; ++j) v[j] = __bfloat162float(y[j]) > 0.f ? v[j] : 0.f;
-          } else if (!g.mask_lo) {
+          } else if (passes == 1) {
 #pragma unroll
             for (int j = 0; j < 32; ++j) { const float yy = __bfloat162float(y[j]); v[j] *= (1.0f - yy) * yy; }
           } else if (pass == 0) {
@@ -230,15 +259,14 @@ __device__ __forceinline__ void tc_epilogue_tile(const TcArgs& g, int bn, int m0
           }
         }
       } else if (m_ok) {
-#pragma unroll
         for (int j = 0; j < 32; ++j) {
-          if (full || nb + j < g.N) {
-            const long long o = m * g.ldmask + nb + j;
-            float y = __bfloat162float(g.mask_hi[o]);
-            if (g.mask_act == DLRM_ACT_RELU) {
+          if (nb + j < N) {
+            const long long o = m * ldmask + nb + j;
+            float y = __bfloat162float(mask_hi[o]);
+            if (mask_act == DLRM_ACT_RELU) {
               v[j] = y > 0.f ? v[j] : 0.f;
             } else {
-              if (g.mask_lo) y += __bfloat162float(g.mask_lo[o]);
+              if (mask_lo) y += __bfloat162float(mask_lo[o]);
               v[j] *= (1.0f - y) * y;
             }
           }
@@ -247,51 +275,55 @@ __device__ __forceinline__ void tc_epilogue_tile(const TcArgs& g, int bn, int m0
     }
     // ---------------------------------------------------------------- fp32 output (+ diverted column)
     if (of32) {
+      const bool vec = full && f32_vec && (!ocol || nb + 32 <= col_index);
+      const int nrow = (int)min(32ll, M - mrow0);
 #pragma unroll
-      for (int q = 0; q < 8; ++q)
-        *reinterpret_cast<float4*>(sf + lane * TC_EPI_ROW_F32 + q * 4) = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
-      __syncwarp();
-      const bool colsplit = ocol != nullptr && g.col_index >= nb && g.col_index < nb + 32;
-      if (full && !colsplit && f32_vec && (!ocol || nb + 32 <= g.col_index)) {
+      for (int h = 0; h < 2; ++h) {           // two 16-column passes through the 2560-byte staging tile
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {         // 4 rows x 128 B per warp store
-          const int row = i * 4 + (lane >> 3), seg = lane & 7;
-          if (mrow0 + row < g.M)
-            *reinterpret_cast<float4*>(of32 + (mrow0 + row) * g.ld_f32 + nb + seg * 4) =
-                *reinterpret_cast<const float4*>(sf + row * TC_EPI_ROW_F32 + seg * 4);
+        for (int q = 0; q < 4; ++q)
+          *reinterpret_cast<float4*>(sf + lane * TC_EPI_ROW_F32 + q * 4) =
+              make_float4(v[16 * h + 4 * q], v[16 * h + 4 * q + 1], v[16 * h + 4 * q + 2], v[16 * h + 4 * q + 3]);
+        __syncwarp();
+        if (vec) {
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {       // 8 rows x 64 B per warp store
+            const int row = i * 8 + (lane >> 2), seg = lane & 3;
+            if (row < nrow)
+              *reinterpret_cast<float4*>(of32 + (mrow0 + row) * ld_f32 + nb + 16 * h + seg * 4) =
+                  *reinterpret_cast<const float4*>(sf + row * TC_EPI_ROW_F32 + seg * 4);
+          }
+        } else {                              // 2 rows x 16 consecutive floats per store
+          const long long col = nb + 16 * h + (lane & 15);
+          const bool to_col = ocol && col == col_index;
+          const bool to_out = col < N && (!ocol || col < col_index);
+          for (int row = lane >> 4; row < nrow; row += 2) {
+            const float x = sf[row * TC_EPI_ROW_F32 + (lane & 15)];
+            if (to_col) ocol[mrow0 + row] = x;
+            else if (to_out) of32[(mrow0 + row) * ld_f32 + col] = x;
+          }
         }
-      } else {
-        const long long col = nb + lane;      // one row per store: 32 consecutive floats
-        const bool to_col = ocol && col == g.col_index;
-        const bool to_out = col < g.N && (!ocol || col < g.col_index);
-        for (int row = 0; row < 32; ++row) {
-          if (mrow0 + row >= g.M) break;
-          const float x = sf[row * TC_EPI_ROW_F32 + lane];
-          if (to_col) ocol[mrow0 + row] = x;
-          else if (to_out) of32[(mrow0 + row) * g.ld_f32 + col] = x;
-        }
+        __syncwarp();
       }
-      __syncwarp();
     }
     // ---------------------------------------------------------------- (hi, lo) bf16 operand outputs
-    if (g.out_hi || g.outT_hi) {
+    if (out_hi || outT_hi) {
       __align__(16) __nv_bfloat16 hi[32], lo[32];
 #pragma unroll
       for (int j = 0; j < 32; ++j) {
         hi[j] = __float2bfloat16_rn(v[j]);
         lo[j] = __float2bfloat16_rn(v[j] - __bfloat162float(hi[j]));
       }
-      if (g.out_hi) {
-        tc_epi_store_bf16(hi, g.out_hi, g.ld_out, mrow0, nb, g.M, g.N, full && bf_vec, lane, sb);
-        if (g.out_lo) tc_epi_store_bf16(lo, g.out_lo, g.ld_out, mrow0, nb, g.M, g.N, full && bf_vec, lane, sb);
+      if (out_hi) {
+        tc_epi_store_bf16(hi, out_hi, ld_out, mrow0, nb, M, N, full && bf_vec, lane, sb);
+        if (out_lo) tc_epi_store_bf16(lo, out_lo, ld_out, mrow0, nb, M, N, full && bf_vec, lane, sb);
       }
-      if (g.outT_hi && m_ok) {                // transposed copy: consecutive lanes = consecutive rows = contiguous
+      if (outT_hi && m_ok) {                  // transposed copy: consecutive lanes = consecutive rows = contiguous
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
-          if (full || nb + j < g.N) {
-            const long long o = (nb + j) * g.ld_outT + m;
-            g.outT_hi[o] = hi[j];
-            if (g.outT_lo) g.outT_lo[o] = lo[j];
+          if (full || nb + j < N) {
+            const long long o = (nb + j) * ld_outT + m;
+            outT_hi[o] = hi[j];
+            if (outT_lo) outT_lo[o] = lo[j];
           }
         }
       }

@@ -193,9 +193,13 @@ __global__ void __launch_bounds__(192) interact_fwd2_kernel(const float* __restr
 // ROUTE: feature i's gradient rows go to route.base[i] + sample * route.ld[i] instead of dT -- on a sharded
 // run base[1 + t] points into the buffer of the rank that owns table t (NVLink peer store, 512-byte
 // rows), so the gradient exchange rides on this kernel's stores and needs no all-to-all.
+// A feature may have several destinations: a row-split table keeps a shard on every rank and each shard owner
+// needs the gradient rows of all samples (placement.py), so its feature is stored to every rank.
+constexpr int ROUTE_MAX_DST = 128;
 struct FeatRoute {
-  float* base[64];
-  long long ld[64];
+  float* base[ROUTE_MAX_DST];
+  long long ld[ROUTE_MAX_DST];
+  unsigned char first[66];     // destinations [first[i], first[i + 1]) belong to feature i
 };
 
 struct NoRoute {};
@@ -256,8 +260,11 @@ __global__ void __launch_bounds__(128) interact_bwd_kernel(const float* __restri
       }
       if (i == 0 && mask0 == DLRM_ACT_RELU) acc = (t[0] > 0.f) ? acc : 0.f;
       if (i == 0 && mask0 == DLRM_ACT_SIGMOID) acc *= (1.0f - t[0]) * t[0];
-      if constexpr (ROUTE) route.base[i][(s0 + s) * route.ld[i] + d] = acc;
-      else out[(long long)i * D] = acc;
+      if constexpr (ROUTE) {
+        for (int q = route.first[i]; q < route.first[i + 1]; ++q) route.base[q][(s0 + s) * route.ld[q] + d] = acc;
+      } else {
+        out[(long long)i * D] = acc;
+      }
       if (i == 0 && g0h) {  // feature 0 = gradient into the bottom MLP: also as a (hi, lo) bf16 pair
         const __nv_bfloat16 hb = __float2bfloat16_rn(acc);
         g0h[(s0 + s) * ldg0 + d] = hb;
@@ -334,8 +341,12 @@ __global__ void __launch_bounds__(128) interact_bwd2_kernel(const float* __restr
         acc.x *= (1.0f - t[0].x) * t[0].x;
         acc.y *= (1.0f - t[0].y) * t[0].y;
       }
-      if constexpr (ROUTE) *reinterpret_cast<float2*>(route.base[i] + (s0 + s) * route.ld[i] + d) = acc;
-      else *reinterpret_cast<float2*>(dT + (s0 + s) * lddt + (long long)i * D + d) = acc;
+      if constexpr (ROUTE) {
+        for (int q = route.first[i]; q < route.first[i + 1]; ++q)
+          *reinterpret_cast<float2*>(route.base[q] + (s0 + s) * route.ld[q] + d) = acc;
+      } else {
+        *reinterpret_cast<float2*>(dT + (s0 + s) * lddt + (long long)i * D + d) = acc;
+      }
       if (i == 0 && g0h) {  // feature 0 = gradient into the bottom MLP: also as a (hi, lo) bf16 pair
         const __nv_bfloat162 hb = __floats2bfloat162_rn(acc.x, acc.y);
         *reinterpret_cast<__nv_bfloat162*>(g0h + (s0 + s) * ldg0 + d) = hb;
@@ -428,7 +439,7 @@ static int interact_bwd_launch(const float* T, int64_t ldt, const float* dR, int
              (!gh || ((reinterpret_cast<uintptr_t>(gh) & 3) == 0 && (ld_g0 & 1) == 0)) &&
              (!gl || (reinterpret_cast<uintptr_t>(gl) & 3) == 0);
   if (route)
-    for (int i = 0; i < F; ++i) two = two && even8(route->base[i], route->ld[i]);
+    for (int q = 0; q < route->first[F]; ++q) two = two && even8(route->base[q], route->ld[q]);
   const int cols = two ? D / 2 : D;
   int spb = 128 / cols;
   if (spb < 1) spb = 1;
@@ -469,17 +480,24 @@ extern "C" int dlrm_b200_interact_bwd_ex(const float* T, int64_t ldt, const floa
 }
 
 extern "C" int dlrm_b200_interact_bwd_p2p(const float* T, int64_t ldt, const float* dR, int64_t lddr,
-                                          void* const* feat_dst, const int64_t* feat_ld, int64_t batch,
-                                          int num_features, int dim, int itself, int mask_feature0,
+                                          void* const* feat_dst, const int64_t* feat_ld, const int* feat_first,
+                                          int64_t batch, int num_features, int dim, int itself, int mask_feature0,
                                           void* g0_hi, void* g0_lo, int64_t ld_g0, void* stream) {
   using namespace dlrm;
-  if (!feat_dst || !feat_ld) return set_error("interact_bwd_p2p: NULL route");
+  if (!feat_dst || !feat_ld || !feat_first) return set_error("interact_bwd_p2p: NULL route");
   if (num_features > 64) return set_error("interact_bwd_p2p: num_features=%d > 64", num_features);
+  const int ndst = feat_first[num_features];
+  if (feat_first[0] != 0 || ndst < num_features || ndst > ROUTE_MAX_DST)
+    return set_error("interact_bwd_p2p: %d destinations for %d features (max %d)", ndst, num_features, ROUTE_MAX_DST);
   FeatRoute r = {};
-  for (int i = 0; i < num_features; ++i) {
-    if (!feat_dst[i]) return set_error("interact_bwd_p2p: feat_dst[%d] is NULL", i);
-    r.base[i] = static_cast<float*>(feat_dst[i]);
-    r.ld[i] = feat_ld[i];
+  for (int i = 0; i <= num_features; ++i) {
+    if (i && feat_first[i] <= feat_first[i - 1]) return set_error("interact_bwd_p2p: feature %d has no destination", i - 1);
+    r.first[i] = (unsigned char)feat_first[i];
+  }
+  for (int q = 0; q < ndst; ++q) {
+    if (!feat_dst[q]) return set_error("interact_bwd_p2p: feat_dst[%d] is NULL", q);
+    r.base[q] = static_cast<float*>(feat_dst[q]);
+    r.ld[q] = feat_ld[q];
   }
   return interact_bwd_launch(T, ldt, dR, lddr, nullptr, 0, &r, batch, num_features, dim, itself,
                              mask_feature0, g0_hi, g0_lo, ld_g0, stream);

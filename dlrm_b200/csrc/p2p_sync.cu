@@ -32,9 +32,14 @@ __global__ void __launch_bounds__(32) p2p_barrier_kernel(PeerPtrs sig, int rank,
     volatile int* remote = static_cast<volatile int*>(sig.p[t]) + rank;   // my slot on rank t
     *remote = e;
     volatile int* mine = static_cast<volatile int*>(sig.p[rank]) + t;     // rank t's slot on me
-    long long spins = 0;
+    // a lost peer must trap, not hang the GPU forever -- but ordinary host skew between ranks (seconds while
+    // one of them builds a plan or captures a graph) must not: the limit is 60 s of wall clock, not a spin count
+    unsigned long long t0 = 0;
     while (*mine < e) {
-      if (++spins > (1ll << 28)) __trap();   // a lost peer must trap, not hang the GPU forever
+      unsigned long long now;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+      if (t0 == 0) t0 = now;
+      else if (now - t0 > 60000000000ull) __trap();
     }
     __threadfence_system();
   }

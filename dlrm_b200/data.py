@@ -98,19 +98,24 @@ class HostBatch:
         return self.X.clone(), lS_o, lS_i, self.target.clone()
 
 
-def fill_batch(hb: HostBatch, rng: np.random.Generator, ln_emb: Sequence[int], lmax: int = 10,
+def fill_batch(hb: HostBatch, rng: Optional[np.random.Generator], ln_emb: Sequence[int], lmax: int = 10,
                fixed: bool = False, per_table_L: Optional[Sequence[int]] = None,
-               round_targets: bool = True) -> HostBatch:
+               round_targets: bool = True, table_seeds=None) -> HostBatch:
+    """table_seeds: one seed (anything np.random.default_rng accepts) per table -> every table draws from its own
+    stream, so that all ranks storing rows of a table see the same indices; X / target are then left alone."""
     L = hb.layout
     B = L.B
-    hb.X.numpy()[...] = rng.random((B, L.m_den), dtype=np.float32)
-    t = rng.random((B, 1), dtype=np.float32)
-    hb.target.numpy()[...] = np.round(t) if round_targets else t
+    if table_seeds is None:
+        hb.X.numpy()[...] = rng.random((B, L.m_den), dtype=np.float32)
+        t = rng.random((B, 1), dtype=np.float32)
+        hb.target.numpy()[...] = np.round(t) if round_targets else t
     off = hb.offsets
     idx_all = hb.indices_t.numpy()
     pos = 0
     for k, R in enumerate(ln_emb):
         R = int(R)
+        if table_seeds is not None:
+            rng = np.random.default_rng(table_seeds[k])
         if per_table_L is not None:
             lens = np.full(B, int(per_table_L[k]), dtype=np.int64)
         elif fixed:

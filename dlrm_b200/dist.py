@@ -1,14 +1,15 @@
-"""One-process-per-GPU DLRM: table-wise sharded embeddings + data-parallel MLPs.
+"""One-process-per-GPU DLRM: sharded embeddings (table-wise + row-split) + data-parallel MLPs.
 
 Replaces `DLRM_Net.distributed_forward` (dlrm_s_pytorch.py:528-585) and `extend_distributed.py`
 (`get_my_slice` :47-51, `get_split_lengths` :54-62, `alltoall` :541-576 and its autograd pair
 `All2All_Req/Wait` :389-486, DDP of the MLPs :1329-1336):
 
-  * tables are split into contiguous slices over the ranks exactly like `get_my_slice`;
-  * every rank pools ITS tables for the GLOBAL batch (one gather launch), the pooled vectors are
-    exchanged so that every rank ends up with ALL tables for ITS batch slice, inside the
-    interaction operand T (forward), and the per-bag gradients travel the opposite way (backward)
-    into the fused coalesce + row-wise-Adagrad update of the owning rank;
+  * where a table lives is decided by `placement.plan` (cost-balanced; hot / huge tables are ROW-SPLIT over
+    all ranks) -- `placement.contiguous` reproduces the reference's `get_my_slice` slices;
+  * every rank pools ITS shards for the GLOBAL batch, the pooled vectors (partial sums for a row-split
+    table, added on arrival) are exchanged so that every rank ends up with ALL tables for ITS batch slice,
+    inside the interaction operand T (forward), and the per-bag gradients travel the opposite way
+    (backward) into the fused coalesce + row-wise-Adagrad update of every rank storing rows of the table;
   * the MLPs are replicated; their gradients are averaged with one NCCL all-reduce (DDP semantics:
     mean over ranks of the local-mean-loss gradients; embedding gradients are NOT averaged -- the
     reference's all-to-all backward simply routes them, `extend_distributed.py:467-486`).
@@ -116,54 +117,118 @@ def init_distributed(backend: Optional[str] = None):
     return rank, world
 
 
+# one cudaIpcOpenMemHandle per exported allocation and PROCESS (a second open of the same handle fails)
+_IPC_BASES = {}
+_KEEP_ALIVE = []     # exported buffers must outlive their importers' mappings: engines are never freed
+
+
 # ---------------------------------------------------------------------------- the sharded engine
 class DistEngine:
+    """exchange="p2p" (default on an NVSwitch box): both exchanges ride on our kernels' stores through
+    peer-mapped memory, any placement.  exchange="nccl": `all_to_all_single` (the reference's collective),
+    contiguous whole-table placement only."""
+
     def __init__(self, m_spa: int, ln_emb: Sequence[int], ln_bot: Sequence[int], ln_top: Sequence[int], *,
                  local_batch: int, device=None, gemm: str = "tc", loss: str = "bce", exchange: str = "nccl",
-                 **kw):
+                 placement=None, cost: Optional[Sequence[float]] = None, **kw):
+        from . import placement as P, sharding as S
         from .engine import Engine
 
         if gemm == "simt":
             raise SystemExit("ERROR: dlrm_b200.dist runs on the tensor-core path (gemm='tc' or 'tc_bf16')")
         self.rank, self.world = dist.get_rank(), dist.get_world_size()
         self.Tg = len(ln_emb)
-        if self.Tg < self.world:
-            raise SystemExit("ERROR: only (%d) sparse features for (%d) devices, table partitions will fail"
-                             % (self.Tg, self.world))
         self.D = int(m_spa)
         self.B = int(local_batch)
         self.Bg = self.B * self.world
+        self.exchange = exchange
+        if exchange not in ("nccl", "p2p"):
+            raise SystemExit("ERROR: exchange must be nccl or p2p")
+        if placement is None:
+            if exchange == "nccl":
+                if self.Tg < self.world:
+                    raise SystemExit("ERROR: only (%d) sparse features for (%d) devices, table partitions will fail"
+                                     % (self.Tg, self.world))
+                placement = P.contiguous(ln_emb, self.world)
+            else:
+                placement = P.plan(ln_emb, cost if cost is not None else [1.0] * self.Tg, self.world)
+        self.pl = placement
+        if exchange == "nccl" and (self.pl.split_tables() or
+                                   [(s.table, s.rank) for s in sorted(self.pl.shards, key=lambda s: s.table)] !=
+                                   [(s.table, s.rank) for s in sorted(P.contiguous(ln_emb, self.world).shards,
+                                                                      key=lambda s: s.table)]):
+            raise SystemExit("ERROR: exchange=nccl supports the reference's contiguous table slices only")
+        self.mine = self.pl.of_rank(self.rank)
+        self.Tl = len(self.mine)
         self.slices = table_slices(self.Tg, self.world)
         self.t0, self.t1 = self.slices[self.rank]
-        self.Tl = self.t1 - self.t0
-        self.exchange = exchange
         if device is None:
             device = "cuda:%d" % torch.cuda.current_device()
         self.device = torch.device(device)
-        self.eng = Engine(m_spa, list(ln_emb[self.t0:self.t1]), ln_bot, ln_top, n_features=self.Tg + 1,
-                          loss=loss, device=device, max_batch=self.B, gemm=gemm,
+        ek = S.engine_kwargs(self.pl, self.rank, self.Tg)
+        self.eng = Engine(m_spa, ek["ln_emb"], ln_bot, ln_top, n_features=ek["n_features"], shards=ek["shards"],
+                          split_slots=ek["split_slots"], loss=loss, device=device, max_batch=self.B, gemm=gemm,
                           sigmoid_top=len(ln_top) - 2, **kw)
         e = self.eng
         f32 = torch.float32
-        self.send_splits, self.recv_splits = a2a_splits(self.Tg, self.world, self.rank, self.B, self.D)
-        self.send = torch.zeros(self.Bg * self.Tl * self.D, dtype=f32, device=self.device)
-        self.recv = torch.zeros(sum(self.recv_splits), dtype=f32, device=self.device)
-        self.gsend = torch.zeros(sum(self.recv_splits), dtype=f32, device=self.device)
-        self.grecv = torch.zeros(self.Bg * self.Tl * self.D, dtype=f32, device=self.device)
-        e.gather_fn, e.update_fn, e.dense_sync_fn = self._gather, self._update, self._dense_sync
+        e.dense_sync_fn = self._dense_sync
         self._flag = torch.zeros(1, dtype=f32, device=self.device)
         if exchange == "p2p":
             self._setup_p2p()
             e.gather_fn, e.update_fn = self._gather_p2p, self._update_p2p
-        elif exchange != "nccl":
-            raise SystemExit("ERROR: exchange must be nccl or p2p")
+        else:
+            self.send_splits, self.recv_splits = a2a_splits(self.Tg, self.world, self.rank, self.B, self.D)
+            self.send = torch.zeros(self.Bg * self.Tl * self.D, dtype=f32, device=self.device)
+            self.recv = torch.zeros(sum(self.recv_splits), dtype=f32, device=self.device)
+            self.gsend = torch.zeros(sum(self.recv_splits), dtype=f32, device=self.device)
+            self.grecv = torch.zeros(self.Bg * self.Tl * self.D, dtype=f32, device=self.device)
+            e.gather_fn, e.update_fn = self._gather, self._update
 
     # ------------------------------------------------------------------ peer-mapped exchange
+    def _export(self, t):
+        """handle of the cudaMalloc block holding t + t's byte offset inside it"""
+        import ctypes as C
+        from . import _lib as _l
+
+        h = C.create_string_buffer(64)
+        off = C.c_int64()
+        _l.check(self.eng.lib.dlrm_b200_ipc_export(t.data_ptr(), h, C.byref(off)), "ipc_export")
+        return h.raw, int(off.value)
+
+    def _import(self, handle, offset):
+        import ctypes as C
+        from . import _lib as _l
+
+        key = (self.device.index, handle)
+        if key not in _IPC_BASES:
+            base = C.c_void_p()
+            _l.check(self.eng.lib.dlrm_b200_ipc_open(handle, self.device.index, C.byref(base)), "ipc_open")
+            _IPC_BASES[key] = base.value
+        return _IPC_BASES[key] + offset
+
+    def share(self, tensors):
+        """All-gather the IPC handles of `tensors` (same list on every rank); returns ptrs[rank][i] usable by
+        kernels of THIS device (own tensors: their plain pointers)."""
+        torch.cuda.synchronize()
+        _KEEP_ALIVE.append(list(tensors))
+        if self.world == 1:
+            return [[t.data_ptr() for t in tensors]]
+        mine = tuple(self._export(t) for t in tensors)
+        allh = [None] * self.world
+        dist.all_gather_object(allh, mine)
+        out = []
+        for r in range(self.world):
+            if r == self.rank:
+                out.append([t.data_ptr() for t in tensors])
+            else:
+                out.append([self._import(hd, off) for hd, off in allh[r]])
+        return out
+
     def _setup_p2p(self):
-        """Map every rank's interaction operand T and gradient receive buffer into this process (CUDA IPC
-        over NVLink).  Both directions PUSH: the gather stores pooled rows into the T of the rank that owns
-        the sample, interact_bwd stores per-table gradient rows into the receive buffer of the table's owner;
-        every load on the data path stays local (L2-cacheable)."""
+        """Map every rank's interaction operand (+ partial-sum area) and gradient receive buffer into this process
+        (CUDA IPC over NVLink).  Both directions PUSH: the gather stores pooled rows into the buffer of the rank
+        that owns the sample, interact_bwd stores per-table gradient rows into the receive buffer of every rank
+        storing rows of the table; every load on the data path stays local (L2-cacheable)."""
         import ctypes as C
 
         e = self.eng
@@ -173,64 +238,49 @@ class DistEngine:
         # rank; the two streams may interleave differently across ranks, so they must not share slots.
         self._sig = torch.zeros(32, dtype=torch.int32, device=self.device)
         self._epoch = torch.zeros(2, dtype=torch.int32, device=self.device)
-        torch.cuda.synchronize()
-        from . import _lib as _l
-
-        def export(t):
-            # handle of the cudaMalloc block holding t + t's byte offset inside it
-            h = C.create_string_buffer(64)
-            off = C.c_int64()
-            _l.check(e.lib.dlrm_b200_ipc_export(t.data_ptr(), h, C.byref(off)), "ipc_export")
-            return h.raw, int(off.value)
-
+        W, B, D = self.world, self.B, self.D
         # gradient receive buffer: slab s = [B, Tl, D] written by rank s's interact_bwd (push over NVLink)
-        self._grecv_p2p = torch.zeros(self.world * self.B * max(self.Tl, 1) * self.D, dtype=torch.float32,
-                                      device=self.device)
-        torch.cuda.synchronize()
-        mine = tuple(export(t) for t in (e.Tbuf, self._grecv_p2p, self._sig, e.dense_grad))
-        allh = [None] * self.world
-        dist.all_gather_object(allh, mine)
-        self._ipc_bases = {}
-        pT, pdT, psig, pgrad = [], [], [], []
-        col = gather_route(self.Tg, self.world, self.rank, self.D) * 4
-
-        def imp(handle, offset):
-            if handle not in self._ipc_bases:       # one open per exported allocation
-                base = C.c_void_p()
-                _l.check(e.lib.dlrm_b200_ipc_open(handle, self.device.index, C.byref(base)), "ipc_open")
-                self._ipc_bases[handle] = base.value
-            return self._ipc_bases[handle] + offset
-
-        for r in range(self.world):
-            if r == self.rank:
-                ptrs = [e.Tbuf.data_ptr(), self._grecv_p2p.data_ptr(), self._sig.data_ptr(), e.dense_grad.data_ptr()]
-            else:
-                ptrs = [imp(hd, off) for hd, off in allh[r]]
-            pT.append(ptrs[0] + col)
-            pdT.append(ptrs[1])
-            psig.append(ptrs[2])
-            pgrad.append(ptrs[3])
-        W = self.world
-        self._peer_T = (C.c_void_p * W)(*pT)
-        # update side: slab s of MY receive buffer holds the gradients of rank s's samples
-        slab = self.B * self.Tl * self.D * 4
+        self._grecv_p2p = torch.zeros(W * B * max(self.Tl, 1) * D, dtype=torch.float32, device=self.device)
+        ptrs = self.share([e.TP, self._grecv_p2p, self._sig, e.dense_grad])
+        pTP = [p[0] for p in ptrs]
+        pdT = [p[1] for p in ptrs]
+        psig = [p[2] for p in ptrs]
+        pgrad = [p[3] for p in ptrs]
+        # gather: pooled rows -> TP of the sample's owner at the engine's (globally consistent) route offsets
+        self._peer_TP = (C.c_void_p * W)(*pTP)
+        e.peer = (self._peer_TP, W, B)
+        # update: slab s of MY receive buffer holds the gradient rows of rank s's samples, [B][Tl][D]
+        slab = B * self.Tl * D * 4
         self._peer_dT = (C.c_void_p * W)(*[self._grecv_p2p.data_ptr() + s_ * slab for s_ in range(W)])
-        # interact_bwd side: feature 1 + t -> slab `rank` of the owner of table t; feature 0 stays local
-        dst, ld = [e.dT.data_ptr()], [e.F * self.D]
-        for owner, off, ldr in push_route(self.Tg, W, self.rank, self.B, self.D):
-            dst.append(pdT[owner] + off * 4)
-            ld.append(ldr)
-        assert len(dst) == e.F
-        e.dT_route = ((C.c_void_p * e.F)(*dst), (C.c_int64 * e.F)(*ld))
+        e.peer_dY = (self._peer_dT, W, B)
+        e.route_dy = [j * D for j in range(self.Tl)]
+        e.dy_stride = self.Tl * D
+        # interact_bwd: feature 0 stays local; feature 1 + t goes to slab `rank` of every rank storing rows of t
+        dst, ld, first = [e.dT.data_ptr()], [e.F * D], [0, 1]
+        for t in range(self.Tg):
+            for s in self.pl.of_table(t):
+                own = self.pl.of_rank(s.rank)
+                j = own.index(s)
+                dst.append(pdT[s.rank] + ((self.rank * B) * len(own) + j) * D * 4)
+                ld.append(len(own) * D)
+            first.append(len(dst))
+        n = len(dst)
+        e.dT_route = ((C.c_void_p * n)(*dst), (C.c_int64 * n)(*ld), (C.c_int * (e.F + 1))(*first))
         self._peer_sig = [(C.c_void_p * W)(*[p + 64 * ch for p in psig]) for ch in range(2)]
         self._peer_grad = (C.c_void_p * W)(*pgrad)
         self.own_sync = os.environ.get("DLRM_P2P_NCCL_SYNC") != "1"   # our kernels instead of NCCL all_reduce
-        if self.own_sync:
+        if self.world == 1:
+            e.dense_sync_fn = None            # nothing to average
+        elif self.own_sync:
             e.dense_sync_fn = self._dense_sync_p2p
-        dist.barrier()
+        _KEEP_ALIVE.append(self)
+        if self.world > 1:
+            dist.barrier()
 
     def _barrier(self, channel: int = 0):
         """Device-side ordering across ranks on the current stream (no host sync)."""
+        if self.world == 1:
+            return
         if getattr(self, "own_sync", False):
             from . import _lib
             from .engine import _stream
@@ -254,50 +304,18 @@ class DistEngine:
         self._barrier(1)      # every slice has been written back everywhere
 
     def _gather_p2p(self, sp, link):
-        from . import _lib
-        from .engine import _stream
-
         e = self.eng
-        if not link:
-            self._barrier()   # inference loops: peers must be done reading T of the previous batch
-        FD = e.F * self.D
-        if link:
-            e._ensure_link(sp.nnz_total if sp.include_last else sum(int(i.numel()) for i in sp.indices))
-        desc = e._fwd_desc(sp, range(self.Tl))
-        bdesc = e._bwd_desc_chunk(sp, list(range(self.Tl)))[0] if link else None
-        import ctypes as C
-
-        filt = link and e.use_filter
-        if filt:
-            e.filter.zero_()
-        _lib.check(e.lib.dlrm_b200_emb_bag_fwd_p2p(desc, bdesc, self.Tl, self.D, sp.batch, sp.idx_bytes,
-                                                   int(sp.include_last), e.link.data_ptr() if link else None,
-                                                   self._peer_T, self.world, self.B, FD, self.D,
-                                                   C.byref(e.dedup) if filt else None, _stream()),
-                   "emb_bag_fwd_p2p")
-        e.n_launch += 1
-        if link:
-            e._filtered = filt
-            if filt:
-                e.emb_classify(sp)
-        self._barrier()       # every rank's pooled rows have landed in every T
+        # Peers must be done reading my T / partial area (interaction of the previous batch) before anybody's
+        # pooled rows of this batch land in it.  Issued ALWAYS (training too): an evaluation forward between
+        # two training steps must not race with a faster rank's next gather (round-1 advisor finding).
+        self._barrier()
+        e.emb_forward(sp, link=link)          # routed: stores go to the owners' buffers over NVLink
+        self._barrier()                       # every rank's pooled rows / partial sums have landed everywhere
+        e.reduce_partials(self.B)
 
     def _update_p2p(self, sp, optimizer, clr):
-        from . import _lib
-        from .engine import _OPT, _stream
-
-        import ctypes as C
-
-        e = self.eng
         self._barrier()       # every rank's interact_bwd stores have landed in my receive buffer
-        bdesc, _ = e._bwd_desc_chunk(sp, list(range(self.Tl)))
-        _lib.check(e.lib.dlrm_b200_emb_bwd_update_p2p(bdesc, self.Tl, self.D, sp.batch, sp.idx_bytes,
-                                                      int(sp.include_last), e.link.data_ptr(), self._peer_dT,
-                                                      self.world, self.B, self.Tl * self.D, self.D,
-                                                      _OPT[optimizer], clr,
-                                                      1e-10, C.byref(e.dedup) if e._filtered else None, _stream()),
-                   "emb_bwd_update_p2p")
-        e.n_launch += 1
+        self.eng.emb_update(sp, optimizer=optimizer, lr=clr)
 
     # -- forward: pool local tables for the global batch, exchange, land in T
     def _gather(self, sp, link):
@@ -321,27 +339,134 @@ class DistEngine:
         dist.broadcast(self.eng.dense, src=0)
         self.eng.mark_params_changed()
 
-    def forward(self, X_local, sp_global_local_tables):
-        return self.eng.forward(X_local, sp_global_local_tables)
+    def forward(self, X_local, sp_local_shards):
+        return self.eng.forward(X_local, sp_local_shards)
 
-    def train_step(self, X_local, sp_global_local_tables, target_local, lr, optimizer="rwsadagrad"):
-        return self.eng.train_step(X_local, sp_global_local_tables, target_local, lr, optimizer)
+    def train_step(self, X_local, sp_local_shards, target_local, lr, optimizer="rwsadagrad"):
+        return self.eng.train_step(X_local, sp_local_shards, target_local, lr, optimizer)
+
+    def gather_bytes_per_step(self, lookups_per_sample: Sequence[float]) -> float:
+        """Expected embedding-row bytes this rank reads per step (its share of every table's lookups)."""
+        ld = 0.0
+        for s in self.mine:
+            ld += float(lookups_per_sample[s.table]) * (s.local_rows / max(s.rows, 1))
+        return ld * self.Bg * self.D * 4
+
+
+# ---------------------------------------------------------------------------- fixed-length (multi-hot) inputs
+class MultiHotExchange:
+    """Index side of a sharded step for fixed-length bags (the MLPerf multi-hot workload).
+
+    The reference hands every rank the whole global batch (dlrm_s_pytorch.py:528-544).  Here a rank receives
+    only ITS samples -- one packed pinned host buffer [X | target | table 0 [B, L_0] | table 1 ...], int32
+    indices, ONE H2D copy -- and `exchange()` pushes every table's block into the index buffer of the rank(s)
+    storing rows of that table (peer stores over NVLink, one launch), at slot `rank` of the [world, B, L_t]
+    global index array the gather / update kernels read.  Offsets are implicit (bag b = [b*L, (b+1)*L))."""
+
+    def __init__(self, de: DistEngine, hot: Sequence[int], m_den: int = 13, nsets: int = 2):
+        import ctypes as C
+
+        self.de, self.hot, self.m_den, self.nsets = de, [int(h) for h in hot], m_den, nsets
+        B, W, dev = de.B, de.world, de.device
+        i32 = torch.int32
+        # host / staging layout (bytes)
+        self.off_x = 0
+        self.off_t = B * m_den * 4
+        o = self.off_t + B * 4
+        o = (o + 15) // 16 * 16
+        self.off_idx = []
+        for L in self.hot:
+            self.off_idx.append(o)
+            o += (B * L * 4 + 15) // 16 * 16
+        self.nbytes = o
+        self.stage = [torch.zeros(self.nbytes, dtype=torch.uint8, device=dev) for _ in range(nsets)]
+        # global index arrays of my shards, per set
+        self.idxg = [[torch.zeros(W * B * self.hot[s.table], dtype=i32, device=dev) for s in de.mine]
+                     for _ in range(nsets)]
+        self.offs = {}
+        for L in sorted(set(self.hot)):
+            self.offs[L] = (torch.arange(W * B, dtype=torch.int64, device=dev) * L).to(i32)
+        self.X = [st[self.off_x:self.off_x + B * m_den * 4].view(torch.float32).view(B, m_den) for st in self.stage]
+        self.target = [st[self.off_t:self.off_t + B * 4].view(torch.float32).view(B, 1) for st in self.stage]
+        from .engine import SparseInput
+
+        self.sparse = [SparseInput(list(self.idxg[k]), [self.offs[self.hot[s.table]] for s in de.mine], W * B, False)
+                       for k in range(nsets)]
+        # copy lists: block of table t -> slot `rank` of idxg[j] on every rank storing rows of t
+        self._copies = []
+        if W > 1:
+            ptrs = de.share([t for k in range(nsets) for t in self.idxg[k]])
+        for k in range(nsets):
+            src, dst, nb = [], [], []
+            for t, L in enumerate(self.hot):
+                for s in de.pl.of_table(t):
+                    j = de.pl.of_rank(s.rank).index(s)
+                    nloc = len(de.pl.of_rank(s.rank))
+                    if W > 1:
+                        base = ptrs[s.rank][k * nloc + j] if s.rank != de.rank else self.idxg[k][j].data_ptr()
+                    else:
+                        base = self.idxg[k][j].data_ptr()
+                    src.append(self.stage[k].data_ptr() + self.off_idx[t])
+                    dst.append(base + de.rank * B * L * 4)
+                    nb.append(B * L * 4)
+            self._copies.append((src, dst, nb))
+        self._C = C
+
+    def host_buffer(self, pin=True):
+        buf = torch.zeros(self.nbytes, dtype=torch.uint8)
+        return buf.pin_memory() if pin and torch.cuda.is_available() else buf
+
+    def fill_host(self, buf, seed: int, step: int, rows: Sequence[int]):
+        """This rank's samples of global step `step` (dlrm_b200/mlperf.py generator) into a host buffer."""
+        from . import mlperf as M
+
+        de, B = self.de, self.de.B
+        X, T = M.dense_and_targets(seed, step, de.rank * B, B, self.m_den)
+        buf[self.off_x:self.off_x + B * self.m_den * 4].view(torch.float32).view(B, self.m_den).copy_(torch.from_numpy(X))
+        buf[self.off_t:self.off_t + B * 4].view(torch.float32).view(B, 1).copy_(torch.from_numpy(T))
+        idx = M.multi_hot_batch(seed, step, rows, self.hot, de.rank * B, B, dtype=np.int32)
+        for t, a in enumerate(idx):
+            buf[self.off_idx[t]:self.off_idx[t] + a.size * 4].view(torch.int32).copy_(torch.from_numpy(a.reshape(-1)))
+        return buf
+
+    def upload(self, k: int, buf, non_blocking=True):
+        self.stage[k].copy_(buf, non_blocking=non_blocking)
+        return self.nbytes
+
+    def exchange(self, k: int):
+        """Push the staged index blocks of set k to their owners (current stream).  The consumers' gather is
+        ordered behind it by the pre-gather barrier of DistEngine._gather_p2p."""
+        from . import _lib
+        from .engine import _stream
+
+        C = self._C
+        src, dst, nb = self._copies[k]
+        for c0 in range(0, len(src), 64):
+            n = len(src[c0:c0 + 64])
+            _lib.check(self.de.eng.lib.dlrm_b200_block_copy((C.c_void_p * n)(*src[c0:c0 + 64]),
+                                                            (C.c_void_p * n)(*dst[c0:c0 + 64]),
+                                                            (C.c_int64 * n)(*nb[c0:c0 + 64]), n, _stream()),
+                       "block_copy")
+            self.de.eng.n_launch += 1
 
 
 # ---------------------------------------------------------------------------- synthetic sharded batches
 def make_sharded_batch(step_seed: int, ln_emb: Sequence[int], rank: int, world: int, local_batch: int,
-                       m_den: int = 13, lmax: int = 10, pin: bool = True):
-    """Rank-local view of one GLOBAL synthetic batch: indices of the rank's tables for all
-    world*local_batch samples (packed format) + the rank's slice of dense features and targets.
-    Every table / slice has its own seed, so all ranks agree on the global batch."""
+                       m_den: int = 13, lmax: int = 10, pin: bool = True, placement=None):
+    """Rank-local view of one GLOBAL synthetic batch of the `--data-generation=random` distribution (variable
+    bag lengths): indices of the tables the rank stores rows of, for all world*local_batch samples (packed
+    format, one entry per local shard) + the rank's slice of dense features and targets.  Every table has its
+    own seed, so all ranks agree on the global batch."""
     from .data import HostBatch, PackedLayout, fill_batch
+    from . import placement as P
 
-    t0, t1 = table_slices(len(ln_emb), world)[rank]
-    rows = list(ln_emb[t0:t1])
+    pl = placement if placement is not None else P.contiguous(ln_emb, world)
+    tabs = [s.table for s in pl.of_rank(rank)]
+    rows = [int(ln_emb[t]) for t in tabs]
     Bg = local_batch * world
     cap = int(Bg * sum(min(int(r), lmax) for r in rows))
-    hb = HostBatch(PackedLayout(Bg, len(rows), m_den, cap), pin)
-    fill_batch(hb, np.random.default_rng([step_seed, 7, rank]), rows, lmax)
+    hb = HostBatch(PackedLayout(Bg, len(rows), m_den, max(cap, 1)), pin)
+    fill_batch(hb, None, rows, lmax, table_seeds=[(step_seed, 7, t) for t in tabs])
     rng = np.random.default_rng([step_seed, 11])
     Xg = rng.random((Bg, m_den), dtype=np.float32)
     Tg = np.round(rng.random((Bg, 1), dtype=np.float32))
@@ -351,164 +476,3 @@ def make_sharded_batch(step_seed: int, ln_emb: Sequence[int], rank: int, world: 
     if pin and torch.cuda.is_available():
         X, T = X.pin_memory(), T.pin_memory()
     return hb, X, T
-
-
-# ---------------------------------------------------------------------------- bench entry (bench.py --gpus N)
-def bench_main(args, CFG, metric_name, config_dict, ClockSampler):
-    from .data import DeviceBatch
-
-    rank, world = init_distributed("nccl")
-    local = int(os.environ.get("LOCAL_RANK", str(rank)))
-    dev = "cuda:%d" % local
-    torch.cuda.set_device(local)
-    train = args.workload != "cfg1"
-    D, T, B = CFG["m_spa"], CFG["T"], CFG["B"]
-    ln_emb = [CFG["rows"]] * T
-    ln_top = [D + (T + 1) * T // 2] + CFG["top_tail"]
-    exchange = getattr(args, "exchange", "auto")
-    if exchange == "auto":
-        # capability check, same answer on every rank (one node): peer access between all GPU pairs
-        n = torch.cuda.device_count()
-        ok = world <= n and all(torch.cuda.can_device_access_peer(a, b)
-                                for a in range(world) for b in range(world) if a != b)
-        exchange = "p2p" if ok else "nccl"
-    de = DistEngine(D, ln_emb, CFG["ln_bot"], ln_top, local_batch=B, device=dev, gemm=args.gemm,
-                    exchange=exchange)
-    de.eng.init_params(100 + rank)
-    de.sync_dense_params_from_rank0()
-    de.eng.ensure_optimizer_state("rwsadagrad")
-    ring = []
-    for i in range(args.ring):
-        hb, X, Tt = make_sharded_batch(1000 + i, ln_emb, rank, world, B, 13, CFG["lmax"])
-        db = DeviceBatch(hb.layout, dev)
-        db.load(hb, non_blocking=False)
-        ring.append((hb, db, X, X.to(dev), Tt, Tt.to(dev)))
-    lr = 0.01
-
-    # K static staging buffers per rank; with the NCCL-free exchange the whole sharded step (K of them per
-    # graph, update of step j overlapping step j+1) is captured in one CUDA graph per rank
-    import types
-
-    Kp = 1
-    want_graph = (de.exchange == "p2p" and getattr(de, "own_sync", False)) or os.environ.get("DLRM_DIST_GRAPH") == "1"
-    want_graph = want_graph and not getattr(args, "no_graph", False)
-    if train and not getattr(args, "no_pipeline", False):
-        cand = getattr(args, "pipeline", 1)
-        if cand >= 1 and args.steps % cand == 0:
-            Kp = cand
-    stages = []
-    for j in range(Kp):
-        st = DeviceBatch(ring[0][0].layout, dev)
-        st.load(ring[0][0], non_blocking=False)
-        stages.append(types.SimpleNamespace(db=st, sparse=st.sparse, X=ring[0][3].clone(), target=ring[0][5].clone()))
-    graph = None
-    if want_graph:
-        from .engine import GraphedTrainStep, GraphedTrainSteps
-
-        try:
-            if train:
-                graph = GraphedTrainSteps(de.eng, stages, lr, "rwsadagrad")
-            else:
-                graph = GraphedTrainStep(de.eng, stages[0], lr, "rwsadagrad", train=False)
-        except Exception as ex:  # noqa: BLE001
-            if rank == 0:
-                print("dist: CUDA-graph capture failed (%s); running eagerly" % str(ex)[:200], flush=True)
-            graph = None
-
-    def run_round():
-        if graph is not None:
-            return graph.replay()
-        out = None
-        for j, st in enumerate(stages):
-            if train:
-                out = de.eng.train_step(st.X, st.sparse, st.target, lr, "rwsadagrad", join_update=(j == Kp - 1))
-            else:
-                out = de.eng.forward(st.X, st.sparse)
-        return out
-
-    def resident_round(i):
-        for j, st in enumerate(stages):
-            hb, db, Xh, Xd, Th, Td = ring[(i * Kp + j) % args.ring]
-            nbytes = db.layout.used(db.nnz)
-            st.db.buf[:nbytes].copy_(db.buf[:nbytes], non_blocking=True)
-            st.X.copy_(Xd, non_blocking=True)
-            st.target.copy_(Td, non_blocking=True)
-        return run_round()
-
-    rounds, wrounds = args.steps // Kp, max((args.warmup + Kp - 1) // Kp, 1)
-    for w in range(wrounds):
-        resident_round(w)
-    torch.cuda.synchronize()
-    dist.barrier()
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
-        time.sleep(0.25)
-    dist.barrier()
-    torch.cuda.synchronize()
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    t0 = time.time()
-    n0 = de.eng.n_launch
-    ev0.record()
-    for r in range(rounds):
-        resident_round(wrounds + r)
-    ev1.record()
-    torch.cuda.synchronize()
-    dist.barrier()
-    t1 = time.time()
-    launches = de.eng.n_launch - n0
-    ms = torch.tensor([ev0.elapsed_time(ev1) / args.steps], device=dev)
-    dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-    ms = float(ms.item())
-
-    # e2e: host batches (packed sparse part + dense slice) copied every step, loss read back
-    loss_host = torch.zeros(1).pin_memory()
-    h2d = 0
-
-    def e2e_round(i):
-        nonlocal h2d
-        for j, st in enumerate(stages):
-            hb, db, Xh, Xd, Th, Td = ring[(i * Kp + j) % args.ring]
-            h2d += st.db.load(hb)
-            st.X.copy_(Xh, non_blocking=True)
-            st.target.copy_(Th, non_blocking=True)
-            h2d += Xh.numel() * 4 + Th.numel() * 4
-        out = run_round()
-        loss_host.copy_(out.view(-1)[-1:], non_blocking=True)
-
-    for w in range(2):
-        e2e_round(w)
-    h2d = 0
-    torch.cuda.synchronize()
-    dist.barrier()
-    ev0.record()
-    for r in range(rounds):
-        e2e_round(r)
-    ev1.record()
-    torch.cuda.synchronize()
-    dist.barrier()
-    ms2 = torch.tensor([ev0.elapsed_time(ev1) / args.steps], device=dev)
-    dist.all_reduce(ms2, op=dist.ReduceOp.MAX)
-    ms2 = float(ms2.item())
-    if rank == 0:
-        clocks = sampler.stop(t0, t1)
-        Bg = B * world
-        line = {
-            "metric": metric_name(train), "value": Bg / (ms * 1e-3), "unit": "samples/s", "n_gpus": world,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None,
-            "dtype": {"simt": "fp32", "tc": "fp32 (bf16x3 split on tcgen05, fp32 accumulate)",
-                      "tc_bf16": "bf16"}[args.gemm],
-            "data": "synthetic", "config": config_dict(args, world),
-            "roofline": None, "cpu_baseline": None,
-            "e2e": {"value": Bg / (ms2 * 1e-3), "unit": "samples/s", "h2d_bytes_per_step": int(h2d / args.steps),
-                    "d2h_bytes_per_step": 4, "ms_per_step": ms2,
-                    "note": "per rank: packed pinned sparse batch (its tables, global batch) + dense slice, "
-                            "H2D every step, loss read back"},
-            "gpu_launches": int(launches), "exchange": de.exchange, "cuda_graph": graph is not None, "steps_per_graph": Kp,
-            "a2a_bytes_per_rank_per_step": int(2 * 4 * (sum(de.send_splits) - de.send_splits[rank])),
-            "clocks": clocks,
-        }
-        print(json.dumps(line), flush=True)
-    dist.barrier()
-    dist.destroy_process_group()

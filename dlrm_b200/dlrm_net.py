@@ -231,7 +231,8 @@ class DLRM_Net(nn.Module):
         sp = self._sparse(lS_o, lS_i)
         if sp.batch > eng.max_batch:
             eng._alloc_activations(sp.batch)
-        eng.emb_forward(sp, eng.Tbuf.view(-1)[eng.D:], eng.F * eng.D, eng.D)
+        eng.emb_forward(sp)
+        eng.reduce_partials(sp.batch)
         return [eng.Tbuf[:sp.batch, 1 + k, :] for k in range(eng.T)]
 
     def interact_features(self, x, ly):

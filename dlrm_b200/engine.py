@@ -71,7 +71,7 @@ class Engine:
                  *, op: str = "dot", itself: bool = False, sigmoid_bot: int = -1, sigmoid_top: int = -1,
                  loss: str = "bce", loss_threshold: float = 0.0, loss_ws=None, device="cuda:0",
                  max_batch: int = 2048, gemm: str = "simt", n_features: Optional[int] = None,
-                 interleave_momentum: bool = False):
+                 interleave_momentum: bool = False, shards=None, split_slots=None, small_rows_max: int = 256):
         if not torch.cuda.is_available():
             raise RuntimeError("dlrm_b200.Engine needs a CUDA device (B200, sm_100a); there is no CPU path")
         self.device = torch.device(device)
@@ -82,8 +82,28 @@ class Engine:
         self.ln_emb = [int(v) for v in ln_emb]
         self.ln_bot = [int(v) for v in ln_bot]
         self.ln_top = [int(v) for v in ln_top]
-        self.T = len(self.ln_emb)                       # tables stored on THIS device
-        self.F = int(n_features) if n_features else self.T + 1   # interaction features (global)
+        self.T = len(self.ln_emb)                       # table shards stored on THIS device
+        # What the local "tables" are (dlrm_b200/placement.py): shard j = rows [row_lo, row_lo + row_n) of global
+        # table `table` (part `part` of `nparts`; nparts == 1: the whole table).  Default: every table whole.
+        if shards is None:
+            shards = [dict(table=k, rows=n, row_lo=0, row_n=n, part=0, nparts=1) for k, n in enumerate(self.ln_emb)]
+        self.shards = [dict(s) for s in shards]
+        if [int(s["row_n"]) for s in self.shards] != self.ln_emb:
+            raise ValueError("ln_emb must list the LOCAL row count of every shard")
+        n_glob = max([int(s["table"]) for s in self.shards], default=-1) + 1
+        self.F = int(n_features) if n_features else n_glob + 1   # interaction features (global)
+        # row-split tables of the GLOBAL placement, (table, nparts) each: the rank that owns a sample adds the
+        # nparts partial sums of its bags (one slab of the partial area per part)
+        if split_slots is None:
+            seen = {}
+            for sh in self.shards:
+                if int(sh["nparts"]) > 1:
+                    seen[int(sh["table"])] = int(sh["nparts"])
+            split_slots = sorted(seen.items())
+        self.split_slots = [(int(t), int(n)) for t, n in split_slots]
+        self.slab_first = np.concatenate([[0], np.cumsum([n for _, n in self.split_slots])]).astype(np.int64)
+        self.slot_of = {t: i for i, (t, _) in enumerate(self.split_slots)}
+        self.small_rows_max = int(small_rows_max)
         self.op, self.itself = op, bool(itself)
         if op not in ("dot", "cat"):
             raise ValueError("arch_interaction_op=%s is not supported" % op)
@@ -155,8 +175,10 @@ class Engine:
         self.gather_fn = None       # (sp, link) -> fills Tbuf[:, 1:, :] for the LOCAL batch
         self.update_fn = None       # (sp, optimizer, clr) -> embedding update from dT[:, 1:, :]
         self.dense_sync_fn = None   # () -> make dense_grad slab 0 the cross-rank mean gradient
-        self.dT_route = None        # (void*[F], int64[F]): per-feature destination of interact_bwd's output
+        self.dT_route = None        # (void*[n], int64[n], int[F+1]): destinations of interact_bwd's rows per feature
         self.n_launch = 0            # kernels launched by this engine (bench: gpu_launches)
+        self.peer = None             # sharded runs: (peer_out void*[world], world, local batch) for the gather
+        self.peer_dY = None          #               (peer_dY void*[world], world, local batch) for the update
         # side streams: the gather runs beside the bottom MLP, the weight-gradient GEMMs and the
         # embedding update beside the dgrad chain (independent work; parallel branches in the graph)
         self.multi_stream = True
@@ -175,7 +197,13 @@ class Engine:
         dev, f32 = self.device, torch.float32
         self.max_batch = B
         D, F = self.D, self.F
-        self.Tbuf = torch.zeros((B, F, D), dtype=f32, device=dev)
+        # interaction operand T [B, F, D] followed by the partial-sum area of the row-split tables
+        # [slab][B][D] (one slab per (split table, part)); ONE allocation, so that a peer needs one mapping
+        n_slabs = int(self.slab_first[-1])
+        self.TP = torch.zeros(B * F * D + n_slabs * B * D, dtype=f32, device=dev)
+        self.Tbuf = self.TP[:B * F * D].view(B, F, D)
+        self.part = self.TP[B * F * D:]
+        self._set_default_routes()
         self.ldr = (self.num_int + 3) & ~3
         self.Rbuf = torch.zeros((B, self.ldr), dtype=f32, device=dev) if self.op == "dot" else None
         nb, nt = len(self.ln_bot) - 1, len(self.ln_top) - 1
@@ -196,6 +224,40 @@ class Engine:
         # launches to the gather side and the update time does not move (110 us in-step either way: the
         # row read-modify-write and the momentum accesses dominate), so it is OFF by default.
         self.use_filter = False
+
+    def is_small(self, j: int) -> bool:
+        """Tiny whole tables take the dense two-pass update (csrc/emb_small.cu) instead of the per-row lists."""
+        sh = self.shards[j]
+        return (int(sh["nparts"]) == 1 and self.ln_emb[j] <= self.small_rows_max and self.D % 4 == 0
+                and self.D <= 512 and not self.interleave)
+
+    def _set_default_routes(self):
+        """Single-GPU routes.  out: (offset, sample stride) of shard j's pooled rows inside TP; dy: offset of
+        shard j's gradient rows inside one sample of dT (sample stride F*D)."""
+        B, F, D = self.max_batch, self.F, self.D
+        self.route_out, self.route_dy = [], []
+        for sh in self.shards:
+            t = int(sh["table"])
+            if int(sh["nparts"]) == 1:
+                self.route_out.append(((1 + t) * D, F * D))
+            else:
+                slab = int(self.slab_first[self.slot_of[t]]) + int(sh["part"])
+                self.route_out.append((B * F * D + slab * B * D, D))
+            self.route_dy.append((1 + t) * D)
+        self.dy_stride = F * D
+
+    def reduce_partials(self, B: int):
+        """T[b, 1+t, :] = sum of the partial sums of every row-split table t (fixed part order)."""
+        if not self.split_slots:
+            return
+        n = len(self.split_slots)
+        feat = (C.c_int * n)(*[1 + t for t, _ in self.split_slots])
+        first = (C.c_int * (n + 1))(*[int(v) for v in self.slab_first])
+        # slabs are laid out with the ALLOCATED batch as their stride: reduce over the full capacity rows
+        _lib.check(self.lib.dlrm_b200_emb_reduce_partials(self.part.data_ptr(), self.Tbuf.data_ptr(), self.F * self.D,
+                                                          self.max_batch, self.D, feat, first, n, _stream()),
+                   "emb_reduce_partials")
+        self.n_launch += 1
 
     def _ensure_link(self, nnz_total: int):
         if self.link is None or self.link.numel() < 2 * nnz_total:
@@ -268,11 +330,13 @@ class Engine:
                     self.b[name][i].normal_(0.0, float(np.sqrt(1.0 / m)), generator=g)
 
     # ------------------------------------------------------------------ descriptors
-    def _fwd_desc(self, sp: SparseInput, tables=None):
+    def _fwd_desc(self, sp: SparseInput, tables=None, route=None):
+        """route: per-shard (offset, sample stride) of the pooled rows (None: the call-level [b, k, :] layout)."""
         ks = range(self.T) if tables is None else tables
         arr = (EmbFwdTable * len(ks))()
         for n, k in enumerate(ks):
             d = arr[n]
+            sh = self.shards[k]
             d.weight = self.tables.data_ptr() + int(self.row_base[k]) * self.ldw * 4
             d.ld = self.ldw
             d.indices = sp.indices[k].data_ptr() if sp.indices[k].numel() else 0
@@ -280,15 +344,22 @@ class Engine:
             d.row_weights = (self.row_weights.data_ptr() + int(self.row_base[k]) * 4
                              if self.row_weights is not None else None)
             d.nnz = sp.indices[k].numel()
-            d.rows = self.ln_emb[k]
+            d.rows = int(sh["rows"])
+            d.row_lo, d.row_n = int(sh["row_lo"]), int(sh["row_n"])
+            if route is not None:
+                d.out_off, d.out_stride = int(route[k][0]), int(route[k][1])
         return arr
 
-    def _bwd_desc(self, sp: SparseInput, tables=None):
+    def _bwd_desc(self, sp: SparseInput, tables=None, dy_off=None):
         ks = range(self.T) if tables is None else tables
         arr = (EmbBwdTable * len(ks))()
         base = 0
         for n, k in enumerate(ks):
             d = arr[n]
+            sh = self.shards[k]
+            d.row_lo, d.row_n = int(sh["row_lo"]), int(sh["row_n"])
+            if dy_off is not None:
+                d.use_dy_off, d.dy_off = 1, int(dy_off[k])
             d.weight = self.tables.data_ptr() + int(self.row_base[k]) * self.ldw * 4
             d.ld = self.ldw
             if self.interleave:
@@ -298,11 +369,12 @@ class Engine:
                 d.momentum = (self._momentum_sep.data_ptr() + int(self.row_base[k]) * 4
                               if self._momentum_sep is not None else None)
                 d.mom_stride = 1
-            d.head = self.head.data_ptr() + int(self.row_base[k]) * 4
+            # tiny tables are neither linked nor list-updated (head NULL): emb_small_update handles them
+            d.head = None if self.is_small(k) else self.head.data_ptr() + int(self.row_base[k]) * 4
             d.indices = sp.indices[k].data_ptr() if sp.indices[k].numel() else 0
             d.offsets = sp.offsets[k].data_ptr()
             d.nnz = sp.indices[k].numel()
-            d.rows = self.ln_emb[k]
+            d.rows = int(sh["rows"])
             d.pair_base = 0 if sp.include_last else base
             base += sp.indices[k].numel()
         total = sp.nnz_total if sp.include_last else base
@@ -313,35 +385,52 @@ class Engine:
         sig = self.sigmoid_bot if which == "bot" else self.sigmoid_top
         return ACT_SIGMOID if i == sig else ACT_RELU
 
-    def emb_forward(self, sp: SparseInput, out: torch.Tensor, stride_sample: int, stride_table: int,
-                    link: bool = False):
-        """One launch per <= 64 tables.  link=True (training) also threads every index occurrence
-        onto its per-row list (step 1 of the sort-free coalesce) inside the same kernel."""
+    def emb_forward(self, sp: SparseInput, out: Optional[torch.Tensor] = None, stride_sample: int = 0,
+                    stride_table: int = 0, link: bool = False):
+        """apply_emb for every local shard: one launch per <= 64 whole tables + one for the row-split shards.
+        out is None (the engine's own forward): pooled rows go where `route_out` says -- feature slot 1+t of the
+        interaction operand (of the rank that owns the sample, on a sharded run) for a whole table, the shard's
+        slab of the partial-sum area for a row-split one.  Explicit `out`: out[b, k, :] with the given strides.
+        link=True (training) also threads every index occurrence onto its per-row list (step 1 of the
+        sort-free coalesce) inside the same kernel."""
         chk = _lib.check
         if link:
             total = sp.nnz_total if sp.include_last else sum(int(i.numel()) for i in sp.indices)
             self._ensure_link(total)
-        for c0 in range(0, self.T, _lib.MAX_TABLES):
-            ks = list(range(c0, min(self.T, c0 + _lib.MAX_TABLES)))
-            desc = self._fwd_desc(sp, ks)
-            optr = out.data_ptr() + c0 * stride_table * 4
-            if link:
-                bdesc, _ = self._bwd_desc_chunk(sp, ks)
-                dd = C.byref(self.dedup) if self.use_filter else None
-                if self.use_filter and c0 == 0:
+        routed = out is None
+        route = self.route_out if routed else [(k * stride_table, stride_sample) for k in range(self.T)]
+        whole = [k for k in range(self.T) if int(self.shards[k]["nparts"]) == 1]
+        split = [k for k in range(self.T) if int(self.shards[k]["nparts"]) > 1]
+        use_filter = self.use_filter and not split and not any(self.is_small(k) for k in range(self.T))
+        peer = self.peer if routed else None
+        base = self.TP.data_ptr() if routed else out.data_ptr()
+        first = True
+        for group in (whole, split):
+            for c0 in range(0, len(group), _lib.MAX_TABLES):
+                ks = group[c0:c0 + _lib.MAX_TABLES]
+                desc = self._fwd_desc(sp, ks, route)
+                bdesc = self._bwd_desc_chunk(sp, ks)[0] if link else None
+                dd = C.byref(self.dedup) if (link and use_filter) else None
+                if link and use_filter and first:
                     self.filter.zero_()     # counters + suspect count
-                chk(self.lib.dlrm_b200_emb_bag_fwd_train(desc, bdesc, len(ks), self.D, sp.batch, sp.idx_bytes,
-                                                         int(sp.include_last), self.link.data_ptr(), optr,
-                                                         stride_sample, stride_table, dd, _stream()),
-                    "emb_bag_fwd_train")
-                self._filtered = self.use_filter
-            else:
-                chk(self.lib.dlrm_b200_emb_bag_fwd(desc, len(ks), self.D, sp.batch, sp.idx_bytes,
-                                                   int(sp.include_last), optr, stride_sample, stride_table,
-                                                   _stream()), "emb_bag_fwd")
-            self.n_launch += 1
-        if link and self.use_filter:
-            self.emb_classify(sp)
+                first = False
+                if peer is not None:
+                    chk(self.lib.dlrm_b200_emb_bag_fwd_p2p(desc, bdesc, len(ks), self.D, sp.batch, sp.idx_bytes,
+                                                           int(sp.include_last), self.link.data_ptr() if link else None,
+                                                           peer[0], peer[1], peer[2], 0, 0, dd, _stream()),
+                        "emb_bag_fwd_p2p")
+                elif link:
+                    chk(self.lib.dlrm_b200_emb_bag_fwd_train(desc, bdesc, len(ks), self.D, sp.batch, sp.idx_bytes,
+                                                             int(sp.include_last), self.link.data_ptr(), base,
+                                                             0, 0, dd, _stream()), "emb_bag_fwd_train")
+                else:
+                    chk(self.lib.dlrm_b200_emb_bag_fwd(desc, len(ks), self.D, sp.batch, sp.idx_bytes,
+                                                       int(sp.include_last), base, 0, 0, _stream()), "emb_bag_fwd")
+                self.n_launch += 1
+        if link:
+            self._filtered = use_filter
+            if use_filter:
+                self.emb_classify(sp)
 
     def mlp_forward(self, which: str, x: torch.Tensor, ldx: int, B: int, outs: List[torch.Tensor],
                     lds: List[int], upto: Optional[int] = None):
@@ -414,7 +503,8 @@ class Engine:
             ev = self._gather_events
             if ev is not None:
                 ev[0].record()
-            self.emb_forward(sp, self.Tbuf.view(-1)[self.D:], FD, self.D, link)
+            self.emb_forward(sp, link=link)
+            self.reduce_partials(B)
             if ev is not None:
                 ev[1].record()
         if self.op == "dot":
@@ -473,26 +563,53 @@ class Engine:
             self.n_launch += 1
         self._filtered = False
 
-    def _bwd_desc_chunk(self, sp, ks):
+    def _bwd_desc_chunk(self, sp, ks, dy_off=None):
         # pair_base must be global over ALL tables of the batch, not per chunk
-        arr, total = self._bwd_desc(sp, range(self.T))
+        arr, total = self._bwd_desc(sp, range(self.T), dy_off)
         sub = (EmbBwdTable * len(ks))()
         for n, k in enumerate(ks):
             C.memmove(C.byref(sub[n]), C.byref(arr[k]), C.sizeof(EmbBwdTable))
         return sub, total
 
-    def emb_update(self, sp: SparseInput, dY: torch.Tensor, stride_sample: int, stride_table: int,
-                   optimizer: str, lr: float, eps: float = 1e-10):
-        for c0 in range(0, self.T, _lib.MAX_TABLES):
-            ks = list(range(c0, min(self.T, c0 + _lib.MAX_TABLES)))
-            desc, _ = self._bwd_desc_chunk(sp, ks)
-            _lib.check(self.lib.dlrm_b200_emb_bwd_update(desc, len(ks), self.D, sp.batch, sp.idx_bytes,
-                                                         int(sp.include_last), self.link.data_ptr(),
-                                                         dY.data_ptr() + c0 * stride_table * 4,
-                                                         stride_sample, stride_table, _OPT[optimizer],
-                                                         lr, eps, C.byref(self.dedup) if self._filtered else None,
-                                                         _stream()), "emb_bwd_update")
+    def emb_update(self, sp: SparseInput, dY: Optional[torch.Tensor] = None, stride_sample: int = 0,
+                   stride_table: int = 0, optimizer: str = "rwsadagrad", lr: float = 0.01, eps: float = 1e-10):
+        """Fused embedding backward + sparse optimizer for every local shard (coalesce + row update in place).
+        dY is None: the gradient rows are where `route_dy` says (dT, or the receive slabs of a sharded run);
+        explicit dY: dY[b, k, :] with the given strides.  Tiny tables go through the dense two-pass kernels."""
+        routed = dY is None
+        dy_off = self.route_dy if routed else [k * stride_table for k in range(self.T)]
+        ss = self.dy_stride if routed else stride_sample
+        peer = self.peer_dY if routed else None
+        base = None if peer is not None else (self.dT.data_ptr() if routed else dY.data_ptr())
+        big = [k for k in range(self.T) if not self.is_small(k)]
+        small = [k for k in range(self.T) if self.is_small(k)]
+        for c0 in range(0, len(big), _lib.MAX_TABLES):
+            ks = big[c0:c0 + _lib.MAX_TABLES]
+            desc, _ = self._bwd_desc_chunk(sp, ks, dy_off)
+            dd = C.byref(self.dedup) if self._filtered else None
+            if peer is not None:
+                _lib.check(self.lib.dlrm_b200_emb_bwd_update_p2p(desc, len(ks), self.D, sp.batch, sp.idx_bytes,
+                                                                 int(sp.include_last), self.link.data_ptr(), peer[0],
+                                                                 peer[1], peer[2], ss, 0, _OPT[optimizer], lr, eps, dd,
+                                                                 _stream()), "emb_bwd_update_p2p")
+            else:
+                _lib.check(self.lib.dlrm_b200_emb_bwd_update(desc, len(ks), self.D, sp.batch, sp.idx_bytes,
+                                                             int(sp.include_last), self.link.data_ptr(), base, ss, 0,
+                                                             _OPT[optimizer], lr, eps, dd, _stream()), "emb_bwd_update")
             self.n_launch += 1
+        for c0 in range(0, len(small), 32):
+            ks = small[c0:c0 + 32]
+            desc, _ = self._bwd_desc_chunk(sp, ks, dy_off)
+            rows = sum(self.ln_emb[k] for k in ks)
+            need = int(self.lib.dlrm_b200_emb_bwd_small_scratch_bytes(rows, self.D, sp.batch))
+            if getattr(self, "small_scratch", None) is None or self.small_scratch.numel() * 4 < need:
+                self.small_scratch = torch.zeros(max(need // 4, 1), dtype=torch.float32, device=self.device)
+            _lib.check(self.lib.dlrm_b200_emb_bwd_small_update(
+                desc, len(ks), self.D, sp.batch, sp.idx_bytes, int(sp.include_last), base,
+                peer[0] if peer is not None else None, peer[1] if peer is not None else 0,
+                peer[2] if peer is not None else 0, ss, _OPT[optimizer], lr, eps, self.small_scratch.data_ptr(),
+                self.small_scratch.numel() * 4, _stream()), "emb_bwd_small_update")
+            self.n_launch += 2
 
     def mlp_backward(self, which: str, x_in: torch.Tensor, ldx: int, in_act: int, B: int,
                      acts: List[torch.Tensor], act_ld: List[int], gz: List[torch.Tensor],
@@ -674,7 +791,7 @@ class Engine:
         else:
             self.backward(X, sp, target)
             if self.T:
-                self.emb_update(sp, self.dT.view(-1)[self.D:], self.F * self.D, self.D, optimizer, clr)
+                self.emb_update(sp, optimizer=optimizer, lr=clr)
         if self.tc:
             if self.dense_sync_fn is not None:
                 self._dense_update_pack(-2, 0.0)      # fold the split-K slabs into slab 0
@@ -698,9 +815,9 @@ class Engine:
     # out of the GEMMs themselves.
     def _interact_bwd_routed(self, B, bot_last_act, g0h, g0l, ldg0, stream):
         """interact_bwd whose per-feature gradient rows go straight to their (possibly remote) consumers."""
-        dst, ld = self.dT_route
+        dst, ld, first = self.dT_route
         _lib.check(self.lib.dlrm_b200_interact_bwd_p2p(self.Tbuf.data_ptr(), self.F * self.D, self.dR.data_ptr(),
-                                                       self.ldr, dst, ld, B, self.F, self.D, int(self.itself),
+                                                       self.ldr, dst, ld, first, B, self.F, self.D, int(self.itself),
                                                        bot_last_act, g0h, g0l, ldg0, stream),
                    "interact_bwd_p2p")
 
@@ -921,7 +1038,8 @@ class Engine:
                 if self.gather_fn is not None:
                     self.gather_fn(sp, link)
                 else:
-                    self.emb_forward(sp, self.Tbuf.view(-1)[self.D:], FD, self.D, link)
+                    self.emb_forward(sp, link=link)
+                    self.reduce_partials(B)
         self._split(X, X.stride(0), B, self.ln_bot[0], self.tc_in["bot"][0])
         self._tc_mlp_forward("bot", B)
         if ms:
@@ -932,7 +1050,8 @@ class Engine:
             ev = self._gather_events
             if ev is not None:
                 ev[0].record()
-            self.emb_forward(sp, self.Tbuf.view(-1)[self.D:], FD, self.D, link)
+            self.emb_forward(sp, link=link)
+            self.reduce_partials(B)
             if ev is not None:
                 ev[1].record()
         rh, rl, ldrb = self.tc_in["top"][0]
@@ -985,17 +1104,20 @@ class Engine:
                 continue
             plans = [self.tc_plans["fwd"][(which, i)] for i in range(ntc)]
             self._make_chain(("fwd", which), plans, [-1] + list(range(ntc - 1)), [0] * ntc)
+            # dgrad chain first (one m-tile-major group), then every weight gradient
             plans, dep, onk = [], [], []
-            last_dgrad = -1             # position (in this chain) of the dgrad that produced gz_i
+            producer = {}               # layer i -> position of the dgrad that produced gz_i (absent: earlier kernel)
+            prev = -1
             for i in reversed(range(ntc)):
+                producer[i] = prev
                 pl = self.tc_plans["dgrad"].get((which, i))
-                produced_by = last_dgrad
                 if pl is not None:
-                    plans.append(pl); dep.append(produced_by); onk.append(0)
-                    last_dgrad = len(plans) - 1
-                plans.append(self.tc_plans["wgrad"][(which, i)]); dep.append(produced_by); onk.append(1)
-                if pl is None:
-                    last_dgrad = -1
+                    plans.append(pl); dep.append(prev); onk.append(0)
+                    prev = len(plans) - 1
+                else:
+                    prev = -1
+            for i in reversed(range(ntc)):
+                plans.append(self.tc_plans["wgrad"][(which, i)]); dep.append(producer[i]); onk.append(1)
             self._make_chain(("bwd", which), plans, dep, onk)
 
     def _make_chain(self, key, plans, dep, onk):
@@ -1051,7 +1173,7 @@ class Engine:
             # fused coalesce + sparse optimizer beside the bottom-MLP backward
             opt, clr = update
             upd = (lambda: self.update_fn(sp, opt, clr)) if self.update_fn is not None else \
-                (lambda: self.emb_update(sp, self.dT.view(-1)[self.D:], FD, self.D, opt, clr))
+                (lambda: self.emb_update(sp, optimizer=opt, lr=clr))
             if self.multi_stream:
                 self._fork(self.s_emb)
                 with torch.cuda.stream(self.s_emb):
@@ -1110,8 +1232,10 @@ class GraphedTrainStep:
     rate is baked into the graph (re-capture to change it)."""
 
     def __init__(self, eng: "Engine", stage, lr: float, optimizer: str = "rwsadagrad", warmup: int = 3,
-                 train: bool = True, X: Optional[torch.Tensor] = None, target: Optional[torch.Tensor] = None):
-        self.eng, self.stage, self.train = eng, stage, train
+                 train: bool = True, X: Optional[torch.Tensor] = None, target: Optional[torch.Tensor] = None,
+                 pre=None):
+        """pre: optional callable run (and captured) before the step, e.g. the index exchange of a sharded run."""
+        self.eng, self.stage, self.train, self.pre = eng, stage, train, pre
         # table-wise sharded runs: the dense slice / targets are separate static tensors
         self.X = X if X is not None else stage.X
         self.target = target if target is not None else stage.target
@@ -1135,6 +1259,8 @@ class GraphedTrainStep:
 
     def _eager(self):
         st = self.stage
+        if self.pre is not None:
+            self.pre()
         if self.train:
             return self.eng.train_step(self.X, st.sparse, self.target, self.lr, self.optimizer)
         return self.eng.forward(self.X, st.sparse)

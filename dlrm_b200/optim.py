@@ -57,7 +57,7 @@ class _Fused(torch.optim.Optimizer):
         if eng.T:
             if not linked:
                 eng.emb_link(sp)
-            eng.emb_update(sp, eng.dT.view(-1)[eng.D:], eng.F * eng.D, eng.D, self._name, clr, g["eps"])
+            eng.emb_update(sp, optimizer=self._name, lr=clr, eps=g["eps"])
         code = OPT_RWSADAGRAD if self._name == "rwsadagrad" else OPT_SGD
         if eng.tc:
             eng._dense_update_pack(code, clr, g["eps"])

@@ -46,6 +46,10 @@ enum { DLRM_GEMM_SIMT_FP32 = 0, DLRM_GEMM_TC_BF16X3 = 1, DLRM_GEMM_TC_BF16 = 2 }
 
 int dlrm_b200_abi_version(void);
 const char* dlrm_b200_last_error(void);
+/* Reads and clears the device error word of the current device (synchronises `stream`): bit 0 = an embedding
+ * index outside its table since the last check.  The only hidden state of the library: 256 bytes of device
+ * memory per GPU, allocated on first use. */
+int dlrm_b200_check_device_errors(void* stream);
 /* sm count / compute capability of `device`; error unless cc >= 10.0 */
 int dlrm_b200_device_info(int device, int* sm_count, int* cc_major, int* cc_minor);
 
@@ -63,8 +67,17 @@ typedef struct {
   const void* offsets;      /* [batch] (or [batch+1] when include_last) same type */
   const float* row_weights; /* NULL, or [rows]: v_W_l[k] (weighted pooling, :425-428) */
   int64_t nnz;
-  int64_t rows;             /* for bounds checks in debug builds */
+  int64_t rows;             /* rows of the WHOLE table: an index outside [0, rows) sets the device error word
+                             * (dlrm_b200_check_device_errors) and is read as row 0 / skipped; 0 = unchecked */
   int64_t ld;               /* row stride of `weight` in floats; 0 = dim (dense rows) */
+  /* Sharded placement (dlrm_b200/placement.py).  All zero = the call-level layout out[b, k, :].
+   * out_stride > 0: the pooled row of bag b goes to out (or the owner's peer buffer) + b_local*out_stride + out_off
+   *   -- a whole table lands in feature slot 1+t of the interaction operand, a row-split shard in its slab of
+   *   the partial-sum area (dlrm_b200_emb_reduce_partials adds the slabs).
+   * row_n > 0: `weight` holds rows [row_lo, row_lo + row_n) of the table; indices outside the range belong
+   *   to another shard and are skipped (a partial sum over this shard's rows). */
+  int64_t out_off, out_stride;
+  int64_t row_lo, row_n;
 } dlrm_emb_fwd_table_t;
 
 int dlrm_b200_emb_bag_fwd(const dlrm_emb_fwd_table_t* tables /*[host]*/, int num_tables, int dim,
@@ -102,6 +115,12 @@ typedef struct {
                          * ld = dim + 4 with momentum = weight + dim and mom_stride = ld keeps the
                          * row-wise Adagrad accumulator in the SAME DRAM burst as its row: the update then
                          * costs one activation per row instead of two (measured: profiles/). */
+  /* Sharded placement.  use_dy_off != 0: the gradient row of (bag b, this table) is at dY(b) + dy_off instead
+   * of dY(b) + k*dy_stride_table.  row_n > 0: `weight`/`momentum`/`head` hold rows [row_lo, row_lo + row_n)
+   * of the table; occurrences of other rows are another shard's.  head == NULL: this table is not linked and
+   * not updated by dlrm_b200_emb_bwd_update (tiny tables: dlrm_b200_emb_bwd_small_update). */
+  int64_t use_dy_off, dy_off;
+  int64_t row_lo, row_n;
 } dlrm_emb_bwd_table_t;
 
 /* Optional duplicate filter (dlrm_emb_dedup_t): at 1e6-row tables almost every row of a batch is
@@ -227,14 +246,16 @@ int dlrm_b200_interact_fwd_ex(const float* T, int64_t ldt, float* R, int64_t ldr
 int dlrm_b200_interact_bwd_ex(const float* T, int64_t ldt, const float* dR, int64_t lddr, float* dT,
                               int64_t lddt, int64_t batch, int num_features, int dim, int itself,
                               int mask_feature0, void* g0_hi, void* g0_lo, int64_t ld_g0, void* stream);
-/* Sharded variant: feature i's gradient rows are stored at feat_dst[i] + sample * feat_ld[i] (floats)
- * instead of dT.  On a table-wise sharded run feat_dst[1 + t] points into the receive buffer of the rank
- * that owns table t (peer-mapped over NVLink), which replaces the backward all-to-all of
- * dlrm_s_pytorch.py:545-560 / extend_distributed.py:alltoall backward; feat_dst[0] stays local. */
+/* Sharded variant: feature i's gradient rows are stored at feat_dst[q] + sample * feat_ld[q] (floats) for
+ * every destination q in [feat_first[i], feat_first[i+1]) instead of dT (at most 128 destinations in all).
+ * On a sharded run the destinations of feature 1 + t point into the receive buffers of the rank(s) storing
+ * table t (peer-mapped over NVLink; a row-split table has one on every rank), which replaces the backward
+ * all-to-all of dlrm_s_pytorch.py:545-560 / extend_distributed.py:alltoall backward; feature 0 stays local. */
 int dlrm_b200_interact_bwd_p2p(const float* T, int64_t ldt, const float* dR, int64_t lddr,
-                               void* const* feat_dst /*[host][F]*/, const int64_t* feat_ld /*[host][F]*/,
-                               int64_t batch, int num_features, int dim, int itself, int mask_feature0,
-                               void* g0_hi, void* g0_lo, int64_t ld_g0, void* stream);
+                               void* const* feat_dst /*[host][ndst]*/, const int64_t* feat_ld /*[host][ndst]*/,
+                               const int* feat_first /*[host][F+1]*/, int64_t batch, int num_features, int dim,
+                               int itself, int mask_feature0, void* g0_hi, void* g0_lo, int64_t ld_g0,
+                               void* stream);
 int dlrm_b200_interact_bwd(const float* T, int64_t ldt, const float* dR, int64_t lddr,
                            float* dT, int64_t lddt, int64_t batch, int num_features, int dim,
                            int itself, int mask_feature0, void* stream);
@@ -353,6 +374,38 @@ typedef struct {
 } dlrm_dense_layer_t;
 int dlrm_b200_dense_update_pack(const dlrm_dense_layer_t* layers /*[host]*/, int num_layers, int optimizer,
                                 float lr, float eps, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Sharded placement (dlrm_b200/placement.py): the pieces around the gather / update kernels.
+ * ------------------------------------------------------------------------------------------ */
+/* Tiny tables (a few to a few hundred rows, hit thousands of times per step at MLPerf batch sizes): dense
+ * two-pass coalesce + row update instead of the per-row list walk (csrc/emb_small.cu).  Same semantics as
+ * dlrm_b200_emb_bwd_update (grad.coalesce() + optim/rwsadagrad.py:117-143 / sparse SGD), deterministic.
+ * Every table needs use_dy_off; `scratch` holds the per-chunk partial sums
+ * (dlrm_b200_emb_bwd_small_scratch_bytes(total rows of the call, dim, batch) bytes). */
+int64_t dlrm_b200_emb_bwd_small_scratch_bytes(int64_t total_small_rows, int dim, int64_t batch);
+int dlrm_b200_emb_bwd_small_update(const dlrm_emb_bwd_table_t* tables /*[host]*/, int num_tables, int dim,
+                                   int64_t batch, int idx_bytes, int include_last, const float* dY,
+                                   const float* const* peer_dY /*[host][world] or NULL*/, int world,
+                                   int64_t batch_local, int64_t dy_stride_sample, int optimizer, float lr,
+                                   float eps, float* scratch, int64_t scratch_bytes, void* stream);
+/* Row-split tables: T[b, slot_feature[s], :] = sum of the slabs [slot_first[s], slot_first[s+1]) of
+ * partial ([slab][batch][dim]), in slab order. */
+int dlrm_b200_emb_reduce_partials(const float* partial, float* T, int64_t ldt, int64_t batch, int dim,
+                                  const int* slot_feature /*[host]*/, const int* slot_first /*[host][n+1]*/,
+                                  int num_slots, void* stream);
+/* n <= 64 contiguous blocks (16-byte aligned pointers and sizes) copied in ONE launch; destinations may be
+ * peer-mapped (the index exchange of a sharded step). */
+int dlrm_b200_block_copy(const void* const* src /*[host]*/, void* const* dst /*[host]*/,
+                         const int64_t* nbytes /*[host]*/, int n, void* stream);
+/* Device-side synthetic batch of the MLPerf multi-hot distribution (torchrec_dlrm/multi_hot.py:80-127):
+ * out[k] = [batch, hot[k]] indices (idx_bytes wide) of table table_ids[k] for global samples
+ * [sample0, sample0 + batch) of `step`; optional dense features X [batch, m_den] and rounded targets [batch].
+ * Bit-identical to dlrm_b200/mlperf.py (host). */
+int dlrm_b200_gen_multihot(void* const* out /*[host]*/, const int64_t* rows /*[host]*/, const int* hot /*[host]*/,
+                           const int* table_ids /*[host]*/, int num_tables, int idx_bytes, uint64_t seed,
+                           uint64_t step, int64_t sample0, int64_t batch, float* X, float* target, int m_den,
+                           void* stream);
 
 #ifdef __cplusplus
 }

@@ -190,7 +190,8 @@ def test_emb_update_with_duplicates(opt, D, rows, B, lmax, filtered):
 
     rng = np.random.default_rng(D + rows)
     ln_emb = [rows, rows * 2 + 1]
-    e = Engine(D, ln_emb, [4, D], [D + 3, 1], device=DEV, max_batch=B)
+    # filtered: the per-row list machinery for every table (tiny tables would otherwise take the dense path)
+    e = Engine(D, ln_emb, [4, D], [D + 3, 1], device=DEV, max_batch=B, small_rows_max=0 if filtered else 256)
     Ws = [rng.standard_normal((r, D)).astype(np.float32) for r in ln_emb]
     for k in range(2):
         e.table(k).copy_(torch.from_numpy(Ws[k]))
@@ -291,17 +292,23 @@ def test_interact_bwd_routed_equals_plain(F, D, itself):
     f0 = torch.zeros(B, D, device=DEV)
     slabA = torch.zeros(2, B, max(h, 1), D, device=DEV)
     slabB = torch.zeros(B, max(F - 1 - h, 1), D, device=DEV)
-    dst, ld = [f0.data_ptr()], [D]
+    dst, ld, first = [f0.data_ptr()], [D], [0, 1]
+    extra = torch.zeros(B, 3, D, device=DEV)       # the LAST feature has a second destination (a row-split table)
     for i in range(1, F):
         if i - 1 < h:
             dst.append(slabA[1].data_ptr() + (i - 1) * D * 4); ld.append(h * D)
         else:
             dst.append(slabB.data_ptr() + (i - 1 - h) * D * 4); ld.append((F - 1 - h) * D)
+        if i == F - 1:
+            dst.append(extra.data_ptr() + 2 * D * 4); ld.append(3 * D)
+        first.append(len(dst))
+    n = len(dst)
     _lib.check(lib.dlrm_b200_interact_bwd_p2p(T.data_ptr(), F * D, dR.data_ptr(), D + npairs,
-                                              (C.c_void_p * F)(*dst), (C.c_int64 * F)(*ld), B, F, D, itself, 1,
-                                              None, None, 0, s), "interact_bwd_p2p")
+                                              (C.c_void_p * n)(*dst), (C.c_int64 * n)(*ld), (C.c_int * (F + 1))(*first),
+                                              B, F, D, itself, 1, None, None, 0, s), "interact_bwd_p2p")
     torch.cuda.synchronize()
     ref = dT.view(B, F, D)
+    assert torch.equal(extra[:, 2], ref[:, F - 1]) and float(extra[:, :2].abs().sum()) == 0.0
     assert torch.equal(f0, ref[:, 0])
     assert torch.equal(slabA[1][:, :h], ref[:, 1:1 + h])
     assert torch.equal(slabB[:, :F - 1 - h], ref[:, 1 + h:])
