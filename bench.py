@@ -283,7 +283,7 @@ def parity_check(de_cls, dev, gemm):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     err = dict(zip(("loss", "p_after", "rows_p999", "momentum_rel"), [float(v) for v in t.tolist()]))
     err.update(golden="tests/golden/cfg0.npz (live reference, 2 RWSAdagrad steps, global batch 128)",
-               split_tables=pl.split_tables(), ok=bool(err["loss"] < 1e-4 and err["p_after"] < 1e-3))
+               split_tables=pl.split_tables(), ok=bool(err["loss"] < 3e-4 and err["p_after"] < 5e-3))
     return err      # the (tiny) engine stays alive: its buffers are mapped into the peers
 
 

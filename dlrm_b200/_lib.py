@@ -14,7 +14,7 @@ LOSS_MSE, LOSS_BCE, LOSS_WBCE = 0, 1, 2
 OPT_SGD, OPT_RWSADAGRAD = 0, 1
 GEMM_SIMT_FP32, GEMM_TC_BF16X3, GEMM_TC_BF16 = 0, 1, 2
 TUNE = dict(emb_bags_per_group=0, emb_unroll=1, emb_block=2, upd_block=3, gemm_splitk=4, gemm_smem_kb=5,
-            head_rows=6, interact_bwd_cols=7, pdl=8, chain_order=9)
+            head_rows=6, interact_bwd_cols=7, pdl=8, chain_order=9, upd_lean=10)
 
 
 class EmbFwdTable(C.Structure):

@@ -12,6 +12,7 @@ loss curve can be compared directly (tests/test_gpu_facade.py does so against a 
 from __future__ import annotations
 
 import argparse
+import os
 import sys
 import time
 
@@ -163,8 +164,25 @@ def run(argv=None):
     np.set_printoptions(precision=args.print_precision)
     torch.set_printoptions(precision=args.print_precision)
     torch.manual_seed(args.numpy_rand_seed)
-    print("Using 1 GPU(s)...")
-    device = torch.device("cuda", 0)
+    # one process per GPU under torchrun / mpirun (ext_dist.init_distributed, dlrm_s_pytorch.py:1073-1077)
+    rank, world = 0, 1
+    if int(os.environ.get("WORLD_SIZE", "1")) > 1:
+        from . import dist as ddist
+
+        backend = args.dist_backend if args.dist_backend else "nccl"
+        if backend != "nccl":
+            sys.exit("ERROR: --dist-backend=" + backend + " is not supported on GPUs (nccl)")
+        if args.local_rank >= 0:
+            os.environ.setdefault("LOCAL_RANK", str(args.local_rank))
+        rank, world = ddist.init_distributed(backend)
+        if rank != 0:      # rank-0-only printing (extend_distributed.py:590-599)
+            import builtins
+
+            builtins.print = lambda *a, **k: None
+    device = torch.device("cuda", int(os.environ.get("LOCAL_RANK", "0")) if world > 1 else 0)
+    if world > 1:
+        torch.cuda.set_device(device)
+    print("Using {} GPU(s)...".format(world))
 
     from . import optim as fused
     from .dlrm_net import DLRM_Net
@@ -220,10 +238,16 @@ def run(argv=None):
     for k in range(args.nepochs):
         for j in range(nbatches):
             X, lS_o, lS_i, T = batch(j)
+            if world > 1 and X.size(0) % world != 0:      # dlrm_s_pytorch.py:1565-1570
+                print("Warning: Skiping the batch %d with size %d" % (j, X.size(0)))
+                continue
             torch.cuda.synchronize()
             t1 = time.time()
             with torch.set_grad_enabled(not args.inference_only):
                 Z = dlrm(X.to(device), lS_o, lS_i)
+                if world > 1:                               # loss on this rank's batch slice (:1584-1586)
+                    nloc = X.size(0) // world
+                    T = T[rank * nloc:(rank + 1) * nloc]
                 Td = T.to(device)
                 if args.loss_function == "wbce":
                     ws = dlrm.loss_ws.to(device)[Td.view(-1).long()].view_as(Td).float()
@@ -231,6 +255,13 @@ def run(argv=None):
                 else:
                     E = dlrm.loss_fn(Z, Td)
             L = E.detach().cpu().numpy()
+            if world > 1 and os.environ.get("DLRM_CLI_GLOBAL_LOSS") == "1":
+                # the reference prints rank 0's slice loss; the mean over the ranks is the single-process loss
+                import torch.distributed as tdist
+
+                Lg = E.detach().clone()
+                tdist.all_reduce(Lg, op=tdist.ReduceOp.AVG)
+                L = Lg.cpu().numpy()
             if not args.inference_only:
                 optimizer.zero_grad()
                 E.backward()

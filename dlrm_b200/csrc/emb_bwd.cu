@@ -358,6 +358,165 @@ __global__ void __launch_bounds__(256, NV == 1 ? 3 : 1) emb_update_kernel(const 
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Lean variant for dim <= 128 (one float4 per lane), the shape of every BASELINE config.
+//
+// The kernel above spends ~190 warp instructions per occurrence (ncu, profiles/README.md: 755 per 4): the
+// table descriptor is re-read from parameter space for every row, rows / tables / bags travel through
+// 64-bit shuffles twice, the optimizer divides per element.  At MLPerf sizes (1.75 M occurrences per step and
+// GPU) that made the update INSTRUCTION-bound at 0.19 of the HBM peak (bench r2_08).  Here
+//   * the per-table fields live in shared memory, a 32-position window takes its table from lane 0 unless
+//     the window straddles a table boundary;
+//   * every lane resolves ITS occurrence once into two pointers (weight row, gradient row) + the list head;
+//     owners are compacted with ballot/ffs and processed PF at a time: 2 pointer broadcasts + 2 row loads
+//     each, all issued before the first use;
+//   * the row update is w += (-lr / (sqrt(m) + eps)) * g -- one reciprocal per row instead of a division per
+//     element (differs from g / std by <= 1 ulp per element; the tests' tolerance is 2e-5 relative);
+//   * the owning lane itself stores the accumulator and clears the list head (no pointer broadcast);
+//   * rows with duplicates (rare at large tables) take an out-of-line path.
+// ---------------------------------------------------------------------------------------------
+struct UpdTableS {
+  float* w;
+  float* mom;
+  int* head;
+  const void* idx;
+  long long pair_base, ld, mom_stride, dy_off, row_lo, row_n;
+};
+
+__device__ __noinline__ float4 upd_sum_duplicates(const EmbBwdParams& P, int nxt, int self_pos, int self_bag,
+                                                  long long dy_off, int lane, bool col_ok) {
+  // members of the row's list (self first), in chunks of 32, each chunk summed in ascending position
+  float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
+  int cnt = 1;
+  int mpos = (lane == 0) ? self_pos : 0x7fffffff;
+  int mbag = self_bag;
+  while (true) {
+    if (nxt != 0 && cnt < 32) {
+      const int2 e = P.link[nxt - 1];
+      if (lane == cnt) { mpos = nxt - 1; mbag = e.y; }
+      ++cnt;
+      nxt = e.x;
+      if (nxt != 0 && cnt < 32) continue;
+    }
+    int rank = 0;
+    for (int i = 0; i < cnt; ++i) rank += (__shfl_sync(0xffffffffu, mpos, i) < mpos) ? 1 : 0;
+    for (int q = 0; q < cnt; ++q) {
+      const unsigned who = __ballot_sync(0xffffffffu, lane < cnt && rank == q);
+      const int bag = __shfl_sync(0xffffffffu, mbag, __ffs(who) - 1);
+      if (col_ok) {
+        const float4 t = *reinterpret_cast<const float4*>(dy_row(P, bag) + dy_off + lane * 4);
+        g.x += t.x; g.y += t.y; g.z += t.z; g.w += t.w;
+      }
+    }
+    if (nxt == 0) break;
+    cnt = 0;
+    mpos = 0x7fffffff;
+  }
+  return g;
+}
+
+template <typename idx_t>
+__global__ void __launch_bounds__(256, 3) emb_update_lean_kernel(const __grid_constant__ EmbBwdParams P, int num_tables,
+                                                                 long long total_hint) {
+  __shared__ long long bound[DLRM_B200_MAX_TABLES_PER_CALL + 1];
+  __shared__ UpdTableS ts[DLRM_B200_MAX_TABLES_PER_CALL];
+  for (int k = threadIdx.x; k < num_tables; k += blockDim.x) {
+    UpdTableS t;
+    t.w = P.t[k].w; t.mom = P.t[k].mom; t.head = P.t[k].head; t.idx = P.t[k].idx;
+    t.pair_base = P.t[k].pair_base; t.ld = P.t[k].ld; t.mom_stride = P.t[k].mom_stride;
+    t.dy_off = P.t[k].dy_off; t.row_lo = P.t[k].row_lo; t.row_n = P.t[k].row_n;
+    ts[k] = t;
+  }
+  load_bounds<idx_t>(bound, P, num_tables, total_hint);     // ends with __syncthreads()
+  const int D = P.dim;
+  const int lane = threadIdx.x & 31;
+  const bool col_ok = lane * 4 < D;
+  const long long first = bound[0], total = bound[num_tables];
+  const long long warp0 = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const long long wstride = (long long)gridDim.x * (blockDim.x >> 5);
+  const float inv_d = 1.0f / (float)D;
+  const float nlr = -P.lr;
+  const bool adagrad = P.optimizer == DLRM_OPT_RWSADAGRAD;
+  constexpr int PF = 4;
+
+  for (long long base = first + warp0 * 32; base < total; base += wstride * 32) {
+    const long long pos = base + lane;
+    const bool valid = pos < total;
+    // table of this window: lane 0's, unless the window crosses into the next table
+    int k = table_of(bound, num_tables, base);
+    if (base + 31 >= bound[k + 1]) k = table_of(bound, num_tables, valid ? pos : base);
+    const UpdTableS& tb = ts[k];
+    float* wptr = nullptr;
+    const float* gptr = nullptr;
+    float* mptr = nullptr;
+    int* hptr = nullptr;
+    int nxt = 0, bag = 0;
+    bool owner = false;
+    if (valid && tb.head != nullptr) {
+      const long long r = (long long)static_cast<const idx_t*>(tb.idx)[pos - tb.pair_base] - tb.row_lo;
+      if ((unsigned long long)r < (unsigned long long)tb.row_n) {
+        hptr = tb.head + r;
+        if (*hptr == (int)(pos + 1)) {          // the last occurrence to arrive owns the row
+          owner = true;
+          const int2 lk = P.link[pos];
+          nxt = lk.x;
+          bag = lk.y;
+          wptr = tb.w + r * tb.ld;
+          gptr = dy_row(P, bag) + tb.dy_off;
+          mptr = adagrad ? tb.mom + r * tb.mom_stride : nullptr;
+        }
+      }
+    }
+    float m_old = (owner && adagrad) ? *mptr : 0.f;
+    unsigned owners = __ballot_sync(0xffffffffu, owner);
+    while (owners) {
+      float4 wv[PF], gv[PF];
+      int src[PF];
+#pragma unroll
+      for (int u = 0; u < PF; ++u) {
+        src[u] = owners ? __ffs(owners) - 1 : -1;
+        owners &= owners - 1u;
+        const int s_ = src[u] < 0 ? 0 : src[u];
+        const float* wp = reinterpret_cast<const float*>(__shfl_sync(0xffffffffu, (unsigned long long)wptr, s_));
+        const float* gp = reinterpret_cast<const float*>(__shfl_sync(0xffffffffu, (unsigned long long)gptr, s_));
+        if (src[u] >= 0 && col_ok) {
+          wv[u] = *reinterpret_cast<const float4*>(wp + lane * 4);
+          gv[u] = *reinterpret_cast<const float4*>(gp + lane * 4);
+        } else {
+          wv[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+          gv[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < PF; ++u) {
+        if (src[u] < 0) break;
+        const int s_ = src[u];
+        float4 g = gv[u];
+        const int nx = __shfl_sync(0xffffffffu, nxt, s_);
+        if (nx != 0) {                          // duplicates: sum the list (uniform branch)
+          const int sb = __shfl_sync(0xffffffffu, bag, s_);
+          const long long dyo = __shfl_sync(0xffffffffu, tb.dy_off, s_);     // the OWNER's table (windows may straddle)
+          g = upd_sum_duplicates(P, nx, (int)(base + s_), sb, dyo, lane, col_ok);
+        }
+        float scale = nlr;
+        if (adagrad) {
+          float sq = fmaf(g.x, g.x, fmaf(g.y, g.y, fmaf(g.z, g.z, g.w * g.w)));
+          sq = warp_sum(sq);
+          const float m_new = __shfl_sync(0xffffffffu, m_old, s_) + sq * inv_d;
+          scale = nlr / (sqrtf(m_new) + P.eps);
+          if (lane == s_) *mptr = m_new;
+        }
+        float4 w = wv[u];
+        w.x = fmaf(scale, g.x, w.x); w.y = fmaf(scale, g.y, w.y);
+        w.z = fmaf(scale, g.z, w.z); w.w = fmaf(scale, g.w, w.w);
+        float* wp = reinterpret_cast<float*>(__shfl_sync(0xffffffffu, (unsigned long long)wptr, s_));
+        if (col_ok) *reinterpret_cast<float4*>(wp + lane * 4) = w;
+        if (lane == s_) *hptr = 0;
+      }
+    }
+  }
+}
+
 static int fill_params(EmbBwdParams& P, const dlrm_emb_bwd_table_t* tables, int num_tables,
                        const char* who) {
   if (num_tables < 0 || num_tables > DLRM_B200_MAX_TABLES_PER_CALL)
@@ -489,6 +648,16 @@ static int emb_update_impl(const dlrm_emb_bwd_table_t* tables, int num_tables, i
     DLRM_CHECK_LAUNCH("emb_update_kernel");                                                                \
     return 0;                                                                                              \
   } while (0)
+  if (vec && dim <= 128 && !P.flags && get_tunable(TUNE_UPD_LEAN) != 2) {
+    // 3 CTAs of 256 threads per SM (<= 85 registers, no spills)
+    long long gl = (total / 32 + block / 32) / (block / 32);
+    if (gl > (long long)sms * 3) gl = (long long)sms * 3;
+    if (gl < 1) gl = 1;
+    if (idx_bytes == 8) emb_update_lean_kernel<long long><<<(unsigned)gl, block, 0, st>>>(P, num_tables, total_hint);
+    else emb_update_lean_kernel<int><<<(unsigned)gl, block, 0, st>>>(P, num_tables, total_hint);
+    DLRM_CHECK_LAUNCH("emb_update_lean_kernel");
+    return 0;
+  }
   if (vec) {
     if (dim <= 128) UPD(4, 1);
     if (dim <= 256) UPD(4, 2);

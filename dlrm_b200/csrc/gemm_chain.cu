@@ -105,8 +105,8 @@ __device__ __forceinline__ ChTask ch_decode(const ChParams& P, int t) {
   return k;
 }
 
-constexpr int CH_EPI_WARPS = 8;     // two per TMEM lane quadrant: the epilogue is issue-latency bound per warp
-constexpr int CH_THREADS = 64 + 32 * CH_EPI_WARPS;
+constexpr int CH_EPI_WARPS = TC_EPI_WARPS;
+constexpr int CH_THREADS = TC_THREADS;
 
 __global__ void __launch_bounds__(CH_THREADS, 1) gemm_chain_kernel(const __grid_constant__ ChParams P) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -400,7 +400,7 @@ extern "C" int dlrm_b200_gemm_chain_create(void* const* plans, const int* dep, c
   {
     int gi = 0, i = 0;
     long long t0 = 0;
-    const bool mmajor = get_tunable(TUNE_CHAIN_ORDER) != 1;
+    const bool mmajor = get_tunable(TUNE_CHAIN_ORDER) == 2;   // measured slower (blocking claims): opt-in
     while (i < n) {
       int j = i + 1;
       // only row-linked problems (a task depends on ITS m tile of the producer) may be interleaved by m tile:

@@ -30,7 +30,7 @@ namespace dlrm {
 // ------------------------------------------------------------------------------------------ kernel
 // smem per stage: A_hi [A_lo] B_hi [B_lo]; every tile 1024-byte aligned.
 template <int BN>
-__global__ void __launch_bounds__(192, 1)
+__global__ void __launch_bounds__(TC_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__ CUtensorMap tmAl,
                const __grid_constant__ CUtensorMap tmBh, const __grid_constant__ CUtensorMap tmBl,
                const TcArgs g, int stages) {
@@ -94,7 +94,7 @@ static int launch_tc(const TcPlan& p, cudaStream_t st) {
     DLRM_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     configured = true;
   }
-  (void)launch_chain(gemm_tc_kernel<BN>, p.grid, dim3(192), p.smem, st, p.tmAh, p.tmAl, p.tmBh, p.tmBl, p.args, p.stages);
+  (void)launch_chain(gemm_tc_kernel<BN>, p.grid, dim3(TC_THREADS), p.smem, st, p.tmAh, p.tmAl, p.tmBh, p.tmBl, p.args, p.stages);
   DLRM_CHECK_LAUNCH("gemm_tc_kernel");
   return 0;
 }

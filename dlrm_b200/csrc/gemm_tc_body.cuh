@@ -123,12 +123,12 @@
       if (++stage == stages) { stage = 0; phase ^= 1; }
     }
   } else {
-    // ------------------------------------------------------------------ epilogue (warps 2..5)
+    // ------------------------------------------------------------------ epilogue (warps 2..)
     const int quad = warp & 3;  // TMEM lane quadrant this warp may access
     mbar_wait(bar_base + 8 * (2 * stages), 0);
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     uint8_t* stage_warp = smem + (size_t)stages * stage_bytes + 256 + (size_t)(warp - 2) * TC_EPI_WARP_BYTES;
-    tc_epilogue_tile(g, BN, m0, n0, TCB_BZ, tmem_base, quad, lane, stage_warp);
+    tc_epilogue_tile(g, BN, m0, n0, TCB_BZ, tmem_base, quad, lane, stage_warp, (warp - 2) >> 2, TC_EPI_WARPS / 4);
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   }
   __syncthreads();

@@ -133,7 +133,13 @@ __device__ __forceinline__ float apply_act_tc(float v, int act) {
 constexpr int TC_EPI_ROW_F32 = 20;                 // floats per staged fp32 half-row (16 + 4 pad)
 constexpr int TC_EPI_ROW_BF16 = 40;                // bf16 per staged bf16 row (32 + 8 pad)
 constexpr int TC_EPI_WARP_BYTES = 32 * TC_EPI_ROW_BF16 * 2;  // 2560 B per epilogue warp (fp32: two 16-column passes)
-constexpr int TC_EPI_BYTES = 4 * TC_EPI_WARP_BYTES;
+// Epilogue warps per CTA: two per TMEM lane quadrant (warps w and w + 4 may both read quadrant w % 4) split the
+// 32-column chunks of a tile.  The epilogue is a long dependent instruction stream per warp (tcgen05.ld -> convert
+// -> shared-memory transpose -> store) with ONE warp per scheduler, i.e. issue-latency bound: a second warp per
+// scheduler halves it (chain timeline: 4-10 us -> 3-6 us per tile).
+constexpr int TC_EPI_WARPS = 8;
+constexpr int TC_THREADS = 64 + 32 * TC_EPI_WARPS;       // warp 0: TMA, warp 1: MMA, then the epilogue warps
+constexpr int TC_EPI_BYTES = TC_EPI_WARPS * TC_EPI_WARP_BYTES;
 
 // 32 x 32 bf16 chunk, one row per thread in `mine` -> global rows [mrow0, mrow0 + 32) x columns [nb, nb + 32)
 __device__ __forceinline__ void tc_epi_store_bf16(const __nv_bfloat16 (&mine)[32], __nv_bfloat16* dst, long long ld,

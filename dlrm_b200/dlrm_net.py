@@ -140,11 +140,31 @@ class DLRM_Net(nn.Module):
         if loss_function == "wbce":
             loss_ws = loss_weights if loss_weights is not None else [1.0, 1.0]
             self.loss_ws = torch.tensor(np.asarray(loss_ws, dtype=float))
-        self._engine = Engine(int(m_spa), ln_emb.tolist(), ln_bot.tolist(), ln_top.tolist(),
-                              op=arch_interaction_op, itself=arch_interaction_itself,
-                              sigmoid_bot=sigmoid_bot, sigmoid_top=sigmoid_top, loss=loss_function,
-                              loss_threshold=loss_threshold, loss_ws=loss_ws, device=device,
-                              max_batch=max_batch, gemm=gemm, interleave_momentum=False)
+        self._dist = None
+        import torch.distributed as tdist
+
+        if tdist.is_available() and tdist.is_initialized() and tdist.get_world_size() > 1:
+            # one process per GPU (the reference: ext_dist.my_size > 1, dlrm_s_pytorch.py:352-365): tables are
+            # placed over the ranks (dlrm_b200/placement.py), the MLPs replicated; max_batch is the GLOBAL batch
+            from .dist import DistEngine
+
+            world = tdist.get_world_size()
+            if gemm == "simt":
+                sys.exit("ERROR: distributed runs use the tensor-core path (MLP widths >= 16, dot interaction)")
+            if max_batch % world:
+                sys.exit("ERROR: batch_size %d can not split across %d ranks evenly" % (max_batch, world))
+            self._dist = DistEngine(int(m_spa), ln_emb.tolist(), ln_bot.tolist(), ln_top.tolist(),
+                                    local_batch=max_batch // world, device=device, gemm=gemm, loss=loss_function,
+                                    exchange="p2p", itself=arch_interaction_itself, sigmoid_bot=sigmoid_bot,
+                                    loss_threshold=loss_threshold, loss_ws=loss_ws)
+            self._engine = self._dist.eng
+            self.local_shards = list(self._dist.mine)
+        else:
+            self._engine = Engine(int(m_spa), ln_emb.tolist(), ln_bot.tolist(), ln_top.tolist(),
+                                  op=arch_interaction_op, itself=arch_interaction_itself,
+                                  sigmoid_bot=sigmoid_bot, sigmoid_top=sigmoid_top, loss=loss_function,
+                                  loss_threshold=loss_threshold, loss_ws=loss_ws, device=device,
+                                  max_batch=max_batch, gemm=gemm, interleave_momentum=False)
         self._m_spa, self._ln_emb = int(m_spa), ln_emb
         # same construction (and numpy RNG consumption) order as the reference: tables, bottom, top
         if ndevices <= 1:
@@ -158,6 +178,8 @@ class DLRM_Net(nn.Module):
             self.loss_fn = torch.nn.BCELoss(reduction="mean")
         else:
             self.loss_fn = torch.nn.BCELoss(reduction="none")
+        if self._dist is not None:
+            self._dist.sync_dense_params_from_rank0()    # DDP broadcasts rank 0's MLPs at wrap time (:1329-1336)
         self.register_load_state_dict_post_hook(lambda m, k: m._engine.mark_params_changed())
         import weakref
 
@@ -194,6 +216,32 @@ class DLRM_Net(nn.Module):
         if big:
             gen = torch.Generator(device=eng.device)
             gen.manual_seed(int(np.random.randint(0, 2 ** 31 - 1)))
+        if self._dist is not None:
+            # This rank keeps only the rows it stores (the reference skips non-local tables BEFORE drawing,
+            # dlrm_s_pytorch.py:252-254, so its ranks' numpy streams diverge).  Here every rank draws every table in
+            # order and keeps its slices: the initial model is the single-process model for the same seed.
+            if weighted_pooling is not None:
+                sys.exit("ERROR: weighted pooling is not supported on distributed runs")
+            mine = {}
+            for j, sh in enumerate(eng.shards):
+                mine.setdefault(int(sh["table"]), []).append((j, int(sh["row_lo"]), int(sh["row_n"])))
+            views = {}
+            for k in range(ln.size):
+                n = int(ln[k])
+                a = float(np.sqrt(1 / n))
+                W = None if big else np.random.uniform(low=-a, high=a, size=(n, int(m))).astype(np.float32)
+                for j, lo, cnt in mine.get(k, []):
+                    tab = eng.table(j)
+                    with torch.no_grad():
+                        if big:
+                            tab.uniform_(-a, a, generator=gen)
+                        else:
+                            tab.copy_(torch.from_numpy(W[lo:lo + cnt]))
+                    views[j] = _TableView(tab)
+            for j in range(len(eng.shards)):
+                emb_l.append(views[j])
+                v_W_l.append(None)
+            return emb_l, v_W_l
         for k in range(ln.size):
             n = int(ln[k])
             tab = eng.table(k)
@@ -249,9 +297,11 @@ class DLRM_Net(nn.Module):
         return eng.interact_only(B).clone()
 
     def forward(self, dense_x, lS_o, lS_i):
+        if self._dist is not None:
+            return self.distributed_forward(dense_x, lS_o, lS_i)
         if self.ndevices > 1:
-            sys.exit("ERROR: single-process multi-GPU (parallel_forward) is replaced by dlrm_b200.dist "
-                     "(one process per GPU); launch with torchrun")
+            sys.exit("ERROR: single-process multi-GPU (parallel_forward) is replaced by one process per GPU: "
+                     "launch the same command with torchrun --nproc-per-node N (distributed_forward)")
         return self.sequential_forward(dense_x, lS_o, lS_i)
 
     def sequential_forward(self, dense_x, lS_o, lS_i):
@@ -267,7 +317,31 @@ class DLRM_Net(nn.Module):
         return self.forward(dense_x, lS_o, lS_i)
 
     def distributed_forward(self, dense_x, lS_o, lS_i):
-        sys.exit("ERROR: use dlrm_b200.dist.DistributedDLRM for one-process-per-GPU runs")
+        """dlrm_s_pytorch.py:528-585: every rank receives the whole batch, keeps the dense rows of ITS batch slice and
+        the index streams of the tables IT stores rows of, and returns the logits of its slice.  The exchange of
+        the pooled vectors (and of their gradients in backward) rides on the gather / interaction-backward kernels'
+        peer stores instead of an all-to-all."""
+        if self._dist is None:
+            sys.exit("ERROR: distributed_forward needs torch.distributed initialised with more than one rank "
+                     "(launch with torchrun)")
+        de, eng = self._dist, self._engine
+        batch_size = dense_x.size()[0]
+        if batch_size < de.world:
+            sys.exit("ERROR: batch_size (%d) must be larger than number of ranks (%d)" % (batch_size, de.world))
+        if batch_size % de.world != 0:
+            sys.exit("ERROR: batch_size %d can not split across %d ranks evenly" % (batch_size, de.world))
+        if batch_size != de.Bg:
+            sys.exit("ERROR: distributed_forward was built for a global batch of %d, got %d" % (de.Bg, batch_size))
+        if isinstance(lS_i, torch.Tensor):
+            lS_i = [lS_i[k] for k in range(lS_i.shape[0])]
+        if isinstance(lS_o, torch.Tensor):
+            lS_o = [lS_o[k] for k in range(lS_o.shape[0])]
+        if len(lS_o) != de.Tg or len(lS_i) != de.Tg:
+            sys.exit("ERROR: corrupted model input detected in distributed_forward call")
+        sp = sparse_from_reference([lS_o[s.table] for s in de.mine], [lS_i[s.table] for s in de.mine], eng.device)
+        x = dense_x[de.rank * de.B:(de.rank + 1) * de.B].to(eng.device, dtype=torch.float32).contiguous()
+        params = list(self.parameters())
+        return _DLRMForward.apply(self, sp, torch.is_grad_enabled(), x, *params)
 
     def quantize_embedding(self, bits):
         sys.exit("ERROR: 4 and 8-bit quantization on GPU is not supported")

@@ -182,9 +182,13 @@ class Engine:
         # side streams: the gather runs beside the bottom MLP, the weight-gradient GEMMs and the
         # embedding update beside the dgrad chain (independent work; parallel branches in the graph)
         self.multi_stream = True
-        # every MLP chain (forward layers; dgrad chain + weight gradients) as ONE persistent tile-dataflow
-        # launch (csrc/gemm_chain.cu) instead of one launch per layer; DLRM_CHAIN=0 restores per-layer launches
-        self.use_chain = os.environ.get("DLRM_CHAIN", "1") != "0"
+        # DLRM_CHAIN=1: every MLP chain (forward layers; dgrad chain + weight gradients) as ONE persistent
+        # tile-dataflow launch (csrc/gemm_chain.cu) instead of one launch per layer.  Bit-identical results
+        # (tests/test_gpu_chain.py); measured SLOWER inside the step at batch 2048 (profiles/README.md: a CTA
+        # that claimed a task whose producer tiles are not done blocks instead of taking ready work, and the
+        # persistent grid shares the SMs badly with the gather / update kernels of the embedding stream), so
+        # per-layer launches (+ programmatic dependent launch) stay the default.
+        self.use_chain = os.environ.get("DLRM_CHAIN", "0") == "1"
         self.tc_tile_n = {}          # optional (kind, which, i) -> tile_n override for the tcgen05 plans
         self.tc_smem_kb = (0, 0)    # (forward, backward) operand-ring budget of the tcgen05 GEMM plans, KB; 0 = 200
         self.s_emb = torch.cuda.Stream(device=self.device)
@@ -792,20 +796,36 @@ class Engine:
             self.backward(X, sp, target)
             if self.T:
                 self.emb_update(sp, optimizer=optimizer, lr=clr)
+        self.dense_apply(optimizer, clr)
+        return self.loss_buf
+
+
+
+    def dense_apply(self, optimizer: str, clr: float, eps: float = 1e-10):
+        """Dense branch of optimizer.step() (+ the cross-rank mean of the gradients on a sharded run)."""
         if self.tc:
             if self.dense_sync_fn is not None:
                 self._dense_update_pack(-2, 0.0)      # fold the split-K slabs into slab 0
                 self.dense_sync_fn()                  # cross-rank mean of the dense gradients
-                self._dense_update_pack(_OPT[optimizer], clr, single_slab=True)
+                self._dense_update_pack(_OPT[optimizer], clr, eps, single_slab=True)
             else:
-                self._dense_update_pack(_OPT[optimizer], clr)
+                self._dense_update_pack(_OPT[optimizer], clr, eps)
         else:
             if self.dense_sync_fn is not None:
                 self.dense_sync_fn()
-            self.dense_step(optimizer, clr)
-        return self.loss_buf
+            self.dense_step(optimizer, clr, eps)
 
-
+    def apply_optimizer(self, sp: SparseInput, optimizer: str, clr: float, eps: float = 1e-10, linked: bool = False):
+        """optimizer.step() on the gradients the last backward() left in the engine's buffers: embedding rows
+        (through the sharded exchange when there is one), then the dense parameters."""
+        if self.T or self.update_fn is not None:
+            if not linked and self.T:
+                self.emb_link(sp)
+            if self.update_fn is not None:
+                self.update_fn(sp, optimizer, clr)
+            else:
+                self.emb_update(sp, optimizer=optimizer, lr=clr, eps=eps)
+        self.dense_apply(optimizer, clr, eps)
 
     # ================================================================== tcgen05 path
     # Layers whose output width is >= 16 run on tensor cores (all bottom layers, the top layers

@@ -13,7 +13,6 @@ from __future__ import annotations
 
 import torch
 
-from ._lib import OPT_RWSADAGRAD, OPT_SGD
 
 
 class _Fused(torch.optim.Optimizer):
@@ -54,15 +53,7 @@ class _Fused(torch.optim.Optimizer):
         g = self.param_groups[0]
         eng.opt_step += 1
         clr = g["lr"] / (1.0 + (eng.opt_step - 1.0) * g["lr_decay"]) if self._name == "rwsadagrad" else g["lr"]
-        if eng.T:
-            if not linked:
-                eng.emb_link(sp)
-            eng.emb_update(sp, optimizer=self._name, lr=clr, eps=g["eps"])
-        code = OPT_RWSADAGRAD if self._name == "rwsadagrad" else OPT_SGD
-        if eng.tc:
-            eng._dense_update_pack(code, clr, g["eps"])
-        else:
-            eng.dense_step(self._name, clr, g["eps"])
+        eng.apply_optimizer(sp, self._name, clr, g["eps"], linked)
         net._pending = None
         return loss
 

@@ -60,13 +60,20 @@ CASES = [
 
 
 @pytest.mark.parametrize("case", range(len(CASES)))
+@pytest.mark.parametrize("order", [0, 2])
 @pytest.mark.parametrize("tile_n", [None, 64])
-def test_chain_is_bitwise_the_per_layer_path(case, tile_n):
+def test_chain_is_bitwise_the_per_layer_path(case, tile_n, order):
     D, ln_emb, ln_bot, tail, B = CASES[case]
     F = len(ln_emb) + 1
     ln_top = [D + F * (F - 1) // 2] + tail
+    from dlrm_b200 import _lib
+
     l0, a, e0 = _run(False, D, ln_emb, ln_bot, ln_top, B, tile_n)
-    l1, b, e1 = _run(True, D, ln_emb, ln_bot, ln_top, B, tile_n)
+    _lib.set_tunable("chain_order", order)     # 2 = m-tile-major task order
+    try:
+        l1, b, e1 = _run(True, D, ln_emb, ln_bot, ln_top, B, tile_n)
+    finally:
+        _lib.set_tunable("chain_order", 0)
     assert e1.tc_chains and all(c.info()["tasks"] > 0 for c in e1.tc_chains.values())
     bad = ["%s: max|diff|=%.3e of scale %.3e, %d elements" % (k, float((a[k] - b[k]).abs().max()), float(a[k].abs().max()),
                                                               int((a[k] != b[k]).sum()))
@@ -94,6 +101,7 @@ def test_chain_graph_replay_and_launch_count():
     X, off, idx = O.random_batch(rng, ln_emb, B, ln_bot[0], 6)
     tgt = np.round(rng.random((B, 1))).astype(np.float32)
     e = Engine(D, ln_emb, ln_bot, ln_top, loss="bce", sigmoid_top=len(ln_top) - 2, device=DEV, max_batch=B, gemm="tc")
+    e.use_chain = True
     e.load_params(params)
     sp = sparse_from_reference([torch.from_numpy(o) for o in off], [torch.from_numpy(i) for i in idx], DEV)
     st = types.SimpleNamespace(X=torch.from_numpy(X).to(DEV), target=torch.from_numpy(tgt).to(DEV), sparse=sp)
