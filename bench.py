@@ -40,9 +40,14 @@ CFG2 = dict(m_spa=128, rows=[1_000_000] * 26, ln_bot=[13, 512, 256, 128], top_ta
             lmax=10, hot=None)
 
 
-def workload(name):
+def workload(name, world=1):
     from dlrm_b200 import mlperf as M
 
+    if name == "cfg4":
+        # BASELINE.json configs[4]: one giant row-split table (2e9 rows x 128 = 1 TB fp32 at 8 GPUs: 2.5e8 rows =
+        # 128 GB per GPU, scaled with N) + 25 tables of 1e6 rows, random bags, batch 8192 per GPU (65536 at 8)
+        return dict(m_spa=128, rows=[250_000_000 * world] + [1_000_000] * 25, ln_bot=[13, 512, 256, 128],
+                    top_tail=[1024, 512, 256, 1], B=8192, lmax=10, hot=None)
     if name == "cfg3":
         return dict(m_spa=M.DIM, rows=list(M.TABLE_ROWS), ln_bot=list(M.LN_BOT), top_tail=list(M.TOP_TAIL), B=8192,
                     lmax=None, hot=list(M.MULTI_HOT))
@@ -206,6 +211,8 @@ def config_dict(args, W, n):
     desc = {"cfg3": "cfg3: MLPerf-DLRM synthetic, 26 Criteo-Terabyte-sized tables (204.18 M rows x 128, 104.5 GB fp32), "
                     "multi-hot L_k sum 214, bot 13-512-256-128, top 479-1024-1024-512-256-1, batch 8192/GPU, "
                     "fwd+bwd+RWSAdagrad",
+            "cfg4": "cfg4: ONE row-split table of 2.5e8 x N rows x 128 (1 TB fp32 at N=8) + 25 x 1e6 x 128 tables, bot "
+                    "13-512-256-128, top 479-1024-512-256-1, batch 8192/GPU, random data Lmax=10, fwd+bwd+RWSAdagrad",
             "cfg2": "cfg2: 26x1e6x128 tables, bot 13-512-256-128, top 479-1024-512-256-1, batch 2048/GPU, random data "
                     "Lmax=10, fwd+bwd+RWSAdagrad",
             "cfg1": "cfg1: cfg2's model, forward only"}[args.workload]
@@ -300,6 +307,9 @@ def ours(args, W):
     local = int(os.environ.get("LOCAL_RANK", str(rank)))
     dev = "cuda:%d" % local
     torch.cuda.set_device(local)
+    warm = torch.zeros(1, device=dev)      # create the communicator now: NCCL prints its version line to stdout at
+    dist.all_reduce(warm)                  # the first collective, and the JSON line must be the LAST line
+    torch.cuda.synchronize()
     train = args.workload != "cfg1"
     D, rows, ln_bot, ln_top = model_dims(W)
     B, T = W["B"], len(rows)
@@ -493,6 +503,7 @@ def ours(args, W):
                             "step, loss read back"},
             "gpu_launches": int(launches), "exchange": "p2p (peer-mapped stores over NVLink, own barriers)",
             "cuda_graph": graphs is not None,
+            "nvlink": de.nvlink_bytes_per_step(ms * 1e-3, mh.nbytes if fixed else 0),
             "placement": {"split_tables": pl.split_tables(), "imbalance": pl.imbalance(),
                           "gather_bytes_per_rank_per_step": gbs,
                           "gather_bytes_max_over_min": max(gbs) / max(min(gbs), 1.0)},
@@ -579,7 +590,7 @@ def main():
     ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="cfg3", choices=["cfg3", "cfg2", "cfg1"])
+    ap.add_argument("--workload", default="cfg3", choices=["cfg3", "cfg2", "cfg1", "cfg4"])
     ap.add_argument("--ring", type=int, default=8)
     ap.add_argument("--gemm", default="tc", choices=["tc", "tc_bf16"])
     ap.add_argument("--no-graph", action="store_true")
@@ -588,7 +599,7 @@ def main():
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
-    W = workload(args.workload)
+    W = workload(args.workload, max(int(os.environ.get("WORLD_SIZE", "1")), 1))
     if args.impl == "reference":
         return reference_arm(args, W)
     if not torch.cuda.is_available():

@@ -30,6 +30,12 @@ class EmbBwdTable(C.Structure):
                 ("use_dy_off", C.c_int64), ("dy_off", C.c_int64), ("row_lo", C.c_int64), ("row_n", C.c_int64)]
 
 
+class EmbRemoteTable(C.Structure):
+    _fields_ = [("shard_weight", C.c_void_p * 8), ("num_shards", C.c_int32), ("rows_per_shard", C.c_int64),
+                ("rows", C.c_int64), ("ld", C.c_int64), ("indices", C.c_void_p), ("offsets", C.c_void_p),
+                ("nnz", C.c_int64), ("out_off", C.c_int64), ("out_stride", C.c_int64)]
+
+
 class EmbDedup(C.Structure):
     _fields_ = [("filter", C.c_void_p), ("log2_size", C.c_int32), ("flags", C.c_void_p), ("suspects", C.c_void_p)]
 
@@ -73,7 +79,7 @@ SYMBOLS = [
     "dlrm_b200_gemm_tc_plan_destroy", "dlrm_b200_gemm_chain_create", "dlrm_b200_gemm_chain_info",
     "dlrm_b200_gemm_chain_run", "dlrm_b200_gemm_chain_destroy", "dlrm_b200_gemm_chain_set_trace",
     "dlrm_b200_emb_bwd_small_scratch_bytes", "dlrm_b200_emb_bwd_small_update", "dlrm_b200_emb_reduce_partials",
-    "dlrm_b200_block_copy", "dlrm_b200_gen_multihot", "dlrm_b200_split_bf16", "dlrm_b200_dense_update_pack",
+    "dlrm_b200_block_copy", "dlrm_b200_gen_multihot", "dlrm_b200_emb_bag_fwd_remote", "dlrm_b200_split_bf16", "dlrm_b200_dense_update_pack",
 ]
 
 
@@ -127,6 +133,7 @@ def _declare(lib):
     lib.dlrm_b200_emb_bwd_small_update.argtypes = [C.POINTER(EmbBwdTable), i32, i32, i64, i32, i32, vp, C.POINTER(vp), i32,
                                                    i64, i64, i32, f32, f32, vp, i64, vp]
     lib.dlrm_b200_emb_reduce_partials.argtypes = [vp, vp, i64, i64, i32, C.POINTER(i32), C.POINTER(i32), i32, vp]
+    lib.dlrm_b200_emb_bag_fwd_remote.argtypes = [C.POINTER(EmbRemoteTable), i32, i32, i64, i32, i32, vp, vp]
     lib.dlrm_b200_block_copy.argtypes = [C.POINTER(vp), C.POINTER(vp), C.POINTER(i64), i32, vp]
     lib.dlrm_b200_gen_multihot.argtypes = [C.POINTER(vp), C.POINTER(i64), C.POINTER(i32), C.POINTER(i32), i32, i32,
                                            C.c_uint64, C.c_uint64, i64, i64, vp, vp, i32, vp]

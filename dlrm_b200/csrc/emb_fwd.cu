@@ -285,6 +285,84 @@ __global__ void __launch_bounds__(256) emb_fwd_shard_kernel(const __grid_constan
   }
 }
 
+// Row-split table, REMOTE-READ forward (BASELINE.json north_star: "P2P reads of remote rows over NVSwitch"):
+// the rank that owns a sample pools the whole bag itself, in index order (bit-identical to the reference CPU
+// kernel, like the local gather), loading each row from the rank that stores it through peer-mapped memory --
+// 512-byte NVLink reads, up to U in flight per lane group.  No partial sums, no reduction; NVLink carries
+// L x 512 B per sample instead of (N-1) x 512 B of partial sums (better for short bags, worse for L = 100).
+struct EmbRemoteTable {
+  const float* shard_w[DLRM_B200_MAX_PEERS];   // base of shard s (rows [s*rps, (s+1)*rps))
+  const void* idx;
+  const void* off;
+  long long nnz, ld, out_off, out_stride, rows, rps;
+};
+struct EmbRemoteParams {
+  EmbRemoteTable t[4];
+  float* out;
+  long long batch;
+  int dim, include_last, bags_per_group;
+  unsigned* err;
+};
+
+template <int G, int NV, int U, typename idx_t>
+__global__ void __launch_bounds__(256) emb_fwd_remote_kernel(const __grid_constant__ EmbRemoteParams P) {
+  const int D = P.dim;
+  constexpr int GROUPS_PER_WARP = 32 / G;
+  const int lane = threadIdx.x & 31;
+  const int gl = lane % G;
+  const int grp = lane / G;
+  const unsigned gmask = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << (grp * G));
+  const EmbRemoteTable& tb = P.t[blockIdx.y];
+  const idx_t* __restrict__ idx = static_cast<const idx_t*>(tb.idx);
+  const idx_t* __restrict__ off = static_cast<const idx_t*>(tb.off);
+  const int S = P.bags_per_group;
+  const long long b0 = (((long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * GROUPS_PER_WARP + grp) * S;
+  for (int s = 0; s < S; ++s) {
+    const long long b = b0 + s;
+    if (b >= P.batch) return;
+    const long long start = (long long)off[b];
+    const long long end = bag_end<idx_t>(off, b, P.batch, tb.nnz, P.include_last);
+    float4 acc[NV];
+#pragma unroll
+    for (int v = 0; v < NV; ++v) acc[v] = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (long long j0 = start; j0 < end; j0 += G) {
+      long long my_row = (j0 + gl < end) ? (long long)idx[j0 + gl] : 0;
+      if ((unsigned long long)my_row >= (unsigned long long)tb.rows) {
+        if (P.err) atomicOr(P.err, 1u);
+        my_row = 0;
+      }
+      const int n = (int)min((long long)G, end - j0);
+      for (int jj = 0; jj < n; jj += U) {
+        float4 val[U][NV];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          const long long r = __shfl_sync(gmask, my_row, jj + u, G);
+          if (jj + u < n) {
+            const long long sh = r / tb.rps;
+            const float* rp = tb.shard_w[sh] + (r - sh * tb.rps) * tb.ld + gl * 4;
+#pragma unroll
+            for (int v = 0; v < NV; ++v)
+              if (gl * 4 + v * G * 4 < D) val[u][v] = ldg_stream_f4(rp + v * G * 4);
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          if (jj + u < n) {
+#pragma unroll
+            for (int v = 0; v < NV; ++v) {
+              acc[v].x += val[u][v].x; acc[v].y += val[u][v].y; acc[v].z += val[u][v].z; acc[v].w += val[u][v].w;
+            }
+          }
+        }
+      }
+    }
+    float* op = P.out + b * tb.out_stride + tb.out_off + gl * 4;
+#pragma unroll
+    for (int v = 0; v < NV; ++v)
+      if (gl * 4 + v * G * 4 < D) *reinterpret_cast<float4*>(op + v * G * 4) = acc[v];
+  }
+}
+
 // any dim / any alignment: one thread per output element, sequential over the bag
 template <typename idx_t, bool WEIGHTED, bool LINK>
 __global__ void emb_fwd_scalar_kernel(const __grid_constant__ EmbFwdParams P) {
@@ -484,4 +562,58 @@ extern "C" int dlrm_b200_emb_bag_fwd_p2p(const dlrm_emb_fwd_table_t* tables,
   if (!peer_out) return dlrm::set_error("emb_bag_fwd_p2p: peer_out is NULL");
   return emb_fwd_impl(tables, train, next, num_tables, dim, batch_global, idx_bytes, include_last, nullptr,
                       out_stride_sample, out_stride_table, stream, peer_out, world, batch_local, dedup);
+}
+
+extern "C" int dlrm_b200_emb_bag_fwd_remote(const dlrm_emb_remote_table_t* tables, int num_tables, int dim,
+                                            int64_t batch, int idx_bytes, int include_last, float* out,
+                                            void* stream) {
+  using namespace dlrm;
+  if (num_tables == 0 || batch == 0) return 0;
+  if (num_tables < 0 || num_tables > 4) return set_error("emb_bag_fwd_remote: num_tables=%d (max 4 per call)", num_tables);
+  if (idx_bytes != 4 && idx_bytes != 8) return set_error("emb_bag_fwd_remote: idx_bytes=%d", idx_bytes);
+  if (!tables || !out) return set_error("emb_bag_fwd_remote: NULL pointer");
+  if (dim <= 0 || dim % 4 || dim > 512 || !aligned16(out)) return set_error("emb_bag_fwd_remote: dim=%d (multiple of 4, <= 512)", dim);
+  EmbRemoteParams P{};
+  for (int k = 0; k < num_tables; ++k) {
+    const dlrm_emb_remote_table_t& s = tables[k];
+    if (s.num_shards < 1 || s.num_shards > DLRM_B200_MAX_PEERS || s.rows_per_shard <= 0 || s.rows <= 0 ||
+        s.rows_per_shard * s.num_shards < s.rows)
+      return set_error("emb_bag_fwd_remote: table %d: %d shards of %lld rows for %lld rows", k, s.num_shards,
+                       (long long)s.rows_per_shard, (long long)s.rows);
+    if (!s.offsets || (!s.indices && s.nnz > 0)) return set_error("emb_bag_fwd_remote: table %d has a NULL pointer", k);
+    EmbRemoteTable& t = P.t[k];
+    for (int d = 0; d < DLRM_B200_MAX_PEERS; ++d) {
+      t.shard_w[d] = d < s.num_shards ? s.shard_weight[d] : s.shard_weight[0];
+      if (d < s.num_shards && (!s.shard_weight[d] || !aligned16(s.shard_weight[d])))
+        return set_error("emb_bag_fwd_remote: table %d shard %d pointer NULL / unaligned", k, d);
+    }
+    t.idx = s.indices; t.off = s.offsets; t.nnz = s.nnz; t.ld = s.ld > 0 ? s.ld : dim;
+    t.out_off = s.out_off; t.out_stride = s.out_stride; t.rows = s.rows; t.rps = s.rows_per_shard;
+    if (t.ld % 4 || t.out_off % 4 || t.out_stride % 4) return set_error("emb_bag_fwd_remote: table %d: unaligned strides", k);
+  }
+  P.out = out; P.batch = batch; P.dim = dim; P.include_last = include_last; P.err = err_word_device();
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+#define REMOTE(G, NV, IDX)                                                                                 \
+  do {                                                                                                     \
+    P.bags_per_group = 2;                                                                                  \
+    const long long gpb = (256 / 32) * (32 / (G));                                                         \
+    const long long groups = (batch + 1) / 2;                                                              \
+    dim3 grid((unsigned)((groups + gpb - 1) / gpb), (unsigned)num_tables);                                 \
+    emb_fwd_remote_kernel<G, NV, ((G) >= 8 ? 8 : (G)), IDX><<<grid, 256, 0, st>>>(P);                       \
+    DLRM_CHECK_LAUNCH("emb_fwd_remote_kernel");                                                            \
+    return 0;                                                                                              \
+  } while (0)
+#define REMOTE_D(IDX)                      \
+  do {                                     \
+    if (dim <= 16) REMOTE(4, 1, IDX);      \
+    if (dim <= 32) REMOTE(8, 1, IDX);      \
+    if (dim <= 64) REMOTE(16, 1, IDX);     \
+    if (dim <= 128) REMOTE(32, 1, IDX);    \
+    if (dim <= 256) REMOTE(32, 2, IDX);    \
+    REMOTE(32, 4, IDX);                    \
+  } while (0)
+  if (idx_bytes == 8) REMOTE_D(long long);
+  REMOTE_D(int);
+#undef REMOTE_D
+#undef REMOTE
 }

@@ -130,7 +130,7 @@ class DistEngine:
 
     def __init__(self, m_spa: int, ln_emb: Sequence[int], ln_bot: Sequence[int], ln_top: Sequence[int], *,
                  local_batch: int, device=None, gemm: str = "tc", loss: str = "bce", exchange: str = "nccl",
-                 placement=None, cost: Optional[Sequence[float]] = None, **kw):
+                 placement=None, cost: Optional[Sequence[float]] = None, split_forward: str = "partial", **kw):
         from . import placement as P, sharding as S
         from .engine import Engine
 
@@ -176,6 +176,10 @@ class DistEngine:
         if exchange == "p2p":
             self._setup_p2p()
             e.gather_fn, e.update_fn = self._gather_p2p, self._update_p2p
+            if split_forward == "remote" and self.pl.split_tables():
+                self._setup_remote_reads()
+            elif split_forward not in ("partial", "remote"):
+                raise SystemExit("ERROR: split_forward must be partial or remote")
         else:
             self.send_splits, self.recv_splits = a2a_splits(self.Tg, self.world, self.rank, self.B, self.D)
             self.send = torch.zeros(self.Bg * self.Tl * self.D, dtype=f32, device=self.device)
@@ -277,6 +281,22 @@ class DistEngine:
         if self.world > 1:
             dist.barrier()
 
+    def _setup_remote_reads(self):
+        """Map every rank's table arena: the forward of a row-split table then reads remote rows directly."""
+        e = self.eng
+        ptrs = self.share([e.tables])
+        tabs = {}
+        for t in self.pl.split_tables():
+            sh = self.pl.of_table(t)
+            bases = []
+            for s in sh:
+                own = self.pl.of_rank(s.rank)
+                row0 = sum(o.local_rows for o in own[:own.index(s)])       # rows before shard s in the owner's arena
+                bases.append(ptrs[s.rank][0] + row0 * e.ldw * 4)
+            tabs[t] = (bases, sh[0].local_rows)
+        e.use_remote_reads(tabs)
+        e.remote_sample0 = self.rank * self.B
+
     def _barrier(self, channel: int = 0):
         """Device-side ordering across ranks on the current stream (no host sync)."""
         if self.world == 1:
@@ -344,6 +364,18 @@ class DistEngine:
 
     def train_step(self, X_local, sp_local_shards, target_local, lr, optimizer="rwsadagrad"):
         return self.eng.train_step(X_local, sp_local_shards, target_local, lr, optimizer)
+
+    def nvlink_bytes_per_step(self, step_seconds: float, staged_index_bytes: int = 0) -> dict:
+        """Bytes THIS rank pushes to its peers per training step (peer stores over NVLink) and what that is per
+        second of step time (a lower bound of the link rate: the pushes happen inside three kernels, not all step)."""
+        W, B, D = self.world, self.B, self.D
+        remote = (W - 1) / W if W > 1 else 0.0
+        fwd = len(self.mine) * self.Bg * D * 4 * remote                    # pooled rows / partial sums of all samples
+        bwd = sum(sum(1 for s in self.pl.of_table(t) if s.rank != self.rank) for t in range(self.Tg)) * B * D * 4
+        idx = staged_index_bytes * remote                                    # upper bound: split tables go to every rank
+        tot = fwd + bwd + idx
+        return {"pooled_rows_fwd": fwd, "gradient_rows_bwd": bwd, "indices": idx, "total_bytes_per_rank_per_step": tot,
+                "gb_per_s_over_step": tot / max(step_seconds, 1e-12) / 1e9, "measured_link_peak_gb_s": 770.0}
 
     def gather_bytes_per_step(self, lookups_per_sample: Sequence[float]) -> float:
         """Expected embedding-row bytes this rank reads per step (its share of every table's lookups)."""

@@ -179,6 +179,11 @@ class Engine:
         self.n_launch = 0            # kernels launched by this engine (bench: gpu_launches)
         self.peer = None             # sharded runs: (peer_out void*[world], world, local batch) for the gather
         self.peer_dY = None          #               (peer_dY void*[world], world, local batch) for the update
+        # Row-split tables, forward variant "remote" (BASELINE north_star: P2P reads of remote rows): table ->
+        # ([base pointer of every shard], rows per shard); the rank that owns a sample pools the whole bag itself,
+        # reading each row from the rank that stores it, instead of every rank pooling a partial sum.
+        self.remote_tables = None
+        self.remote_sample0 = 0      # first global sample of THIS rank (its bags inside the global index streams)
         # side streams: the gather runs beside the bottom MLP, the weight-gradient GEMMs and the
         # embedding update beside the dgrad chain (independent work; parallel branches in the graph)
         self.multi_stream = True
@@ -250,9 +255,61 @@ class Engine:
             self.route_dy.append((1 + t) * D)
         self.dy_stride = F * D
 
+    def _emb_forward_remote(self, sp: SparseInput, split, link: bool):
+        """Row-split tables, remote-read variant: pool the bags of MY samples (rows fetched from the shards' owners
+        through peer-mapped memory, summed in index order -> bit-identical to the reference), and -- training --
+        thread the global occurrences that fall into my row ranges onto their lists (indices only)."""
+        B = sp.batch if self.peer is None else self.peer[2]
+        done = set()
+        descs = []
+        for k in split:
+            t = int(self.shards[k]["table"])
+            if t in done:
+                continue
+            done.add(t)
+            ptrs, rps = self.remote_tables[t]
+            d = _lib.EmbRemoteTable()
+            for i, p_ in enumerate(ptrs):
+                d.shard_weight[i] = p_
+            d.num_shards, d.rows_per_shard, d.rows, d.ld = len(ptrs), int(rps), int(self.shards[k]["rows"]), self.ldw
+            es = sp.offsets[k].element_size()
+            d.indices = sp.indices[k].data_ptr() if sp.indices[k].numel() else 0
+            d.offsets = sp.offsets[k].data_ptr() + self.remote_sample0 * es     # my bags inside the global stream
+            d.nnz = sp.indices[k].numel()
+            d.out_off, d.out_stride = (1 + t) * self.D, self.F * self.D
+            # offsets[b + 1] exists for my last bag unless it is the last bag of the global batch (reference format)
+            last_global = self.remote_sample0 + B >= sp.batch
+            descs.append((d, 1 if (sp.include_last or not last_global) else 0))
+        for inc in (0, 1):
+            group = [d for d, i in descs if i == inc]
+            for c0 in range(0, len(group), 4):
+                arr = (_lib.EmbRemoteTable * len(group[c0:c0 + 4]))(*group[c0:c0 + 4])
+                _lib.check(self.lib.dlrm_b200_emb_bag_fwd_remote(arr, len(arr), self.D, B, sp.idx_bytes, inc,
+                                                                 self.TP.data_ptr(), _stream()), "emb_bag_fwd_remote")
+                self.n_launch += 1
+        if link:
+            for c0 in range(0, len(split), _lib.MAX_TABLES):
+                ks = split[c0:c0 + _lib.MAX_TABLES]
+                desc, _ = self._bwd_desc_chunk(sp, ks)
+                _lib.check(self.lib.dlrm_b200_emb_bwd_link(desc, len(ks), sp.batch, sp.idx_bytes, int(sp.include_last),
+                                                           self.link.data_ptr(), _stream()), "emb_bwd_link")
+                self.n_launch += 1
+
+    def use_remote_reads(self, tables=None):
+        """Switch the row-split tables to the remote-read forward.  tables: {table: ([shard base pointers], rows per
+        shard)}; None (single GPU): every shard is a local one."""
+        if tables is None:
+            tables = {}
+            for t, n in self.split_slots:
+                js = sorted((int(sh["part"]), j) for j, sh in enumerate(self.shards) if int(sh["table"]) == t)
+                ptrs = [self.tables.data_ptr() + int(self.row_base[j]) * self.ldw * 4 for _, j in js]
+                rps = int(self.shards[js[0][1]]["row_n"])
+                tables[t] = (ptrs, rps)
+        self.remote_tables = tables
+
     def reduce_partials(self, B: int):
         """T[b, 1+t, :] = sum of the partial sums of every row-split table t (fixed part order)."""
-        if not self.split_slots:
+        if not self.split_slots or self.remote_tables is not None:
             return
         n = len(self.split_slots)
         feat = (C.c_int * n)(*[1 + t for t, _ in self.split_slots])
@@ -405,6 +462,10 @@ class Engine:
         route = self.route_out if routed else [(k * stride_table, stride_sample) for k in range(self.T)]
         whole = [k for k in range(self.T) if int(self.shards[k]["nparts"]) == 1]
         split = [k for k in range(self.T) if int(self.shards[k]["nparts"]) > 1]
+        remote = routed and self.remote_tables is not None and bool(split)
+        if remote:
+            self._emb_forward_remote(sp, split, link)
+            split = []
         use_filter = self.use_filter and not split and not any(self.is_small(k) for k in range(self.T))
         peer = self.peer if routed else None
         base = self.TP.data_ptr() if routed else out.data_ptr()

@@ -378,6 +378,22 @@ int dlrm_b200_dense_update_pack(const dlrm_dense_layer_t* layers /*[host]*/, int
 /* ------------------------------------------------------------------------------------------
  * Sharded placement (dlrm_b200/placement.py): the pieces around the gather / update kernels.
  * ------------------------------------------------------------------------------------------ */
+/* Row-split table, remote-read forward: the rank that owns the samples pools each bag itself, in index order,
+ * reading every row from the rank that stores it (shard_weight[s] = base of rows [s*rows_per_shard, ...), a
+ * peer-mapped pointer for s != own rank): 512-byte NVLink loads inside the gather kernel instead of partial sums
+ * + reduction.  out[b*out_stride + out_off .. +dim) for the `batch` bags described by offsets / indices. */
+typedef struct {
+  const float* shard_weight[DLRM_B200_MAX_PEERS];
+  int32_t num_shards;
+  int64_t rows_per_shard;
+  int64_t rows;
+  int64_t ld;
+  const void* indices; const void* offsets; int64_t nnz;
+  int64_t out_off, out_stride;
+} dlrm_emb_remote_table_t;
+int dlrm_b200_emb_bag_fwd_remote(const dlrm_emb_remote_table_t* tables /*[host]*/, int num_tables, int dim,
+                                 int64_t batch, int idx_bytes, int include_last, float* out, void* stream);
+
 /* Tiny tables (a few to a few hundred rows, hit thousands of times per step at MLPerf batch sizes): dense
  * two-pass coalesce + row update instead of the per-row list walk (csrc/emb_small.cu).  Same semantics as
  * dlrm_b200_emb_bwd_update (grad.coalesce() + optim/rwsadagrad.py:117-143 / sparse SGD), deterministic.

@@ -28,7 +28,7 @@ from dlrm_b200.engine import sparse_from_reference  # noqa: E402
 from golden_util import Golden  # noqa: E402
 
 
-def run_case(name, opt, exchange, mode, rank, world, dev, gemm):
+def run_case(name, opt, exchange, mode, rank, world, dev, gemm, split_forward="partial"):
     g = Golden(name)
     if g.B % world:
         return None
@@ -43,7 +43,7 @@ def run_case(name, opt, exchange, mode, rank, world, dev, gemm):
     else:
         pl = P.plan(g.ln_emb, [5.0] * T, world)
     de = DistEngine(g.m_spa, g.ln_emb, g.ln_bot, g.ln_top, local_batch=B, device=dev, gemm=gemm, exchange=exchange,
-                    placement=pl, loss=g.loss, itself=g.itself, loss_threshold=g.thr)
+                    placement=pl, loss=g.loss, itself=g.itself, loss_threshold=g.thr, split_forward=split_forward)
     de.eng.load_params(S.slice_params(g.params(), pl, rank))
     lr = float(g[f"{opt}_lr"])
     sl = slice(rank * B, (rank + 1) * B)
@@ -100,8 +100,8 @@ def run_case(name, opt, exchange, mode, rank, world, dev, gemm):
     # (Adagrad's first steps divide by |g|: entries with g ~ 0 are ill-conditioned, hence medians for the weights and
     #  a loose bound on the worst accumulator; the single-step optimizer checks of test_gpu_parity.py are tight)
     if rank == 0:
-        print("%-16s %-10s %-4s %-10s split=%s %s -> %s" % (
-            name, opt, exchange, mode, pl.split_tables(), " ".join("%s=%.2e" % kv for kv in e.items()),
+        print("%-16s %-10s %-4s %-10s %-7s split=%s %s -> %s" % (
+            name, opt, exchange, mode, split_forward, pl.split_tables(), " ".join("%s=%.2e" % kv for kv in e.items()),
             "PASS" if ok else "FAIL"), flush=True)
     return ok
 
@@ -116,14 +116,16 @@ def main():
     results = []
     cases = [("cfg0", "rwsadagrad", "p2p", "plan"), ("cfg0", "sgd", "p2p", "forced"),
              ("mini_cfg1", "rwsadagrad", "p2p", "plan"), ("mini_cfg1", "rwsadagrad", "p2p", "forced"),
-             ("mini_cfg1", "sgd", "nccl", "contiguous"), ("cfg0_itself_thr", "rwsadagrad", "p2p", "forced")]
+             ("mini_cfg1", "sgd", "nccl", "contiguous"), ("cfg0_itself_thr", "rwsadagrad", "p2p", "forced"),
+             ("mini_cfg1", "rwsadagrad", "p2p", "forced", "remote"), ("cfg0", "sgd", "p2p", "forced", "remote")]
     only = os.environ.get("DLRM_DIST_CASES")
-    for name, opt, exchange, mode in cases:
+    for case in cases:
+        name, opt, exchange, mode = case[:4]
         if only and name not in only.split(","):
             continue
         if exchange == "nccl" and world == 1:
             continue
-        r = run_case(name, opt, exchange, mode, rank, world, dev, gemm)
+        r = run_case(name, opt, exchange, mode, rank, world, dev, gemm, *case[4:])
         if r is not None:
             results.append(r)
     ok = bool(results) and all(results)

@@ -70,6 +70,41 @@ def test_row_split_tables_on_one_gpu_match_oracle(gemm):
     assert int(e.head.abs().sum().item()) == 0
 
 
+def test_remote_read_forward_is_bit_exact_and_trains_like_the_partial_sum_variant():
+    """Row-split tables, remote-read forward (here every 'remote' shard is a local one): the sample owner pools the
+    whole bag in index order from the shards -> the pooled rows equal the reference's EmbeddingBag bit for bit;
+    the training steps (stand-alone link of the shard's occurrences + the usual update) match the oracle."""
+    from oracle import dlrm_numpy as O
+    from dlrm_b200 import placement as P, sharding as S
+    from dlrm_b200.engine import Engine
+
+    rng = np.random.default_rng(6)
+    D, ln_emb, ln_bot, tail, B = 128, [3000, 777, 40, 1501], [13, 64, 128], [64, 32, 1], 200
+    ln_top, params, X, off, idx, tgt = _model(rng, D, ln_emb, ln_bot, tail, B, 9)
+    pl = P.plan(ln_emb, [5.0] * 4, 1, force_split=[1, 3])
+    kw = S.engine_kwargs(pl, 0, len(ln_emb))
+    e = Engine(D, kw["ln_emb"], ln_bot, ln_top, loss="bce", sigmoid_top=len(ln_top) - 2, device=DEV, max_batch=B,
+               gemm="tc", shards=kw["shards"], split_slots=kw["split_slots"], n_features=kw["n_features"])
+    e.use_remote_reads()
+    e.load_params(S.slice_params(params, pl, 0))
+    streams = S.local_streams(list(zip(off, idx)), pl, 0)
+    sp = _sp([o for o, _ in streams], [i for _, i in streams])
+    Xd, Td = torch.from_numpy(X).to(DEV), torch.from_numpy(tgt).to(DEV)
+    got = e.forward(Xd, sp).cpu().numpy()
+    np.testing.assert_allclose(got, O.dlrm_forward(params, X, off, idx), rtol=0, atol=1e-5)
+    Tb = e.Tbuf[:B].cpu().numpy()
+    for t in range(len(ln_emb)):
+        assert np.array_equal(Tb[:, 1 + t, :], O.emb_bag_sum(params["emb"][t], idx[t], off[t])), t
+    pc = copy.deepcopy(params)
+    st = O.new_state(pc)
+    for step in range(2):
+        loss = float(e.train_step(Xd, sp, Td, 0.05, "rwsadagrad").item())
+        r = O.train_step(pc, st, X, off, idx, tgt, lr=0.05, optimizer="rwsadagrad", loss="bce")
+        assert abs(loss - float(r["loss"])) < 2e-5, (step, loss, float(r["loss"]))
+    assert e.lib.dlrm_b200_check_device_errors(None) == 0
+    assert int(e.head.abs().sum().item()) == 0
+
+
 @pytest.mark.parametrize("opt", ["rwsadagrad", "sgd"])
 @pytest.mark.parametrize("idx_dtype", [np.int64, np.int32])
 def test_tiny_tables_dense_update_matches_oracle(opt, idx_dtype):
