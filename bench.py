@@ -247,7 +247,7 @@ def parity_check(de_cls, dev, gemm):
     B = Bg // world
     pl = P.plan(ln_emb, [5.0] * T, world, force_split=[0] if world <= 2 else [])
     de = de_cls(D, ln_emb, ln_bot, ln_top, local_batch=B, device=dev, gemm=gemm, exchange="p2p", placement=pl,
-                loss=str(z["loss"]))
+                loss=str(z["loss"]), semantics="single_process")   # the golden is a single-process run of the batch
     params = dict(emb=[z["emb%d" % k] for k in range(T)],
                   bot=[(z["botW%d" % i], z["botb%d" % i]) for i in range(len(ln_bot) - 1)],
                   top=[(z["topW%d" % i], z["topb%d" % i]) for i in range(len(ln_top) - 1)], v_W_l=None)
@@ -319,7 +319,7 @@ def ours(args, W):
         check = parity_check(ddist.DistEngine, dev, args.gemm)
     pl = P.plan(rows, cost, world)
     de = ddist.DistEngine(D, rows, ln_bot, ln_top, local_batch=B, device=dev, gemm=args.gemm, exchange="p2p",
-                          placement=pl)
+                          placement=pl, split_forward=args.split_forward)
     de.eng.init_params(100 + rank)
     if world > 1:
         de.sync_dense_params_from_rank0()
@@ -503,7 +503,8 @@ def ours(args, W):
                             "step, loss read back"},
             "gpu_launches": int(launches), "exchange": "p2p (peer-mapped stores over NVLink, own barriers)",
             "cuda_graph": graphs is not None,
-            "nvlink": de.nvlink_bytes_per_step(ms * 1e-3, mh.nbytes if fixed else 0),
+            "nvlink": de.nvlink_bytes_per_step(ms * 1e-3, mh.nbytes if fixed else 0, cost),
+            "split_forward": args.split_forward,
             "placement": {"split_tables": pl.split_tables(), "imbalance": pl.imbalance(),
                           "gather_bytes_per_rank_per_step": gbs,
                           "gather_bytes_max_over_min": max(gbs) / max(min(gbs), 1.0)},
@@ -593,6 +594,9 @@ def main():
     ap.add_argument("--workload", default="cfg3", choices=["cfg3", "cfg2", "cfg1", "cfg4"])
     ap.add_argument("--ring", type=int, default=8)
     ap.add_argument("--gemm", default="tc", choices=["tc", "tc_bf16"])
+    ap.add_argument("--split-forward", default="partial", choices=["partial", "remote"],
+                    help="row-split tables: every rank pools a partial sum of its rows (partial), or the sample's owner "
+                         "reads the rows from their owners over NVLink inside the gather (remote)")
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-check", action="store_true", help="skip the pre-run parity check against the live-reference golden")
     ap.add_argument("--cpu-budget", type=float, default=15.0)

@@ -14,7 +14,7 @@ LOSS_MSE, LOSS_BCE, LOSS_WBCE = 0, 1, 2
 OPT_SGD, OPT_RWSADAGRAD = 0, 1
 GEMM_SIMT_FP32, GEMM_TC_BF16X3, GEMM_TC_BF16 = 0, 1, 2
 TUNE = dict(emb_bags_per_group=0, emb_unroll=1, emb_block=2, upd_block=3, gemm_splitk=4, gemm_smem_kb=5,
-            head_rows=6, interact_bwd_cols=7, pdl=8, chain_order=9, upd_lean=10)
+            head_rows=6, interact_bwd_cols=7, pdl=8, chain_order=9, upd_lean=10, upd_debug=11)
 
 
 class EmbFwdTable(C.Structure):
@@ -27,7 +27,8 @@ class EmbBwdTable(C.Structure):
     _fields_ = [("weight", C.c_void_p), ("momentum", C.c_void_p), ("head", C.c_void_p),
                 ("indices", C.c_void_p), ("offsets", C.c_void_p), ("nnz", C.c_int64),
                 ("rows", C.c_int64), ("pair_base", C.c_int64), ("ld", C.c_int64), ("mom_stride", C.c_int64),
-                ("use_dy_off", C.c_int64), ("dy_off", C.c_int64), ("row_lo", C.c_int64), ("row_n", C.c_int64)]
+                ("use_dy_off", C.c_int64), ("dy_off", C.c_int64), ("row_lo", C.c_int64), ("row_n", C.c_int64),
+                ("head_stride", C.c_int64)]
 
 
 class EmbRemoteTable(C.Structure):
@@ -117,8 +118,8 @@ def _declare(lib):
     lib.dlrm_b200_linear_dgrad.argtypes = [vp, i64, vp, i64, vp, i64, i32, vp, i64, i64, i64, i64, i32, vp]
     lib.dlrm_b200_linear_wgrad.argtypes = [vp, i64, vp, i64, vp, i64, vp, i64, i64, i64, i32, vp]
     lib.dlrm_b200_interact_fwd.argtypes = [vp, i64, vp, i64, i64, i32, i32, i32, vp]
-    lib.dlrm_b200_interact_bwd_p2p.argtypes = [vp, i64, vp, i64, C.POINTER(vp), C.POINTER(i64), C.POINTER(i32), i64, i32,
-                                               i32, i32, i32, vp, vp, i64, vp]
+    lib.dlrm_b200_interact_bwd_p2p.argtypes = [vp, i64, vp, i64, C.POINTER(vp), C.POINTER(i64), C.POINTER(i32), f32, i64,
+                                               i32, i32, i32, i32, vp, vp, i64, vp]
     lib.dlrm_b200_interact_bwd.argtypes = [vp, i64, vp, i64, vp, i64, i64, i32, i32, i32, i32, vp]
     lib.dlrm_b200_loss_fwd_bwd.argtypes = [vp, vp, vp, i64, i32, f32, i32, vp, vp, vp, vp]
     lib.dlrm_b200_dense_update.argtypes = [vp, vp, vp, i64, i32, f32, f32, vp]

@@ -27,6 +27,7 @@ enum Tunable {
   TUNE_INTERACT_BWD_COLS = 7,   // 1 = one column per thread (first kernel), else float2 columns
   TUNE_PDL = 8,                 // programmatic dependent launch on the dense chain: 0/1 = on, 2 = off
   TUNE_UPD_LEAN = 10,           // embedding update: 0/1 = lean kernel for dim <= 128, 2 = the general kernel
+  TUNE_UPD_DEBUG = 11,          // timing experiments on the update kernel (see EmbBwdParams::debug); 0 = off
   TUNE_CHAIN_ORDER = 9,         // gemm_chain task order: 0/1 = layer by layer, 2 = m-tile major across layers
   TUNE_COUNT = 16
 };

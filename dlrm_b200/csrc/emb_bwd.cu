@@ -32,6 +32,7 @@ struct EmbBwdTable {
   long long pair_base;
   long long ld;          // row stride of w in floats
   long long mom_stride;  // elements between consecutive rows' accumulators
+  long long hs;          // elements between consecutive rows' list heads
   long long dy_off;      // the dY row of (bag, this table) is dy_row(bag) + dy_off
   long long rows;        // rows of the whole table
   long long row_lo;      // this shard stores rows [row_lo, row_lo + row_n) at local index (row - row_lo);
@@ -56,6 +57,8 @@ struct EmbBwdParams {
   long long peer_batch;
   // duplicate filter (optional): occurrences with flags[pos] == 0 are the only occurrence of their row
   const unsigned char* flags;
+  int debug;   // TIMING EXPERIMENTS ONLY (tunable upd_debug): 1 = no weight store, 2 = no weight load, 4 = no
+               // accumulator / list-head stores, 8 = no gradient load.  Results are wrong when non-zero.
 };
 
 __device__ __forceinline__ const float* dy_row(const EmbBwdParams& P, long long bag) {
@@ -95,7 +98,7 @@ __global__ void __launch_bounds__(256) emb_link_kernel(const __grid_constant__ E
     const long long r = (long long)idx[j] - tb.row_lo;
     const long long pos = tb.pair_base + j;
     const bool mine = tb.head != nullptr && (unsigned long long)r < (unsigned long long)tb.row_n;
-    const int prev = mine ? atomicExch(tb.head + r, (int)(pos + 1)) : 0;
+    const int prev = mine ? atomicExch(tb.head + r * tb.hs, (int)(pos + 1)) : 0;
     P.link[pos] = make_int2(prev, (int)lo);
   }
 }
@@ -129,20 +132,22 @@ __device__ __forceinline__ void st_pack(float* p, const Pack<W>& r) {
   }
 }
 
-// first global position of every table (+ end) in shared memory; see emb_update_kernel
+// first global position of every table of the call (+ the end of the last) in shared memory; tend[k] = end of
+// table k's own positions.  The tables of a call need not be adjacent in the position space (tiny tables are
+// updated by another kernel and leave gaps): a position p belongs to table k = table_of(p) only if p < tend[k].
 template <typename idx_t>
-__device__ __forceinline__ void load_bounds(long long* bound, const EmbBwdParams& P, int num_tables,
+__device__ __forceinline__ void load_bounds(long long* bound, long long* tend, const EmbBwdParams& P, int num_tables,
                                             long long total_hint) {
-  if ((int)threadIdx.x <= num_tables) {
+  if ((int)threadIdx.x < num_tables) {
     const int k = threadIdx.x;
-    long long v;
-    if (k < num_tables) {
-      v = P.include_last ? (long long)static_cast<const idx_t*>(P.t[k].off)[0] : P.t[k].pair_base;
-    } else {
-      v = P.include_last ? (long long)static_cast<const idx_t*>(P.t[num_tables - 1].off)[P.batch] : total_hint;
-    }
-    bound[k] = v;
+    const idx_t* off = static_cast<const idx_t*>(P.t[k].off);
+    const long long b = P.include_last ? (long long)off[0] : P.t[k].pair_base;
+    const long long e = P.include_last ? (long long)off[P.batch] : P.t[k].pair_base + P.t[k].nnz;
+    bound[k] = b;
+    tend[k] = e;
+    if (k == num_tables - 1) bound[num_tables] = e;
   }
+  (void)total_hint;
   __syncthreads();
 }
 // table of a position: largest k with bound[k] <= pos (empty tables share a bound)
@@ -163,8 +168,8 @@ __global__ void __launch_bounds__(256) emb_classify_kernel(const __grid_constant
                                                            long long total_hint, const unsigned* filter,
                                                            int log2_size, unsigned char* flags, int* suspects,
                                                            int* n_suspects) {
-  __shared__ long long bound[DLRM_B200_MAX_TABLES_PER_CALL + 1];
-  load_bounds<idx_t>(bound, P, num_tables, total_hint);
+  __shared__ long long bound[DLRM_B200_MAX_TABLES_PER_CALL + 1], tend[DLRM_B200_MAX_TABLES_PER_CALL + 1];
+  load_bounds<idx_t>(bound, tend, P, num_tables, total_hint);
   const int lane = threadIdx.x & 31;
   const long long first = bound[0], total = bound[num_tables];
   const long long warp0 = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -172,10 +177,11 @@ __global__ void __launch_bounds__(256) emb_classify_kernel(const __grid_constant
   for (long long base = first + warp0 * 32; base < total; base += wstride * 32) {
     const long long pos = base + lane;
     bool susp = false;
-    if (pos < total) {
-      const EmbBwdTable& tb = P.t[table_of(bound, num_tables, pos)];
+    const int kk = table_of(bound, num_tables, pos < total ? pos : first);
+    if (pos < total && pos < tend[kk]) {
+      const EmbBwdTable& tb = P.t[kk];
       const long long r = static_cast<const idx_t*>(tb.idx)[pos - tb.pair_base];
-      susp = filter[filter_slot(tb.head + r, log2_size)] > 1u;
+      susp = filter[filter_slot(tb.head + r * tb.hs, log2_size)] > 1u;
       flags[pos] = susp ? 1 : 0;
     }
     const unsigned m = __ballot_sync(0xffffffffu, susp);
@@ -193,14 +199,14 @@ template <typename idx_t>
 __global__ void __launch_bounds__(256) emb_link_suspects_kernel(const __grid_constant__ EmbBwdParams P,
                                                                 int num_tables, long long total_hint,
                                                                 const int* suspects, const int* n_suspects) {
-  __shared__ long long bound[DLRM_B200_MAX_TABLES_PER_CALL + 1];
-  load_bounds<idx_t>(bound, P, num_tables, total_hint);
+  __shared__ long long bound[DLRM_B200_MAX_TABLES_PER_CALL + 1], tend[DLRM_B200_MAX_TABLES_PER_CALL + 1];
+  load_bounds<idx_t>(bound, tend, P, num_tables, total_hint);
   const int n = *n_suspects;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
     const long long pos = suspects[i];
     const EmbBwdTable& tb = P.t[table_of(bound, num_tables, pos)];
     const long long r = static_cast<const idx_t*>(tb.idx)[pos - tb.pair_base];
-    P.link[pos].x = atomicExch(tb.head + r, (int)(pos + 1));
+    P.link[pos].x = atomicExch(tb.head + r * tb.hs, (int)(pos + 1));
   }
 }
 
@@ -212,8 +218,8 @@ __global__ void __launch_bounds__(256) emb_link_suspects_kernel(const __grid_con
 template <int W, int NV, typename idx_t>
 __global__ void __launch_bounds__(256, NV == 1 ? 3 : 1) emb_update_kernel(const __grid_constant__ EmbBwdParams P,
                                                                           int num_tables, long long total_hint) {
-  __shared__ long long bound[DLRM_B200_MAX_TABLES_PER_CALL + 1];
-  load_bounds<idx_t>(bound, P, num_tables, total_hint);
+  __shared__ long long bound[DLRM_B200_MAX_TABLES_PER_CALL + 1], tend[DLRM_B200_MAX_TABLES_PER_CALL + 1];
+  load_bounds<idx_t>(bound, tend, P, num_tables, total_hint);
   const int D = P.dim;
   const int lane = threadIdx.x & 31;
   const long long first = bound[0], total = bound[num_tables];
@@ -227,8 +233,8 @@ __global__ void __launch_bounds__(256, NV == 1 ? 3 : 1) emb_update_kernel(const 
 
   for (long long base = first + warp0 * 32; base < total; base += wstride * 32) {
     const long long pos = base + lane;
-    const bool valid = pos < total;
-    const int k = table_of(bound, num_tables, pos);
+    const int k = table_of(bound, num_tables, pos < total ? pos : first);
+    const bool valid = pos < total && pos < tend[k];
     long long my_r = 0;
     int my_head = 0;
     int2 my_link = make_int2(0, 0);
@@ -243,7 +249,7 @@ __global__ void __launch_bounds__(256, NV == 1 ? 3 : 1) emb_update_kernel(const 
         my_link = P.link[pos];
         if (P.flags) my_susp = P.flags[pos] != 0;
         // an unflagged occurrence is the only one of its row: it owns the row, head[] is never touched
-        my_head = my_susp ? tb.head[my_r] : (int)(pos + 1);
+        my_head = my_susp ? tb.head[my_r * tb.hs] : (int)(pos + 1);
         if (!my_susp) my_link.x = 0;
       }
     }
@@ -352,7 +358,7 @@ __global__ void __launch_bounds__(256, NV == 1 ? 3 : 1) emb_update_kernel(const 
               st_pack<W>(wrow + lane * W + v * 32 * W, w[v]);
             }
         }
-        if (lane == 0 && ((susp_mask >> src) & 1u)) tb.head[r] = 0;
+        if (lane == 0 && ((susp_mask >> src) & 1u)) tb.head[r * tb.hs] = 0;
       }
     }
   }
@@ -380,7 +386,7 @@ struct UpdTableS {
   float* mom;
   int* head;
   const void* idx;
-  long long pair_base, ld, mom_stride, dy_off, row_lo, row_n;
+  long long pair_base, ld, mom_stride, hs, dy_off, row_lo, row_n;
 };
 
 __device__ __noinline__ float4 upd_sum_duplicates(const EmbBwdParams& P, int nxt, int self_pos, int self_bag,
@@ -415,36 +421,41 @@ __device__ __noinline__ float4 upd_sum_duplicates(const EmbBwdParams& P, int nxt
   return g;
 }
 
-template <typename idx_t>
+template <typename idx_t, int PF>      // PF: row PAIRS in flight per warp
 __global__ void __launch_bounds__(256, 3) emb_update_lean_kernel(const __grid_constant__ EmbBwdParams P, int num_tables,
                                                                  long long total_hint) {
-  __shared__ long long bound[DLRM_B200_MAX_TABLES_PER_CALL + 1];
+  __shared__ long long bound[DLRM_B200_MAX_TABLES_PER_CALL + 1], tend[DLRM_B200_MAX_TABLES_PER_CALL + 1];
   __shared__ UpdTableS ts[DLRM_B200_MAX_TABLES_PER_CALL];
   for (int k = threadIdx.x; k < num_tables; k += blockDim.x) {
     UpdTableS t;
     t.w = P.t[k].w; t.mom = P.t[k].mom; t.head = P.t[k].head; t.idx = P.t[k].idx;
-    t.pair_base = P.t[k].pair_base; t.ld = P.t[k].ld; t.mom_stride = P.t[k].mom_stride;
+    t.pair_base = P.t[k].pair_base; t.ld = P.t[k].ld; t.mom_stride = P.t[k].mom_stride; t.hs = P.t[k].hs;
     t.dy_off = P.t[k].dy_off; t.row_lo = P.t[k].row_lo; t.row_n = P.t[k].row_n;
     ts[k] = t;
   }
-  load_bounds<idx_t>(bound, P, num_tables, total_hint);     // ends with __syncthreads()
+  load_bounds<idx_t>(bound, tend, P, num_tables, total_hint);     // ends with __syncthreads()
   const int D = P.dim;
   const int lane = threadIdx.x & 31;
-  const bool col_ok = lane * 4 < D;
+  // Rows WITHOUT duplicates (almost all of them at large tables) are processed TWO per warp step: lanes 0-15
+  // take one row, lanes 16-31 another, 8 columns (two float4) per lane.  Every shuffle / FMA / branch of the
+  // step then serves two rows, and twice as many rows are in flight per warp.
+  const int half = lane >> 4, l16 = lane & 15;
+  const bool c0_ok = l16 * 8 < D, c1_ok = l16 * 8 + 4 < D;
+  const bool col_ok = lane * 4 < D;                          // full-warp layout of the duplicate path
   const long long first = bound[0], total = bound[num_tables];
   const long long warp0 = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const long long wstride = (long long)gridDim.x * (blockDim.x >> 5);
   const float inv_d = 1.0f / (float)D;
   const float nlr = -P.lr;
   const bool adagrad = P.optimizer == DLRM_OPT_RWSADAGRAD;
-  constexpr int PF = 4;
+  const int dbg = P.debug;
 
   for (long long base = first + warp0 * 32; base < total; base += wstride * 32) {
     const long long pos = base + lane;
-    const bool valid = pos < total;
     // table of this window: lane 0's, unless the window crosses into the next table
     int k = table_of(bound, num_tables, base);
-    if (base + 31 >= bound[k + 1]) k = table_of(bound, num_tables, valid ? pos : base);
+    if (base + 31 >= bound[k + 1]) k = table_of(bound, num_tables, pos < total ? pos : base);
+    const bool valid = pos < total && pos < tend[k];       // positions between two tables of the call are not ours
     const UpdTableS& tb = ts[k];
     float* wptr = nullptr;
     const float* gptr = nullptr;
@@ -455,7 +466,7 @@ __global__ void __launch_bounds__(256, 3) emb_update_lean_kernel(const __grid_co
     if (valid && tb.head != nullptr) {
       const long long r = (long long)static_cast<const idx_t*>(tb.idx)[pos - tb.pair_base] - tb.row_lo;
       if ((unsigned long long)r < (unsigned long long)tb.row_n) {
-        hptr = tb.head + r;
+        hptr = tb.head + r * tb.hs;
         if (*hptr == (int)(pos + 1)) {          // the last occurrence to arrive owns the row
           owner = true;
           const int2 lk = P.link[pos];
@@ -468,51 +479,82 @@ __global__ void __launch_bounds__(256, 3) emb_update_lean_kernel(const __grid_co
       }
     }
     float m_old = (owner && adagrad) ? *mptr : 0.f;
-    unsigned owners = __ballot_sync(0xffffffffu, owner);
-    while (owners) {
-      float4 wv[PF], gv[PF];
-      int src[PF];
+    unsigned simple = __ballot_sync(0xffffffffu, owner && nxt == 0);
+    unsigned dups = __ballot_sync(0xffffffffu, owner && nxt != 0);
+
+    // ---------------------------------------------------------------- rows without duplicates, two per step
+    while (simple) {
+      float4 wv[PF][2], gv[PF][2];
+      int sa[PF], sb[PF];
 #pragma unroll
       for (int u = 0; u < PF; ++u) {
-        src[u] = owners ? __ffs(owners) - 1 : -1;
-        owners &= owners - 1u;
-        const int s_ = src[u] < 0 ? 0 : src[u];
-        const float* wp = reinterpret_cast<const float*>(__shfl_sync(0xffffffffu, (unsigned long long)wptr, s_));
-        const float* gp = reinterpret_cast<const float*>(__shfl_sync(0xffffffffu, (unsigned long long)gptr, s_));
-        if (src[u] >= 0 && col_ok) {
-          wv[u] = *reinterpret_cast<const float4*>(wp + lane * 4);
-          gv[u] = *reinterpret_cast<const float4*>(gp + lane * 4);
-        } else {
-          wv[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-          gv[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-        }
+        sa[u] = simple ? __ffs(simple) - 1 : -1;
+        simple &= simple - 1u;
+        sb[u] = simple ? __ffs(simple) - 1 : -1;
+        simple &= simple - 1u;
+        const int s_ = half ? sb[u] : sa[u];
+        const int sc = s_ < 0 ? 0 : s_;
+        const float* wp = reinterpret_cast<const float*>(__shfl_sync(0xffffffffu, (unsigned long long)wptr, sc)) + l16 * 8;
+        const float* gp = reinterpret_cast<const float*>(__shfl_sync(0xffffffffu, (unsigned long long)gptr, sc)) + l16 * 8;
+        const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+        const bool ldw = !(dbg & 2), ldg = !(dbg & 8);
+        wv[u][0] = (s_ >= 0 && c0_ok && ldw) ? *reinterpret_cast<const float4*>(wp) : z;
+        wv[u][1] = (s_ >= 0 && c1_ok && ldw) ? *reinterpret_cast<const float4*>(wp + 4) : z;
+        gv[u][0] = (s_ >= 0 && c0_ok && ldg) ? *reinterpret_cast<const float4*>(gp) : z;
+        gv[u][1] = (s_ >= 0 && c1_ok && ldg) ? *reinterpret_cast<const float4*>(gp + 4) : z;
       }
 #pragma unroll
       for (int u = 0; u < PF; ++u) {
-        if (src[u] < 0) break;
-        const int s_ = src[u];
-        float4 g = gv[u];
-        const int nx = __shfl_sync(0xffffffffu, nxt, s_);
-        if (nx != 0) {                          // duplicates: sum the list (uniform branch)
-          const int sb = __shfl_sync(0xffffffffu, bag, s_);
-          const long long dyo = __shfl_sync(0xffffffffu, tb.dy_off, s_);     // the OWNER's table (windows may straddle)
-          g = upd_sum_duplicates(P, nx, (int)(base + s_), sb, dyo, lane, col_ok);
-        }
+        if (sa[u] < 0) break;
+        const int s_ = half ? sb[u] : sa[u];
+        const int sc = s_ < 0 ? 0 : s_;
+        const float4 g0 = gv[u][0], g1 = gv[u][1];
         float scale = nlr;
         if (adagrad) {
-          float sq = fmaf(g.x, g.x, fmaf(g.y, g.y, fmaf(g.z, g.z, g.w * g.w)));
-          sq = warp_sum(sq);
-          const float m_new = __shfl_sync(0xffffffffu, m_old, s_) + sq * inv_d;
+          float sq = fmaf(g0.x, g0.x, fmaf(g0.y, g0.y, fmaf(g0.z, g0.z, g0.w * g0.w)));
+          sq = fmaf(g1.x, g1.x, fmaf(g1.y, g1.y, fmaf(g1.z, g1.z, fmaf(g1.w, g1.w, sq))));
+#pragma unroll
+          for (int o = 8; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);     // within the half
+          const float m_new = __shfl_sync(0xffffffffu, m_old, sc) + sq * inv_d;
           scale = nlr / (sqrtf(m_new) + P.eps);
-          if (lane == s_) *mptr = m_new;
+          const float mA = __shfl_sync(0xffffffffu, m_new, 0), mB = __shfl_sync(0xffffffffu, m_new, 16);
+          if (lane == sa[u] && !(dbg & 4)) *mptr = mA;               // the owning lanes store their accumulators
+          if (lane == sb[u] && !(dbg & 4)) *mptr = mB;
         }
-        float4 w = wv[u];
-        w.x = fmaf(scale, g.x, w.x); w.y = fmaf(scale, g.y, w.y);
-        w.z = fmaf(scale, g.z, w.z); w.w = fmaf(scale, g.w, w.w);
-        float* wp = reinterpret_cast<float*>(__shfl_sync(0xffffffffu, (unsigned long long)wptr, s_));
-        if (col_ok) *reinterpret_cast<float4*>(wp + lane * 4) = w;
-        if (lane == s_) *hptr = 0;
+        float* wp = reinterpret_cast<float*>(__shfl_sync(0xffffffffu, (unsigned long long)wptr, sc)) + l16 * 8;
+        if (s_ >= 0) {
+          float4 w0 = wv[u][0], w1 = wv[u][1];
+          w0.x = fmaf(scale, g0.x, w0.x); w0.y = fmaf(scale, g0.y, w0.y); w0.z = fmaf(scale, g0.z, w0.z); w0.w = fmaf(scale, g0.w, w0.w);
+          w1.x = fmaf(scale, g1.x, w1.x); w1.y = fmaf(scale, g1.y, w1.y); w1.z = fmaf(scale, g1.z, w1.z); w1.w = fmaf(scale, g1.w, w1.w);
+          if (c0_ok && !(dbg & 1)) *reinterpret_cast<float4*>(wp) = w0;
+          if (c1_ok && !(dbg & 1)) *reinterpret_cast<float4*>(wp + 4) = w1;
+        }
+        if ((lane == sa[u] || lane == sb[u]) && !(dbg & 4)) *hptr = 0;
       }
+    }
+
+    // ---------------------------------------------------------------- rows with duplicates, one per step
+    while (dups) {
+      const int s_ = __ffs(dups) - 1;
+      dups &= dups - 1u;
+      const int nx = __shfl_sync(0xffffffffu, nxt, s_);
+      const int sbg = __shfl_sync(0xffffffffu, bag, s_);
+      const long long dyo = __shfl_sync(0xffffffffu, tb.dy_off, s_);       // the OWNER's table (windows may straddle)
+      float* wp = reinterpret_cast<float*>(__shfl_sync(0xffffffffu, (unsigned long long)wptr, s_));
+      float4 w = col_ok ? *reinterpret_cast<const float4*>(wp + lane * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+      const float4 g = upd_sum_duplicates(P, nx, (int)(base + s_), sbg, dyo, lane, col_ok);
+      float scale = nlr;
+      if (adagrad) {
+        float sq = fmaf(g.x, g.x, fmaf(g.y, g.y, fmaf(g.z, g.z, g.w * g.w)));
+        sq = warp_sum(sq);
+        const float m_new = __shfl_sync(0xffffffffu, m_old, s_) + sq * inv_d;
+        scale = nlr / (sqrtf(m_new) + P.eps);
+        if (lane == s_) *mptr = m_new;
+      }
+      w.x = fmaf(scale, g.x, w.x); w.y = fmaf(scale, g.y, w.y);
+      w.z = fmaf(scale, g.z, w.z); w.w = fmaf(scale, g.w, w.w);
+      if (col_ok) *reinterpret_cast<float4*>(wp + lane * 4) = w;
+      if (lane == s_) *hptr = 0;
     }
   }
 }
@@ -536,6 +578,7 @@ static int fill_params(EmbBwdParams& P, const dlrm_emb_bwd_table_t* tables, int 
     P.t[k].pair_base = tables[k].pair_base;
     P.t[k].ld = tables[k].ld;   // 0 -> dim, resolved by the update entry point
     P.t[k].mom_stride = tables[k].mom_stride > 0 ? tables[k].mom_stride : 1;
+    P.t[k].hs = tables[k].head_stride > 0 ? tables[k].head_stride : 1;
     P.t[k].dy_off = 0;          // resolved by the update entry point
     P.t[k].rows = tables[k].rows > 0 ? tables[k].rows : 0x7fffffffffffffffLL;
     P.t[k].row_lo = tables[k].row_n > 0 ? tables[k].row_lo : 0;
@@ -623,6 +666,7 @@ static int emb_update_impl(const dlrm_emb_bwd_table_t* tables, int num_tables, i
   P.optimizer = optimizer;
   P.lr = lr;
   P.eps = eps;
+  P.debug = get_tunable(TUNE_UPD_DEBUG);
   const int block = 256;
   long long total = 0;
   for (int k = 0; k < num_tables; ++k) total += tables[k].nnz;   // reference format: exact; packed: capacity
@@ -653,8 +697,14 @@ static int emb_update_impl(const dlrm_emb_bwd_table_t* tables, int num_tables, i
     long long gl = (total / 32 + block / 32) / (block / 32);
     if (gl > (long long)sms * 3) gl = (long long)sms * 3;
     if (gl < 1) gl = 1;
-    if (idx_bytes == 8) emb_update_lean_kernel<long long><<<(unsigned)gl, block, 0, st>>>(P, num_tables, total_hint);
-    else emb_update_lean_kernel<int><<<(unsigned)gl, block, 0, st>>>(P, num_tables, total_hint);
+    const bool pf2 = get_tunable(TUNE_UPD_LEAN) == 3;     // 2 row pairs in flight (79 registers, no spills) instead of 3
+    if (idx_bytes == 8) {
+      if (pf2) emb_update_lean_kernel<long long, 2><<<(unsigned)gl, block, 0, st>>>(P, num_tables, total_hint);
+      else emb_update_lean_kernel<long long, 3><<<(unsigned)gl, block, 0, st>>>(P, num_tables, total_hint);
+    } else {
+      if (pf2) emb_update_lean_kernel<int, 2><<<(unsigned)gl, block, 0, st>>>(P, num_tables, total_hint);
+      else emb_update_lean_kernel<int, 3><<<(unsigned)gl, block, 0, st>>>(P, num_tables, total_hint);
+    }
     DLRM_CHECK_LAUNCH("emb_update_lean_kernel");
     return 0;
   }

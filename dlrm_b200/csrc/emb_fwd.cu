@@ -20,6 +20,8 @@ struct EmbFwdTable {
   const float* rw;
   long long nnz;
   int* head;            // training: per-row list heads of this table (see emb_bwd.cu); null = do not link
+  long long hs;         // elements between the list heads of consecutive rows (1, or the row stride when the
+                        // head lives inside the row's own DRAM page: [weights | accumulator | head | pad])
   long long pair_base;  // training: first slot of this table in link[]
   long long ld;         // row stride in floats
   long long out_off;    // pooled row of bag b goes to out_row(b) [+ b_local * out_stride] + out_off
@@ -53,10 +55,10 @@ struct EmbFwdParams {
 __device__ __forceinline__ int note_occurrence(const EmbFwdParams& P, const EmbFwdTable& tb, long long row,
                                                long long pos_local) {
   if (P.filter) {
-    atomicAdd(P.filter + filter_slot(tb.head + row, P.filter_log2), 1u);
+    atomicAdd(P.filter + filter_slot(tb.head + row * tb.hs, P.filter_log2), 1u);
     return 0;
   }
-  return atomicExch(tb.head + row, (int)(tb.pair_base + pos_local + 1));
+  return atomicExch(tb.head + row * tb.hs, (int)(tb.pair_base + pos_local + 1));
 }
 
 // Where the pooled row of (table tb, global bag b) goes: buffer of the rank that owns the sample (peer-mapped
@@ -467,6 +469,7 @@ static int emb_fwd_impl(const dlrm_emb_fwd_table_t* tables, const dlrm_emb_bwd_t
     if (P.t[k].ld < dim) return set_error("emb_bag_fwd: table %d: ld=%lld < dim", k, (long long)tables[k].ld);
     vec_ok = vec_ok && (P.t[k].ld % 4 == 0);
     P.t[k].head = train ? train[k].head : nullptr;   // train[k].head == NULL: this table is not linked
+    P.t[k].hs = (train && train[k].head_stride > 0) ? train[k].head_stride : 1;
     P.t[k].pair_base = train ? train[k].pair_base : 0;
     // per-table output routing (0 = the call-level layout out[b, k, :])
     P.t[k].out_stride = tables[k].out_stride > 0 ? tables[k].out_stride : out_stride_sample;

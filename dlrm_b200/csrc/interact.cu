@@ -200,6 +200,7 @@ struct FeatRoute {
   float* base[ROUTE_MAX_DST];
   long long ld[ROUTE_MAX_DST];
   unsigned char first[66];     // destinations [first[i], first[i + 1]) belong to feature i
+  float emb_scale;             // factor on the gradient rows of features >= 1 (see dlrm_b200_interact_bwd_p2p)
 };
 
 struct NoRoute {};
@@ -261,7 +262,8 @@ __global__ void __launch_bounds__(128) interact_bwd_kernel(const float* __restri
       if (i == 0 && mask0 == DLRM_ACT_RELU) acc = (t[0] > 0.f) ? acc : 0.f;
       if (i == 0 && mask0 == DLRM_ACT_SIGMOID) acc *= (1.0f - t[0]) * t[0];
       if constexpr (ROUTE) {
-        for (int q = route.first[i]; q < route.first[i + 1]; ++q) route.base[q][(s0 + s) * route.ld[q] + d] = acc;
+        const float a_ = i ? acc * route.emb_scale : acc;
+        for (int q = route.first[i]; q < route.first[i + 1]; ++q) route.base[q][(s0 + s) * route.ld[q] + d] = a_;
       } else {
         out[(long long)i * D] = acc;
       }
@@ -342,8 +344,9 @@ __global__ void __launch_bounds__(128) interact_bwd2_kernel(const float* __restr
         acc.y *= (1.0f - t[0].y) * t[0].y;
       }
       if constexpr (ROUTE) {
+        const float2 a_ = i ? make_float2(acc.x * route.emb_scale, acc.y * route.emb_scale) : acc;
         for (int q = route.first[i]; q < route.first[i + 1]; ++q)
-          *reinterpret_cast<float2*>(route.base[q] + (s0 + s) * route.ld[q] + d) = acc;
+          *reinterpret_cast<float2*>(route.base[q] + (s0 + s) * route.ld[q] + d) = a_;
       } else {
         *reinterpret_cast<float2*>(dT + (s0 + s) * lddt + (long long)i * D + d) = acc;
       }
@@ -481,8 +484,8 @@ extern "C" int dlrm_b200_interact_bwd_ex(const float* T, int64_t ldt, const floa
 
 extern "C" int dlrm_b200_interact_bwd_p2p(const float* T, int64_t ldt, const float* dR, int64_t lddr,
                                           void* const* feat_dst, const int64_t* feat_ld, const int* feat_first,
-                                          int64_t batch, int num_features, int dim, int itself, int mask_feature0,
-                                          void* g0_hi, void* g0_lo, int64_t ld_g0, void* stream) {
+                                          float emb_grad_scale, int64_t batch, int num_features, int dim, int itself,
+                                          int mask_feature0, void* g0_hi, void* g0_lo, int64_t ld_g0, void* stream) {
   using namespace dlrm;
   if (!feat_dst || !feat_ld || !feat_first) return set_error("interact_bwd_p2p: NULL route");
   if (num_features > 64) return set_error("interact_bwd_p2p: num_features=%d > 64", num_features);
@@ -490,6 +493,7 @@ extern "C" int dlrm_b200_interact_bwd_p2p(const float* T, int64_t ldt, const flo
   if (feat_first[0] != 0 || ndst < num_features || ndst > ROUTE_MAX_DST)
     return set_error("interact_bwd_p2p: %d destinations for %d features (max %d)", ndst, num_features, ROUTE_MAX_DST);
   FeatRoute r = {};
+  r.emb_scale = emb_grad_scale;
   for (int i = 0; i <= num_features; ++i) {
     if (i && feat_first[i] <= feat_first[i - 1]) return set_error("interact_bwd_p2p: feature %d has no destination", i - 1);
     r.first[i] = (unsigned char)feat_first[i];

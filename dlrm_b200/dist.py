@@ -130,7 +130,8 @@ class DistEngine:
 
     def __init__(self, m_spa: int, ln_emb: Sequence[int], ln_bot: Sequence[int], ln_top: Sequence[int], *,
                  local_batch: int, device=None, gemm: str = "tc", loss: str = "bce", exchange: str = "nccl",
-                 placement=None, cost: Optional[Sequence[float]] = None, split_forward: str = "partial", **kw):
+                 placement=None, cost: Optional[Sequence[float]] = None, split_forward: str = "partial",
+                 semantics: str = "reference", **kw):
         from . import placement as P, sharding as S
         from .engine import Engine
 
@@ -171,6 +172,19 @@ class DistEngine:
                           sigmoid_top=len(ln_top) - 2, **kw)
         e = self.eng
         f32 = torch.float32
+        # "reference": every rank's loss is the mean over ITS batch slice, dense gradients are averaged (DDP) and
+        # embedding gradients SUMMED over the ranks (the all-to-all backward just routes them,
+        # extend_distributed.py:467-486) -- i.e. world x the single-process embedding gradient, exactly what
+        # `torchrun dlrm_s_pytorch.py` computes.  "single_process": embedding gradients scaled by 1/world = the
+        # gradient of the GLOBAL mean loss, so the run reproduces a single-process run of the whole batch (what
+        # the live-reference goldens record).  The two differ by one scalar inside the interaction backward.
+        if semantics not in ("reference", "single_process"):
+            raise SystemExit("ERROR: semantics must be reference or single_process")
+        self.semantics = semantics
+        if semantics == "single_process":
+            if exchange != "p2p":
+                raise SystemExit("ERROR: semantics=single_process needs exchange=p2p")
+            e.emb_grad_scale = 1.0 / self.world
         e.dense_sync_fn = self._dense_sync
         self._flag = torch.zeros(1, dtype=f32, device=self.device)
         if exchange == "p2p":
@@ -365,16 +379,23 @@ class DistEngine:
     def train_step(self, X_local, sp_local_shards, target_local, lr, optimizer="rwsadagrad"):
         return self.eng.train_step(X_local, sp_local_shards, target_local, lr, optimizer)
 
-    def nvlink_bytes_per_step(self, step_seconds: float, staged_index_bytes: int = 0) -> dict:
+    def nvlink_bytes_per_step(self, step_seconds: float, staged_index_bytes: int = 0, lookups=None) -> dict:
         """Bytes THIS rank pushes to its peers per training step (peer stores over NVLink) and what that is per
         second of step time (a lower bound of the link rate: the pushes happen inside three kernels, not all step)."""
         W, B, D = self.world, self.B, self.D
         remote = (W - 1) / W if W > 1 else 0.0
         fwd = len(self.mine) * self.Bg * D * 4 * remote                    # pooled rows / partial sums of all samples
+        rd = 0.0
+        if self.eng.remote_tables is not None:                              # remote-read forward of the split tables:
+            nsplit = sum(1 for s in self.mine if not s.whole)               # no partial sums pushed, rows PULLED instead
+            fwd -= nsplit * self.Bg * D * 4 * remote
+            if lookups is not None:
+                rd = sum(float(lookups[t]) for t in self.pl.split_tables()) * B * D * 4 * remote
         bwd = sum(sum(1 for s in self.pl.of_table(t) if s.rank != self.rank) for t in range(self.Tg)) * B * D * 4
         idx = staged_index_bytes * remote                                    # upper bound: split tables go to every rank
-        tot = fwd + bwd + idx
-        return {"pooled_rows_fwd": fwd, "gradient_rows_bwd": bwd, "indices": idx, "total_bytes_per_rank_per_step": tot,
+        tot = fwd + bwd + idx + rd
+        return {"pooled_rows_fwd": fwd, "remote_rows_read_fwd": rd, "gradient_rows_bwd": bwd, "indices": idx,
+                "total_bytes_per_rank_per_step": tot,
                 "gb_per_s_over_step": tot / max(step_seconds, 1e-12) / 1e9, "measured_link_peak_gb_s": 770.0}
 
     def gather_bytes_per_step(self, lookups_per_sample: Sequence[float]) -> float:

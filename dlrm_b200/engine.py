@@ -71,7 +71,7 @@ class Engine:
                  *, op: str = "dot", itself: bool = False, sigmoid_bot: int = -1, sigmoid_top: int = -1,
                  loss: str = "bce", loss_threshold: float = 0.0, loss_ws=None, device="cuda:0",
                  max_batch: int = 2048, gemm: str = "simt", n_features: Optional[int] = None,
-                 interleave_momentum: bool = False, shards=None, split_slots=None, small_rows_max: int = 256):
+                 interleave_momentum: Optional[bool] = None, shards=None, split_slots=None, small_rows_max: int = 256):
         if not torch.cuda.is_available():
             raise RuntimeError("dlrm_b200.Engine needs a CUDA device (B200, sm_100a); there is no CPU path")
         self.device = torch.device(device)
@@ -132,15 +132,19 @@ class Engine:
         rows = np.asarray(self.ln_emb, dtype=np.int64)
         self.row_base = np.concatenate([[0], np.cumsum(rows)]).astype(np.int64)
         self.total_rows = int(self.row_base[-1])
-        # Default: dense [rows, D] tables (512-byte aligned rows at D=128) + a separate accumulator array.
-        # interleave_momentum=True stores [D weights | accumulator | 3 pad] per row (stride D+4) so the
-        # accumulator shares the row's DRAM burst.  Measured on B200 (r12, profiles/README.md): the update
-        # does not get faster (126-129 us either way) and the gather loses 6-7 points of HBM efficiency
-        # because rows are no longer 512-byte aligned -> kept as an option, off.
+        # Row layout.  interleave (default when D % 4 == 0): [D weights | Adagrad accumulator | list head (int32) |
+        # 2 pad], row stride D + 4 floats -- the two per-row words of the backward live in the row's own DRAM page.
+        # Measured (profiles/README.md, r2_12): the update kernel is bound by the RATE of random DRAM accesses
+        # (~10 G/s: a 4-byte head[] read costs what a 512-byte row costs); dropping the weight-row traffic
+        # entirely only saved 26 %, the separate head / accumulator arrays are the rest.  The gather pays a few
+        # points of bandwidth for rows that are no longer 512-byte aligned (528-byte stride).
+        # interleave=False: dense [rows, D] tables + separate accumulator / head arrays (round 1's layout).
+        if interleave_momentum is None:
+            interleave_momentum = (self.D % 4 == 0) and os.environ.get("DLRM_ROW_META", "1") != "0"
         self.interleave = bool(interleave_momentum)
         self.ldw = self.D + 4 if self.interleave else self.D
         self.tables = torch.zeros((self.total_rows, self.ldw), dtype=torch.float32, device=dev)
-        self.head = torch.zeros(self.total_rows, dtype=torch.int32, device=dev)
+        self._head_sep = None if self.interleave else torch.zeros(self.total_rows, dtype=torch.int32, device=dev)
         self._momentum_sep: Optional[torch.Tensor] = None
         self.row_weights: Optional[torch.Tensor] = None  # weighted pooling v_W_l, arena [total_rows]
         # ---- dense arena
@@ -182,6 +186,7 @@ class Engine:
         # Row-split tables, forward variant "remote" (BASELINE north_star: P2P reads of remote rows): table ->
         # ([base pointer of every shard], rows per shard); the rank that owns a sample pools the whole bag itself,
         # reading each row from the rank that stores it, instead of every rank pooling a partial sum.
+        self.emb_grad_scale = 1.0    # sharded runs: factor on the embedding gradient rows (DistEngine.semantics)
         self.remote_tables = None
         self.remote_sample0 = 0      # first global sample of THIS rank (its bags inside the global index streams)
         # side streams: the gather runs beside the bottom MLP, the weight-gradient GEMMs and the
@@ -238,7 +243,7 @@ class Engine:
         """Tiny whole tables take the dense two-pass update (csrc/emb_small.cu) instead of the per-row lists."""
         sh = self.shards[j]
         return (int(sh["nparts"]) == 1 and self.ln_emb[j] <= self.small_rows_max and self.D % 4 == 0
-                and self.D <= 512 and not self.interleave)
+                and self.D <= 512)
 
     def _set_default_routes(self):
         """Single-GPU routes.  out: (offset, sample stride) of shard j's pooled rows inside TP; dy: offset of
@@ -341,6 +346,11 @@ class Engine:
         return self.tables[int(self.row_base[k]):int(self.row_base[k + 1]), :self.D]
 
     @property
+    def head(self) -> torch.Tensor:
+        """Per-row list heads of the sort-free coalesce, [sum rows] int32 (a strided view when interleaved)."""
+        return self.tables.view(torch.int32)[:, self.D + 1] if self.interleave else self._head_sep
+
+    @property
     def momentum(self) -> Optional[torch.Tensor]:
         """Row-wise Adagrad accumulator of every row, [sum rows] (a strided view when interleaved)."""
         return self.tables[:, self.D] if self.interleave else self._momentum_sep
@@ -431,7 +441,12 @@ class Engine:
                               if self._momentum_sep is not None else None)
                 d.mom_stride = 1
             # tiny tables are neither linked nor list-updated (head NULL): emb_small_update handles them
-            d.head = None if self.is_small(k) else self.head.data_ptr() + int(self.row_base[k]) * 4
+            if self.is_small(k):
+                d.head = None
+            elif self.interleave:
+                d.head, d.head_stride = d.weight + (self.D + 1) * 4, self.ldw
+            else:
+                d.head, d.head_stride = self._head_sep.data_ptr() + int(self.row_base[k]) * 4, 1
             d.indices = sp.indices[k].data_ptr() if sp.indices[k].numel() else 0
             d.offsets = sp.offsets[k].data_ptr()
             d.nnz = sp.indices[k].numel()
@@ -898,7 +913,8 @@ class Engine:
         """interact_bwd whose per-feature gradient rows go straight to their (possibly remote) consumers."""
         dst, ld, first = self.dT_route
         _lib.check(self.lib.dlrm_b200_interact_bwd_p2p(self.Tbuf.data_ptr(), self.F * self.D, self.dR.data_ptr(),
-                                                       self.ldr, dst, ld, first, B, self.F, self.D, int(self.itself),
+                                                       self.ldr, dst, ld, first, float(self.emb_grad_scale), B, self.F,
+                                                       self.D, int(self.itself),
                                                        bot_last_act, g0h, g0l, ldg0, stream),
                    "interact_bwd_p2p")
 

@@ -121,6 +121,11 @@ typedef struct {
    * not updated by dlrm_b200_emb_bwd_update (tiny tables: dlrm_b200_emb_bwd_small_update). */
   int64_t use_dy_off, dy_off;
   int64_t row_lo, row_n;
+  /* elements between consecutive rows' list heads; 0 = 1.  head = (int32*)weight + dim + 1 with head_stride = ld
+   * (and momentum = weight + dim, mom_stride = ld, ld = dim + 4) keeps BOTH per-row words inside the row's own
+   * DRAM page: the update is bound by the RATE of random DRAM accesses (~10 G/s measured: the gather's 512-byte
+   * rows and the update's 4-byte words cost the same), so 6 accesses per occurrence become 2-3. */
+  int64_t head_stride;
 } dlrm_emb_bwd_table_t;
 
 /* Optional duplicate filter (dlrm_emb_dedup_t): at 1e6-row tables almost every row of a batch is
@@ -250,10 +255,14 @@ int dlrm_b200_interact_bwd_ex(const float* T, int64_t ldt, const float* dR, int6
  * every destination q in [feat_first[i], feat_first[i+1]) instead of dT (at most 128 destinations in all).
  * On a sharded run the destinations of feature 1 + t point into the receive buffers of the rank(s) storing
  * table t (peer-mapped over NVLink; a row-split table has one on every rank), which replaces the backward
- * all-to-all of dlrm_s_pytorch.py:545-560 / extend_distributed.py:alltoall backward; feature 0 stays local. */
+ * all-to-all of dlrm_s_pytorch.py:545-560 / extend_distributed.py:alltoall backward; feature 0 stays local.
+ * emb_grad_scale multiplies the rows of features >= 1: 1 = the reference's distributed semantics (every rank's
+ * loss is the mean over ITS batch slice and the embedding gradients of the ranks are SUMMED, i.e. world x the
+ * single-process gradient); 1/world = the gradient of the global mean loss (equals a single-process run). */
 int dlrm_b200_interact_bwd_p2p(const float* T, int64_t ldt, const float* dR, int64_t lddr,
                                void* const* feat_dst /*[host][ndst]*/, const int64_t* feat_ld /*[host][ndst]*/,
-                               const int* feat_first /*[host][F+1]*/, int64_t batch, int num_features, int dim,
+                               const int* feat_first /*[host][F+1]*/, float emb_grad_scale, int64_t batch,
+                               int num_features, int dim,
                                int itself, int mask_feature0, void* g0_hi, void* g0_lo, int64_t ld_g0,
                                void* stream);
 int dlrm_b200_interact_bwd(const float* T, int64_t ldt, const float* dR, int64_t lddr,

@@ -305,7 +305,7 @@ def test_interact_bwd_routed_equals_plain(F, D, itself):
     n = len(dst)
     _lib.check(lib.dlrm_b200_interact_bwd_p2p(T.data_ptr(), F * D, dR.data_ptr(), D + npairs,
                                               (C.c_void_p * n)(*dst), (C.c_int64 * n)(*ld), (C.c_int * (F + 1))(*first),
-                                              B, F, D, itself, 1, None, None, 0, s), "interact_bwd_p2p")
+                                              1.0, B, F, D, itself, 1, None, None, 0, s), "interact_bwd_p2p")
     torch.cuda.synchronize()
     ref = dT.view(B, F, D)
     assert torch.equal(extra[:, 2], ref[:, F - 1]) and float(extra[:, :2].abs().sum()) == 0.0
