@@ -471,8 +471,40 @@ def ours(args, W):
         gbs = [gb]
     gbs = [float(g.item()) for g in gbs]
 
+    # ---- optional phase timeline (eager launches, timing events on every stream): where the step's time goes
+    phases = None
+    if args.phases > 0:
+        acc = {}
+        order = []
+        for r in range(args.phases + 2):
+            k = r % nsets
+            load_dev(k, r)
+            sync_all()
+            de.eng._marks = []
+            de.eng._mark("step_begin")
+            p = pre(k)
+            if p is not None:
+                p()
+                de.eng._mark("index_exchange")
+            if train:
+                de.eng.train_step(stages[k].X, stages[k].sparse, stages[k].target, lr, "rwsadagrad")
+            else:
+                de.eng.forward(stages[k].X, stages[k].sparse)
+            de.eng._mark("step_end")
+            torch.cuda.synchronize()
+            marks, de.eng._marks = de.eng._marks, None
+            if r < 2:
+                continue
+            for name, ev in marks[1:]:
+                if name not in acc:
+                    acc[name] = []
+                    order.append(name)
+                acc[name].append(marks[0][1].elapsed_time(ev) * 1e3)
+        phases = {"unit": "us after step_begin (event recorded when the named phase finished on its stream; "
+                          "'emb:' = embedding stream; eager launches, mean of %d steps)" % args.phases,
+                  "marks": [[n, round(float(np.mean(acc[n])), 1)] for n in order]}
     roof = roof_upd = cb = None
-    if rank == 0 and world == 1:
+    if world > 1 or rank == 0:
         peaks = {}
         try:
             with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as fh:
@@ -482,7 +514,7 @@ def ours(args, W):
         hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
         peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s"
         roof, roof_upd = measure_rooflines(de, stages, load_dev, pre, args, W, cost, hbm_peak, peak_src, train)
-        if not args.no_cpu:
+        if not args.no_cpu and world == 1:
             cb = cpu_arm(args, W, budget_s=args.cpu_budget)
     if rank == 0:
         clocks = sampler.stop(t0, t1)
@@ -508,7 +540,7 @@ def ours(args, W):
             "placement": {"split_tables": pl.split_tables(), "imbalance": pl.imbalance(),
                           "gather_bytes_per_rank_per_step": gbs,
                           "gather_bytes_max_over_min": max(gbs) / max(min(gbs), 1.0)},
-            "parity_check": check, "clocks": clocks,
+            "parity_check": check, "clocks": clocks, "phases": phases,
         }
         print(json.dumps(line), flush=True)
     if world > 1:
@@ -598,6 +630,7 @@ def main():
                     help="row-split tables: every rank pools a partial sum of its rows (partial), or the sample's owner "
                          "reads the rows from their owners over NVLink inside the gather (remote)")
     ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--phases", type=int, default=0, help="also record a per-phase timeline over this many eager steps")
     ap.add_argument("--no-check", action="store_true", help="skip the pre-run parity check against the live-reference golden")
     ap.add_argument("--cpu-budget", type=float, default=15.0)
     ap.add_argument("--no-cpu", action="store_true")

@@ -3,7 +3,11 @@ the B200 engine, so that `bench/dlrm_s_benchmark.sh` runs unmodified from this r
 
 Every flag of the reference is accepted with the same default.  Flags that select subsystems outside
 the hot path (datasets, QR/MD embeddings, quantisation, ONNX, mlperf logging, ...) exit with the
-reference's style of error.  The random-data generator draws from numpy's global RNG in EXACTLY the
+reference's style of error.  --test-freq / --inference-only run the reference's test pass (inference(),
+:759-900), --save-model / --load-model write and read the reference's checkpoint dictionary (:860-866,
+:1399-1456, :1703-1715; a checkpoint written by the reference loads here and vice versa), --enable-profiling
+and --debug-mode do what they do there.  --max-ind-range and --mlperf-grad-accum-iter only act on the
+dataset / mlperf-logging paths in the reference (rejected above), so they have no effect here either.  The random-data generator draws from numpy's global RNG in EXACTLY the
 reference's order (dlrm_data_pytorch.py:899-960 and :838-846; re-seeded at batch 0 of every epoch,
 :637-638), and parameters are initialised in the reference's order, so for the same
 `--numpy-rand-seed` the inputs and initial weights are bit-identical to the reference's and the printed
@@ -208,7 +212,8 @@ def run(argv=None):
     # every batch is drawn in the reference's order (datagen.py; identical batches for identical flags)
     from . import datagen
 
-    train_data, _, _, _ = datagen.make_random_data_and_loader(args, ln_emb, m_den)
+    train_data, _, test_data, _ = datagen.make_random_data_and_loader(args, ln_emb, m_den)
+    nbatches_test = len(test_data)
 
     def batch(j):
         return datagen.collate_wrapper_random_offset([train_data[j]])
@@ -230,20 +235,115 @@ def run(argv=None):
             sys.exit("ERROR: --optimizer=" + args.optimizer + " is not supported (sgd | rwsadagrad)")
         lr_scheduler = LRPolicy(optimizer, args.lr_num_warmup_steps, args.lr_decay_start_step,
                                 args.lr_num_decay_steps)
-    if args.load_model:
-        ld = torch.load(args.load_model, map_location=device)
-        dlrm.load_state_dict(ld["state_dict"] if "state_dict" in ld else ld)
+    if args.debug_mode:                                     # dlrm_s_pytorch.py:1222-1262, :1308-1311
+        print("model arch:")
+        print("mlp top arch " + str(ln_top.size - 1) + " layers, with input to output dimensions:")
+        print(ln_top)
+        print("# of interactions")
+        print(num_int)
+        print("mlp bot arch " + str(ln_bot.size - 1) + " layers, with input to output dimensions:")
+        print(ln_bot)
+        print("# of features (sparse and dense)")
+        print(num_fea)
+        print("dense feature size")
+        print(m_den)
+        print("sparse feature size")
+        print(m_spa)
+        print("# of embeddings (= # of sparse features) " + str(ln_emb.size) + ", with dimensions "
+              + str(m_spa) + "x:")
+        print(ln_emb)
+        print("initial parameters (weights and bias):")
+        for param in dlrm.parameters():
+            print(param.detach().cpu().numpy())
+
+    best_acc_test = 0
+    skip_upto_epoch = skip_upto_batch = 0
     total_time = total_loss = total_iter = total_samp = 0
-    print("time/loss/accuracy (if enabled):")
-    for k in range(args.nepochs):
-        for j in range(nbatches):
-            X, lS_o, lS_i, T = batch(j)
-            if world > 1 and X.size(0) % world != 0:      # dlrm_s_pytorch.py:1565-1570
-                print("Warning: Skiping the batch %d with size %d" % (j, X.size(0)))
+    if args.load_model:                                      # dlrm_s_pytorch.py:1399-1456
+        print("Loading saved model {}".format(args.load_model))
+        ld = torch.load(args.load_model, map_location=device, weights_only=False)
+        dlrm.load_state_dict(ld["state_dict"])
+        ld_j, ld_k = ld["iter"], ld["epoch"]
+        ld_nepochs, ld_nbatches, ld_nbatches_test = ld["nepochs"], ld["nbatches"], ld["nbatches_test"]
+        ld_train_loss, ld_total_loss, ld_acc_test = ld["train_loss"], ld["total_loss"], ld["test_acc"]
+        if not args.inference_only:
+            optimizer.load_state_dict(ld["opt_state_dict"])
+            best_acc_test = ld_acc_test
+            total_loss = ld_total_loss
+            skip_upto_epoch = ld_k
+            skip_upto_batch = ld_j
+            # dlrm_b200: the schedule resumes at the saved position (the reference's scheduler restarts at step 1)
+            for _ in range(ld_k * ld_nbatches + ld_j):
+                lr_scheduler.step()
+        else:
+            args.print_freq = ld_nbatches
+            args.test_freq = 0
+        print("Saved at: epoch = {:d}/{:d}, batch = {:d}/{:d}, ntbatch = {:d}".format(
+            ld_k, ld_nepochs, ld_j, ld_nbatches, ld_nbatches_test))
+        print("Training state: loss = {:.6f}".format(ld_train_loss))
+        print("Testing state: accuracy = {:3.3f} %".format(ld_acc_test * 100))
+
+    def inference(best_acc):
+        """One pass over the test set (inference(), dlrm_s_pytorch.py:759-900): accuracy of round(Z) against the
+        targets, every rank's slice gathered first."""
+        test_accu = test_samp = 0
+        for i in range(nbatches_test):
+            if nbatches > 0 and i >= nbatches:
+                break
+            X_t, lS_o_t, lS_i_t, T_t = datagen.collate_wrapper_random_offset([test_data[i]])
+            if world > 1 and X_t.size(0) % world != 0:
+                print("Warning: Skiping the batch %d with size %d" % (i, X_t.size(0)))
                 continue
-            torch.cuda.synchronize()
-            t1 = time.time()
-            with torch.set_grad_enabled(not args.inference_only):
+            with torch.no_grad():
+                Z_t = dlrm(X_t.to(device), lS_o_t, lS_i_t)
+            if world > 1:
+                import torch.distributed as tdist
+
+                parts = [torch.empty_like(Z_t) for _ in range(world)]
+                tdist.all_gather(parts, Z_t.contiguous())
+                Z_t = torch.cat(parts)
+            S_t, T_n = Z_t.detach().cpu().numpy(), T_t.numpy()
+            test_accu += np.sum((np.round(S_t, 0) == T_n).astype(np.uint8))
+            test_samp += T_n.shape[0]
+        acc = test_accu / test_samp
+        metrics = {"nepochs": args.nepochs, "nbatches": nbatches, "nbatches_test": nbatches_test,
+                   "state_dict": dlrm.state_dict(), "test_acc": acc}
+        is_best = acc > best_acc
+        if is_best:
+            best_acc = acc
+        print(" accuracy {:3.3f} %, best {:3.3f} %".format(acc * 100, best_acc * 100), flush=True)
+        return metrics, is_best, best_acc
+
+    def checkpoint(metrics, k, it, train_loss):
+        metrics.update(epoch=k, iter=it, train_loss=train_loss, total_loss=total_loss,
+                       opt_state_dict=optimizer.state_dict())
+        print("Saving model to {}".format(args.save_model))
+        if rank == 0:
+            torch.save(metrics, args.save_model)
+
+    import contextlib
+
+    prof_ctx = (torch.autograd.profiler.profile(True, use_cuda=True, record_shapes=True)
+                if args.enable_profiling else contextlib.nullcontext())
+    print("time/loss/accuracy (if enabled):")
+    saved = False
+    train_loss = 0.0
+    with prof_ctx as prof:
+        if args.inference_only:
+            print("Testing for inference only")
+            inference(best_acc_test)
+        for k in range(0 if not args.inference_only else args.nepochs, args.nepochs):
+            if k < skip_upto_epoch:
+                continue
+            for j in range(nbatches):
+                X, lS_o, lS_i, T = batch(j)       # drawn even when skipped: the generator's order is the reference's
+                if j < skip_upto_batch:
+                    continue
+                if world > 1 and X.size(0) % world != 0:      # dlrm_s_pytorch.py:1565-1570
+                    print("Warning: Skiping the batch %d with size %d" % (j, X.size(0)))
+                    continue
+                torch.cuda.synchronize()
+                t1 = time.time()
                 Z = dlrm(X.to(device), lS_o, lS_i)
                 if world > 1:                               # loss on this rank's batch slice (:1584-1586)
                     nloc = X.size(0) // world
@@ -254,34 +354,61 @@ def run(argv=None):
                     E = (ws * dlrm.loss_fn(Z, Td)).mean()
                 else:
                     E = dlrm.loss_fn(Z, Td)
-            L = E.detach().cpu().numpy()
-            if world > 1 and os.environ.get("DLRM_CLI_GLOBAL_LOSS") == "1":
-                # the reference prints rank 0's slice loss; the mean over the ranks is the single-process loss
-                import torch.distributed as tdist
+                L = E.detach().cpu().numpy()
+                if world > 1 and os.environ.get("DLRM_CLI_GLOBAL_LOSS") == "1":
+                    # the reference prints rank 0's slice loss; the mean over the ranks is the single-process loss
+                    import torch.distributed as tdist
 
-                Lg = E.detach().clone()
-                tdist.all_reduce(Lg, op=tdist.ReduceOp.AVG)
-                L = Lg.cpu().numpy()
-            if not args.inference_only:
+                    Lg = E.detach().clone()
+                    tdist.all_reduce(Lg, op=tdist.ReduceOp.AVG)
+                    L = Lg.cpu().numpy()
                 optimizer.zero_grad()
                 E.backward()
                 optimizer.step()
                 lr_scheduler.step()
-            torch.cuda.synchronize()
-            total_time += time.time() - t1
-            mbs = T.shape[0]
-            total_loss += L * mbs
-            total_iter += 1
-            total_samp += mbs
-            if ((j + 1) % args.print_freq == 0) or (j + 1 == nbatches):
-                gT = 1000.0 * total_time / total_iter if args.print_time else -1
-                wall = " ({})".format(time.strftime("%H:%M")) if args.print_wall_time else ""
-                print("Finished {} it {}/{} of epoch {}, {:.2f} ms/it,".format(
-                    "inference" if args.inference_only else "training", j + 1, nbatches, k, gT)
-                    + " loss {:.6f}".format(total_loss / total_samp) + wall, flush=True)
-                total_time = total_loss = total_iter = total_samp = 0
-    if args.save_model:
-        torch.save({"state_dict": dlrm.state_dict(), "epoch": args.nepochs, "nbatches": nbatches}, args.save_model)
+                torch.cuda.synchronize()
+                total_time += time.time() - t1
+                mbs = T.shape[0]
+                total_loss += L * mbs
+                total_iter += 1
+                total_samp += mbs
+                should_print = ((j + 1) % args.print_freq == 0) or (j + 1 == nbatches)
+                should_test = (args.test_freq > 0 and args.data_generation in ("dataset", "random")
+                               and (((j + 1) % args.test_freq == 0) or (j + 1 == nbatches)))
+                if should_print or should_test:
+                    gT = 1000.0 * total_time / total_iter if args.print_time else -1
+                    train_loss = total_loss / total_samp
+                    wall = " ({})".format(time.strftime("%H:%M")) if args.print_wall_time else ""
+                    print("Finished {} it {}/{} of epoch {}, {:.2f} ms/it,".format("training", j + 1, nbatches, k, gT)
+                          + " loss {:.6f}".format(train_loss) + wall, flush=True)
+                    total_time = total_loss = total_iter = total_samp = 0
+                if should_test:
+                    print("Testing at - {}/{} of epoch {},".format(j + 1, nbatches, k))
+                    # (the reference does not carry the best accuracy back to this loop, :1691-1700: every test
+                    #  pass that beats the LOADED accuracy saves)
+                    metrics, is_best, _ = inference(best_acc_test)
+                    if is_best and args.save_model:
+                        checkpoint(metrics, k, j + 1, train_loss)
+                        saved = True
+    if args.save_model and not saved and not args.inference_only:
+        # dlrm_b200 addition: the reference only saves after a test pass that improved the accuracy
+        # (:1703-1715); without --test-freq it would write nothing, so the final state is saved here
+        checkpoint({"nepochs": args.nepochs, "nbatches": nbatches, "nbatches_test": nbatches_test,
+                    "state_dict": dlrm.state_dict(), "test_acc": best_acc_test}, args.nepochs, 0, train_loss)
+    if args.enable_profiling:                               # dlrm_s_pytorch.py:1795-1805
+        import datetime
+
+        stamp = str(datetime.datetime.now()).replace(" ", "_")
+        if rank == 0:
+            with open("dlrm_s_pytorch" + stamp + "_shape.prof", "w") as f:
+                f.write(prof.key_averages(group_by_input_shape=True).table(sort_by="self_cpu_time_total"))
+            with open("dlrm_s_pytorch" + stamp + "_total.prof", "w") as f:
+                f.write(prof.key_averages().table(sort_by="self_cpu_time_total"))
+            prof.export_chrome_trace("dlrm_s_pytorch" + stamp + ".json")
+    if not args.inference_only and args.debug_mode:
+        print("updated parameters (weights and bias):")
+        for param in dlrm.parameters():
+            print(param.detach().cpu().numpy())
     return dlrm
 
 

@@ -343,12 +343,17 @@ class DistEngine:
         # pooled rows of this batch land in it.  Issued ALWAYS (training too): an evaluation forward between
         # two training steps must not race with a faster rank's next gather (round-1 advisor finding).
         self._barrier()
+        e._mark("emb:barrier_pre_gather")
         e.emb_forward(sp, link=link)          # routed: stores go to the owners' buffers over NVLink
+        e._mark("emb:gather")
         self._barrier()                       # every rank's pooled rows / partial sums have landed everywhere
+        e._mark("emb:barrier_post_gather")
         e.reduce_partials(self.B)
+        e._mark("emb:reduce_partials")
 
     def _update_p2p(self, sp, optimizer, clr):
         self._barrier()       # every rank's interact_bwd stores have landed in my receive buffer
+        self.eng._mark("emb:barrier_pre_update")
         self.eng.emb_update(sp, optimizer=optimizer, lr=clr)
 
     # -- forward: pool local tables for the global batch, exchange, land in T

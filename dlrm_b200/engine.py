@@ -175,6 +175,7 @@ class Engine:
         if loss_ws is not None:
             self.loss_ws = torch.as_tensor(loss_ws, dtype=torch.float32, device=dev)
         self.opt_step = 0
+        self._marks = None      # phase timeline (bench.py --phases): list of (name, stream tag, CUDA event)
         # hooks replaced by dlrm_b200.dist for table-wise sharded runs
         self.gather_fn = None       # (sp, link) -> fills Tbuf[:, 1:, :] for the LOCAL batch
         self.update_fn = None       # (sp, optimizer, clr) -> embedding update from dT[:, 1:, :]
@@ -882,10 +883,13 @@ class Engine:
         if self.tc:
             if self.dense_sync_fn is not None:
                 self._dense_update_pack(-2, 0.0)      # fold the split-K slabs into slab 0
+                self._mark("dense_fold")
                 self.dense_sync_fn()                  # cross-rank mean of the dense gradients
+                self._mark("dense_allreduce")
                 self._dense_update_pack(_OPT[optimizer], clr, eps, single_slab=True)
             else:
                 self._dense_update_pack(_OPT[optimizer], clr, eps)
+            self._mark("dense_update")
         else:
             if self.dense_sync_fn is not None:
                 self.dense_sync_fn()
@@ -917,6 +921,13 @@ class Engine:
                                                        self.D, int(self.itself),
                                                        bot_last_act, g0h, g0l, ldg0, stream),
                    "interact_bwd_p2p")
+
+    def _mark(self, name: str):
+        """Phase timeline: a timing event on the current stream (only while `_marks` is a list; never in a graph)."""
+        if self._marks is not None:
+            ev = torch.cuda.Event(enable_timing=True)
+            ev.record()
+            self._marks.append((name, ev))
 
     def _fork(self, side):
         """side stream starts after everything enqueued so far on the current stream."""
@@ -1129,6 +1140,7 @@ class Engine:
             raise RuntimeError("gemm='tc' needs op='dot' and MLP layers of width >= 16; use gemm='simt'")
         FD = self.F * self.D
         ms = self.multi_stream and (self.T > 0 or self.gather_fn is not None)
+        self._mark("begin")
         if ms:   # gather (+ link) beside the bottom MLP
             self._fork(self.s_emb)
             with torch.cuda.stream(self.s_emb):
@@ -1136,11 +1148,15 @@ class Engine:
                     self.gather_fn(sp, link)
                 else:
                     self.emb_forward(sp, link=link)
+                    self._mark("emb:gather")
                     self.reduce_partials(B)
+                    self._mark("emb:reduce_partials")
         self._split(X, X.stride(0), B, self.ln_bot[0], self.tc_in["bot"][0])
         self._tc_mlp_forward("bot", B)
+        self._mark("bot_fwd")
         if ms:
             self._join(self.s_emb)
+            self._mark("join_gather")
         elif self.gather_fn is not None:
             self.gather_fn(sp, link)
         elif self.T:
@@ -1163,7 +1179,9 @@ class Engine:
                                                        self.F, self.D, int(self.itself), _stream()), "interact_fwd")
             self.n_launch += 1
             self._split(self.Rbuf, self.ldr, B, self.num_int, self.tc_in["top"][0])
+        self._mark("interact_fwd")
         self._tc_mlp_forward("top", B, skip_head)
+        self._mark("top_fwd")
         p = self.top_act[-1][:B]
         if 0.0 < self.loss_threshold < 1.0:
             return torch.clamp(p, self.loss_threshold, 1.0 - self.loss_threshold)
@@ -1253,7 +1271,9 @@ class Engine:
             self.n_launch += 3
         if not head_to_tc:
             self._split(self.top_gz[ntc - 1], top_ld[ntc - 1], B, self.ln_top[ntc], self.tc_gz["top"][ntc - 1])
+        self._mark("head+loss")
         self._tc_mlp_backward("top", B)
+        self._mark("top_bwd_dgrad")
         bot_last_act = self._act("bot", len(self.ln_bot) - 2)
         g0h, g0l, ldg0 = self.tc_gz["bot"][-1]
         if self.dT_route is not None:
@@ -1265,6 +1285,7 @@ class Engine:
                                                           g0l.data_ptr(), ldg0, s),
                        "interact_bwd_ex")
         self.n_launch += 1
+        self._mark("interact_bwd")
         has_emb = self.T > 0 or self.update_fn is not None
         if update is not None and has_emb:
             # fused coalesce + sparse optimizer beside the bottom-MLP backward
@@ -1275,14 +1296,19 @@ class Engine:
                 self._fork(self.s_emb)
                 with torch.cuda.stream(self.s_emb):
                     upd()
+                    self._mark("emb:update")
             else:
                 upd()
+                self._mark("emb:update")
         self._tc_mlp_backward("bot", B)
+        self._mark("bot_bwd_dgrad")
         if self.multi_stream:
             if not self.use_chain:
                 self._join(self.s_wg)
+                self._mark("join_wgrads")
             if update is not None and has_emb and getattr(self, "_join_update", True):
                 self._join(self.s_emb)
+                self._mark("join_update")
 
 
 class GraphedTrainSteps:

@@ -58,6 +58,51 @@ class _Fused(torch.optim.Optimizer):
         return loss
 
 
+    # ------------------------------------------------------------------ checkpoint (opt_state_dict)
+    def _state_view(self, p):
+        """('momentum', [rows] view) for an embedding table, ('sum', same-shape view) for an MLP parameter: the
+        engine memory that holds the reference's per-parameter state (optim/rwsadagrad.py:86-100)."""
+        eng = self.net._engine
+        lo = eng.dense.data_ptr()
+        if lo <= p.data_ptr() < lo + eng.dense.numel() * 4:
+            off = (p.data_ptr() - lo) // 4
+            return "sum", eng.dense_state[off:off + p.numel()].view(p.shape)
+        for k in range(len(eng.row_base) - 1):
+            if eng.table(k).data_ptr() == p.data_ptr():
+                return "momentum", eng.momentum[int(eng.row_base[k]):int(eng.row_base[k + 1])]
+        raise RuntimeError("parameter is not backed by the engine's memory")
+
+    def state_dict(self):
+        """torch.optim's layout with the reference optimizer's keys: RWSAdagrad keeps 'step' and, per parameter,
+        'momentum' ([rows], embedding tables) or 'sum' (dense parameters); SGD has no state."""
+        eng = self.net._engine
+        params = [p for g in self.param_groups for p in g["params"]]
+        state = {}
+        if self._name == "rwsadagrad":
+            for i, p in enumerate(params):
+                kind, view = self._state_view(p)
+                state[i] = {"step": int(eng.opt_step), kind: view.detach().clone()}
+        group = {k: v for k, v in self.param_groups[0].items() if k != "params"}
+        group["params"] = list(range(len(params)))
+        return {"state": state, "param_groups": [group], "opt_step": int(eng.opt_step)}
+
+    @torch.no_grad()
+    def load_state_dict(self, sd):
+        eng = self.net._engine
+        params = [p for g in self.param_groups for p in g["params"]]
+        for k, v in sd["param_groups"][0].items():
+            if k != "params":
+                self.param_groups[0][k] = v
+        step = int(sd.get("opt_step", 0))
+        for i, st in sd.get("state", {}).items():
+            kind, view = self._state_view(params[int(i)])
+            if kind not in st:
+                raise KeyError("optimizer state of parameter %d has no '%s'" % (int(i), kind))
+            view.copy_(torch.as_tensor(st[kind]).to(view.device))
+            step = max(step, int(st.get("step", 0)))
+        eng.opt_step = step
+
+
 class SGD(_Fused):
     _name = "sgd"
 

@@ -61,7 +61,9 @@ def test_gaussian_and_trace_driven_sources_and_inference_only(cli_on_cpu, capsys
     cli, seen = cli_on_cpu
     cli.run(BASE + ["--num-batches=2", "--rand-data-dist=gaussian", "--rand-data-max=60", "--rand-data-sigma=9",
                     "--inference-only"])
-    assert "Finished inference it 2/2 of epoch 0" in capsys.readouterr().out
+    out = capsys.readouterr().out       # the reference's inference-only run is ONE test pass (dlrm_s_pytorch.py:1781-1792)
+    assert "Testing for inference only" in out and " accuracy " in out
+    assert len(seen) == 2
     assert all(int(i.max()) <= 60 for _, _, ids in seen for i in ids)
     del seen[:]
     monkeypatch.chdir(GOLD)

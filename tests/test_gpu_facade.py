@@ -183,3 +183,84 @@ def test_gradient_accumulation_fails_loudly():
     net.loss_fn(net(X, lS_o, lS_i), T.to(DEV)).backward()
     with pytest.raises(RuntimeError, match="accumulation"):
         net.loss_fn(net(X, lS_o, lS_i), T.to(DEV)).backward()
+
+
+_CLI_BASE = ["--arch-sparse-feature-size=16", "--arch-embedding-size=1000-1000-1000", "--arch-mlp-bot=13-512-256-64-16",
+             "--arch-mlp-top=512-256-1", "--mini-batch-size=128", "--data-generation=random", "--num-batches=6",
+             "--print-freq=1", "--learning-rate=0.1", "--numpy-rand-seed=727", "--use-gpu"]
+
+
+def test_cli_test_pass_and_checkpoint_follow_the_reference(tmp_path):
+    """--test-freq / --save-model: the printed lines (loss curve, 'Testing at', accuracy, 'Saving model') equal the
+    reference CLI's run recorded in tests/golden/cli_cfg0_C.txt (the test set re-seeds numpy, so the training batches
+    after a test pass differ from a run without one -- the same happens here), and the checkpoint carries the
+    reference's key set (dlrm_s_pytorch.py:860-866, :1703-1715) with the reference's state_dict keys."""
+    flags = open(os.path.join(ROOT, "tests", "golden", "cli_cfg0_C.flags")).read().split()
+    want = open(os.path.join(ROOT, "tests", "golden", "cli_cfg0_C.txt")).read().splitlines()
+    ck = str(tmp_path / "ours.pt")
+    cmd = [sys.executable, os.path.join(ROOT, "dlrm_s_pytorch.py")] + _CLI_BASE + flags + ["--save-model=" + ck]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=ROOT)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    got = [ln for ln in r.stdout.splitlines() if re.match(r"time/loss|Finished| accuracy|Testing at|Saving model", ln)]
+    assert len(got) == len(want), r.stdout
+    for a, b in zip(got, want):
+        if a.startswith("Finished"):
+            la, lb = float(a.rsplit(" ", 1)[1]), float(b.rsplit(" ", 1)[1])
+            assert a.rsplit(" ", 1)[0] == b.rsplit(" ", 1)[0] and abs(la - lb) < 2e-5, (a, b)
+        elif a.startswith("Saving model"):
+            assert b.startswith("Saving model")
+        else:
+            assert a == b
+    ref = torch.load(os.path.join(ROOT, "tests", "golden", "cli_cfg0_C_ref.pt"), map_location="cpu", weights_only=False)
+    ours = torch.load(ck, map_location="cpu", weights_only=False)
+    assert set(ours.keys()) == set(ref.keys())
+    assert list(ours["state_dict"].keys()) == list(ref["state_dict"].keys())
+    for k in ("epoch", "iter", "nepochs", "nbatches", "nbatches_test"):
+        assert ours[k] == ref[k], k
+    assert abs(float(ours["test_acc"]) - float(ref["test_acc"])) < 1e-9
+    assert abs(float(ours["train_loss"]) - float(ref["train_loss"])) < 2e-5
+    for k, v in ref["state_dict"].items():          # same weights after the same 6 SGD steps
+        np.testing.assert_allclose(ours["state_dict"][k].numpy(), v.numpy(), rtol=0, atol=2e-5)
+
+
+def test_cli_loads_a_reference_checkpoint_for_inference():
+    """A checkpoint WRITTEN BY THE REFERENCE (tests/golden/cli_cfg0_C_ref.pt) loads through --load-model
+    --inference-only; the test pass gives the accuracy the reference recorded in it."""
+    flags = ["--round-targets=True", "--loss-function=bce"]
+    ck = os.path.join(ROOT, "tests", "golden", "cli_cfg0_C_ref.pt")
+    cmd = [sys.executable, os.path.join(ROOT, "dlrm_s_pytorch.py")] + _CLI_BASE + flags + \
+        ["--load-model=" + ck, "--inference-only"]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=ROOT)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert "Saved at: epoch = 0/1, batch = 6/6, ntbatch = 6" in r.stdout
+    assert "Testing for inference only" in r.stdout
+    assert " accuracy 51.693 %, best 51.693 %" in r.stdout
+
+
+def test_checkpoint_resume_restores_optimizer_state(tmp_path):
+    """--optimizer=rwsadagrad: opt_state_dict round-trips the row-wise accumulators ('momentum'), the dense
+    accumulators ('sum') and the step count, with the reference optimizer's per-parameter keys
+    (optim/rwsadagrad.py:86-100); resuming skips the batches already trained (:1430-1436)."""
+    from dlrm_b200 import cli
+
+    ck = str(tmp_path / "ada.pt")
+    args = [a for a in _CLI_BASE if not a.startswith("--num-batches")] + \
+        ["--round-targets=True", "--loss-function=bce", "--optimizer=rwsadagrad"]
+    net = cli.run(args + ["--num-batches=4", "--test-freq=4", "--save-model=" + ck])
+    sd = torch.load(ck, map_location="cpu", weights_only=False)
+    assert sd["iter"] == 4 and sd["epoch"] == 0
+    st = sd["opt_state_dict"]["state"]
+    assert len(st) == 3 + 2 * 4 + 2 * 3
+    assert all(set(st[i]) == {"step", "momentum"} and st[i]["momentum"].shape == (1000,) for i in range(3))
+    assert all(set(st[i]) == {"step", "sum"} for i in range(3, len(st)))
+    assert all(st[i]["step"] == 4 for i in st)
+    assert float(st[0]["momentum"].abs().sum()) > 0 and float(st[3]["sum"].abs().sum()) > 0
+    mom = net._engine.momentum.detach().cpu().clone()
+    dsum = net._engine.dense_state.detach().cpu().clone()
+    del net
+    net2 = cli.run(args + ["--num-batches=4", "--load-model=" + ck])        # every batch skipped: state == checkpoint
+    assert net2._engine.opt_step == 4
+    np.testing.assert_array_equal(net2._engine.momentum.cpu().numpy(), mom.numpy())
+    np.testing.assert_array_equal(net2._engine.dense_state.cpu().numpy(), dsum.numpy())
+    for k, v in sd["state_dict"].items():
+        np.testing.assert_array_equal(net2.state_dict()[k].cpu().numpy(), v.numpy())
