@@ -393,8 +393,10 @@ class Engine:
         g.manual_seed(seed)
         with torch.no_grad():
             for k, n in enumerate(self.ln_emb):
-                a = float(np.sqrt(1.0 / n))
-                self.table(k).uniform_(-a, a, generator=g)
+                a = float(np.sqrt(1.0 / int(self.shards[k]["rows"])))      # the bound of the WHOLE table (:280-284)
+                tk = self.table(k)
+                for r0 in range(0, tk.shape[0], 1 << 24):                    # chunks: any temporary stays < 8.6 GB
+                    tk[r0:r0 + (1 << 24)].uniform_(-a, a, generator=g)
             for name, ln in (("bot", self.ln_bot), ("top", self.ln_top)):
                 for i in range(len(ln) - 1):
                     n, m = ln[i], ln[i + 1]
