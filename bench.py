@@ -504,7 +504,10 @@ def ours(args, W):
                           "'emb:' = embedding stream; eager launches, mean of %d steps)" % args.phases,
                   "marks": [[n, round(float(np.mean(acc[n])), 1)] for n in order]}
     roof = roof_upd = cb = None
-    if world > 1 or rank == 0:
+    # Rank 0 ALONE times its gather / update kernels (at N > 1 the other ranks wait in the final barrier): the loop
+    # refreshes the indices between a link and its update without the step's barriers, which is only safe while no
+    # peer is running its own link / update on indices this rank's exchange overwrites.
+    if rank == 0:
         peaks = {}
         try:
             with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as fh:
@@ -578,9 +581,13 @@ def measure_rooflines(de, stages, load_dev, pre, args, W, cost, hbm_peak, peak_s
         evs.append((e0, e1))
     torch.cuda.synchronize()
     tg = float(np.median([a.elapsed_time(b) for a, b in evs])) * 1e-3
-    nnz = float(sum(cost)) * B
+    # this rank's share: the rows of its shards the global batch touches, all index words of its shards (a shard
+    # scans every occurrence of its table), one pooled row per (sample, shard)
+    nnz = de.gather_bytes_per_step(cost) / (D * 4)
+    scanned = float(sum(cost[s.table] for s in de.mine)) * B
+    T = len(de.mine)
     idx_b = 4 if W["hot"] is not None else 8
-    by = nnz * D * 4 + nnz * idx_b + T * B * idx_b + T * B * D * 4      # rows + indices + offsets + pooled out
+    by = nnz * D * 4 + scanned * idx_b + T * B * idx_b + T * B * D * 4  # rows + indices + offsets + pooled out
     ach = by / tg / 1e9
     roof = {"kernel": "emb_fwd_vec_kernel (multi-table EmbeddingBag gather, forward)", "bound": "hbm", "achieved": ach,
             "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak, "traffic": None,
@@ -606,7 +613,7 @@ def measure_rooflines(de, stages, load_dev, pre, args, W, cost, hbm_peak, peak_s
         torch.cuda.synchronize()
         t_gl = float(np.median([a.elapsed_time(b) for a, b, _ in evs])) * 1e-3
         tu = float(np.median([b.elapsed_time(c) for _, b, c in evs])) * 1e-3
-        by_u = nnz * (D * 4 * 2 + 8) + T * B * D * 4 + nnz * idx_b      # SURVEY 8(d) bytes_bwd (unique rows ~ nnz)
+        by_u = nnz * (D * 4 * 2 + 8) + T * B * D * 4 + scanned * idx_b  # SURVEY 8(d) bytes_bwd (unique rows ~ nnz)
         achu = by_u / tu / 1e9
         roof_upd = {"kernel": "emb_update_kernel (+ emb_small_*: coalesce + row-wise Adagrad, in place)", "bound": "hbm",
                     "achieved": achu, "peak": hbm_peak, "unit": "GB/s", "frac": achu / hbm_peak, "traffic": None,

@@ -22,6 +22,22 @@
 
 namespace dlrm {
 
+// A per-row occurrence list is acyclic by construction (every gather+link is followed by the update that resets
+// the heads it used).  If a caller breaks that contract (indices rewritten between link and update, a skipped
+// update), stale heads can close a cycle and the walk would spin for ever: past 2^17 members the walk checks the
+// clock and traps after 20 s instead of hanging the GPU.
+__device__ __forceinline__ void list_walk_guard(unsigned& chunks, unsigned long long& t0) {
+  if (++chunks >= 4096u && (chunks & 4095u) == 0u) {
+    unsigned long long now;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+    if (t0 == 0) t0 = now;
+    else if (now - t0 > 20000000000ULL) {
+      if ((threadIdx.x & 31) == 0) printf("dlrm_b200: emb update: a row's occurrence list does not end (stale list heads?)\n");
+      __trap();
+    }
+  }
+}
+
 struct EmbBwdTable {
   float* w;
   float* mom;
@@ -302,6 +318,8 @@ __global__ void __launch_bounds__(256, NV == 1 ? 3 : 1) emb_update_kernel(const 
           int cnt = 1;
           int mpos = (lane == 0) ? (int)(base + src) : 0x7fffffff;
           int mbag = self_bag;
+          unsigned walk_chunks = 0;
+          unsigned long long walk_t0 = 0;
           while (true) {
             if (nxt != 0 && cnt < 32) {
               const int2 e = P.link[nxt - 1];
@@ -325,6 +343,7 @@ __global__ void __launch_bounds__(256, NV == 1 ? 3 : 1) emb_update_kernel(const 
               }
             }
             if (nxt == 0) break;
+            list_walk_guard(walk_chunks, walk_t0);
             cnt = 0;
             mpos = 0x7fffffff;
           }
@@ -396,6 +415,8 @@ __device__ __noinline__ float4 upd_sum_duplicates(const EmbBwdParams& P, int nxt
   int cnt = 1;
   int mpos = (lane == 0) ? self_pos : 0x7fffffff;
   int mbag = self_bag;
+  unsigned walk_chunks = 0;
+  unsigned long long walk_t0 = 0;
   while (true) {
     if (nxt != 0 && cnt < 32) {
       const int2 e = P.link[nxt - 1];
@@ -415,6 +436,7 @@ __device__ __noinline__ float4 upd_sum_duplicates(const EmbBwdParams& P, int nxt
       }
     }
     if (nxt == 0) break;
+    list_walk_guard(walk_chunks, walk_t0);
     cnt = 0;
     mpos = 0x7fffffff;
   }

@@ -21,6 +21,7 @@ HBM layout (fp32 unless noted)
 """
 from __future__ import annotations
 
+import contextlib
 import ctypes as C
 import os
 from dataclasses import dataclass
@@ -142,7 +143,10 @@ class Engine:
         if interleave_momentum is None:
             interleave_momentum = (self.D % 4 == 0) and os.environ.get("DLRM_ROW_META", "1") != "0"
         self.interleave = bool(interleave_momentum)
-        self.ldw = self.D + 4 if self.interleave else self.D
+        # DLRM_ROW_PAD: floats appended to a row (>= 2: accumulator + list head).  4 keeps rows 16-B aligned (+3 % memory);
+        # 16 keeps 512-B rows 64-B aligned (every row the same 8 DRAM atoms + 1 for the two words, +12.5 % memory).
+        self.row_pad = max(4, (int(os.environ.get("DLRM_ROW_PAD", "4")) + 3) // 4 * 4)
+        self.ldw = self.D + self.row_pad if self.interleave else self.D
         self.tables = torch.zeros((self.total_rows, self.ldw), dtype=torch.float32, device=dev)
         self._head_sep = None if self.interleave else torch.zeros(self.total_rows, dtype=torch.int32, device=dev)
         self._momentum_sep: Optional[torch.Tensor] = None
@@ -204,6 +208,7 @@ class Engine:
         self.tc_smem_kb = (0, 0)    # (forward, backward) operand-ring budget of the tcgen05 GEMM plans, KB; 0 = 200
         self.s_emb = torch.cuda.Stream(device=self.device)
         self.s_wg = torch.cuda.Stream(device=self.device)
+        self.s_small = torch.cuda.Stream(device=self.device)
         self._gather_events = None   # optional (start, end) CUDA events recorded around the gather
         self._alloc_activations(int(max_batch))
 
@@ -666,6 +671,25 @@ class Engine:
         base = None if peer is not None else (self.dT.data_ptr() if routed else dY.data_ptr())
         big = [k for k in range(self.T) if not self.is_small(k)]
         small = [k for k in range(self.T) if self.is_small(k)]
+        # The tiny-table kernels (few, long-running CTAs) go FIRST, on their own stream: they take their SM slots and the
+        # grid-stride list-path update fills the rest of the machine beside them (different tables, no ordering needed).
+        side = bool(small) and bool(big) and self.multi_stream and os.environ.get("DLRM_SMALL_SIDE", "1") != "0"
+        if side:
+            self._fork(self.s_small)
+        with (torch.cuda.stream(self.s_small) if side else contextlib.nullcontext()):
+            for c0 in range(0, len(small), 32):
+                ks = small[c0:c0 + 32]
+                desc, _ = self._bwd_desc_chunk(sp, ks, dy_off)
+                rows = sum(self.ln_emb[k] for k in ks)
+                need = int(self.lib.dlrm_b200_emb_bwd_small_scratch_bytes(rows, self.D, sp.batch))
+                if getattr(self, "small_scratch", None) is None or self.small_scratch.numel() * 4 < need:
+                    self.small_scratch = torch.zeros(max(need // 4, 1), dtype=torch.float32, device=self.device)
+                _lib.check(self.lib.dlrm_b200_emb_bwd_small_update(
+                    desc, len(ks), self.D, sp.batch, sp.idx_bytes, int(sp.include_last), base,
+                    peer[0] if peer is not None else None, peer[1] if peer is not None else 0,
+                    peer[2] if peer is not None else 0, ss, _OPT[optimizer], lr, eps, self.small_scratch.data_ptr(),
+                    self.small_scratch.numel() * 4, _stream()), "emb_bwd_small_update")
+                self.n_launch += 2
         for c0 in range(0, len(big), _lib.MAX_TABLES):
             ks = big[c0:c0 + _lib.MAX_TABLES]
             desc, _ = self._bwd_desc_chunk(sp, ks, dy_off)
@@ -680,19 +704,8 @@ class Engine:
                                                              int(sp.include_last), self.link.data_ptr(), base, ss, 0,
                                                              _OPT[optimizer], lr, eps, dd, _stream()), "emb_bwd_update")
             self.n_launch += 1
-        for c0 in range(0, len(small), 32):
-            ks = small[c0:c0 + 32]
-            desc, _ = self._bwd_desc_chunk(sp, ks, dy_off)
-            rows = sum(self.ln_emb[k] for k in ks)
-            need = int(self.lib.dlrm_b200_emb_bwd_small_scratch_bytes(rows, self.D, sp.batch))
-            if getattr(self, "small_scratch", None) is None or self.small_scratch.numel() * 4 < need:
-                self.small_scratch = torch.zeros(max(need // 4, 1), dtype=torch.float32, device=self.device)
-            _lib.check(self.lib.dlrm_b200_emb_bwd_small_update(
-                desc, len(ks), self.D, sp.batch, sp.idx_bytes, int(sp.include_last), base,
-                peer[0] if peer is not None else None, peer[1] if peer is not None else 0,
-                peer[2] if peer is not None else 0, ss, _OPT[optimizer], lr, eps, self.small_scratch.data_ptr(),
-                self.small_scratch.numel() * 4, _stream()), "emb_bwd_small_update")
-            self.n_launch += 2
+        if side:
+            self._join(self.s_small)
 
     def mlp_backward(self, which: str, x_in: torch.Tensor, ldx: int, in_act: int, B: int,
                      acts: List[torch.Tensor], act_ld: List[int], gz: List[torch.Tensor],

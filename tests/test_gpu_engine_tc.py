@@ -97,11 +97,27 @@ def test_tc_train_steps_vs_reference(name, opt):
     for s in range(g.nsteps):
         X, sp, T = _dev_batch(g, s)
         losses.append(float(e.train_step(X, sp, T, lr, optimizer=opt).item()))
+        if s == 0:  # after ONE step the rows / accumulators are a well-conditioned function of the batch-0 gradients
+            for k in range(g.T):
+                if g.has(f"{opt}1_emb{k}_rows"):
+                    rows = g[f"{opt}1_emb{k}_rows"]
+                    np.testing.assert_allclose(e.table(k)[torch.from_numpy(rows).to(DEV)].cpu().numpy(),
+                                               g[f"{opt}1_emb{k}_vals"], rtol=1e-3, atol=5e-6)
+                assert abs(float(e.table(k).double().sum().item()) - float(g[f"{opt}1_emb{k}_sum"])) < 2e-3
+                if opt == "rwsadagrad":
+                    m = e.momentum[int(e.row_base[k]):int(e.row_base[k + 1])].cpu().numpy()
+                    np.testing.assert_allclose(m, g[f"{opt}1_mom{k}"], rtol=2e-3, atol=1e-10)
+    assert int(e.head.abs().sum().item()) == 0, "row-list heads not reset"
     tight = opt == "sgd"
     np.testing.assert_allclose(losses, g[f"{opt}_losses"], rtol=0, atol=2e-5 if tight else 3e-4)
     X, sp, T = _dev_batch(g, g.nsteps)
     pa = e.forward(X, sp).cpu().numpy()
     _robust_close(pa, g[f"{opt}_p_after"], 3e-5 if tight else 5e-4, 2e-4 if tight else 5e-3, "p_after")
+    for k in range(g.T):        # rows after all steps (Adagrad: robust, the normalised update amplifies rounding)
+        if g.has(f"{opt}_emb{k}_rows"):
+            rows = torch.from_numpy(g[f"{opt}_emb{k}_rows"]).to(DEV)
+            _robust_close(e.table(k)[rows].cpu().numpy(), g[f"{opt}_emb{k}_vals"], 2e-6 if tight else 2e-5,
+                          2e-5 if tight else 2.5 * lr, f"emb{k}")
     for nm in ("bot", "top"):
         for i in range(len(e.W[nm])):
             _robust_close(e.b[nm][i].cpu().numpy(), g[f"{opt}_{nm}b{i}"], 2e-6 if tight else 2e-5,
