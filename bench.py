@@ -471,38 +471,6 @@ def ours(args, W):
         gbs = [gb]
     gbs = [float(g.item()) for g in gbs]
 
-    # ---- optional phase timeline (eager launches, timing events on every stream): where the step's time goes
-    phases = None
-    if args.phases > 0:
-        acc = {}
-        order = []
-        for r in range(args.phases + 2):
-            k = r % nsets
-            load_dev(k, r)
-            sync_all()
-            de.eng._marks = []
-            de.eng._mark("step_begin")
-            p = pre(k)
-            if p is not None:
-                p()
-                de.eng._mark("index_exchange")
-            if train:
-                de.eng.train_step(stages[k].X, stages[k].sparse, stages[k].target, lr, "rwsadagrad")
-            else:
-                de.eng.forward(stages[k].X, stages[k].sparse)
-            de.eng._mark("step_end")
-            torch.cuda.synchronize()
-            marks, de.eng._marks = de.eng._marks, None
-            if r < 2:
-                continue
-            for name, ev in marks[1:]:
-                if name not in acc:
-                    acc[name] = []
-                    order.append(name)
-                acc[name].append(marks[0][1].elapsed_time(ev) * 1e3)
-        phases = {"unit": "us after step_begin (event recorded when the named phase finished on its stream; "
-                          "'emb:' = embedding stream; eager launches, mean of %d steps)" % args.phases,
-                  "marks": [[n, round(float(np.mean(acc[n])), 1)] for n in order]}
     roof = roof_upd = cb = None
     # Rank 0 ALONE times its gather / update kernels (at N > 1 the other ranks wait in the final barrier): the loop
     # refreshes the indices between a link and its update without the step's barriers, which is only safe while no
@@ -543,9 +511,47 @@ def ours(args, W):
             "placement": {"split_tables": pl.split_tables(), "imbalance": pl.imbalance(),
                           "gather_bytes_per_rank_per_step": gbs,
                           "gather_bytes_max_over_min": max(gbs) / max(min(gbs), 1.0)},
-            "parity_check": check, "clocks": clocks, "phases": phases,
+            "parity_check": check, "clocks": clocks,
         }
         print(json.dumps(line), flush=True)
+    # ---- optional phase timeline (eager launches, timing events on every stream): where the step's time goes
+    if args.phases > 0:
+        acc = {}
+        order = []
+        for r in range(args.phases + 2):
+            k = r % nsets
+            load_dev(k, r)
+            sync_all()
+            de.eng._marks = []
+            de.eng._mark("step_begin")
+            p = pre(k)
+            if p is not None:
+                p()
+                de.eng._mark("index_exchange")
+            if train:
+                de.eng.train_step(stages[k].X, stages[k].sparse, stages[k].target, lr, "rwsadagrad")
+            else:
+                de.eng.forward(stages[k].X, stages[k].sparse)
+            de.eng._mark("step_end")
+            torch.cuda.synchronize()
+            marks, de.eng._marks = de.eng._marks, None
+            if r < 2:
+                continue
+            for name, ev in marks[1:]:
+                if name not in acc:
+                    acc[name] = []
+                    order.append(name)
+                acc[name].append(marks[0][1].elapsed_time(ev) * 1e3)
+        phases = {"n_gpus": world, "workload": args.workload, "unit": "us after step_begin (event recorded when the named phase finished on its stream; "
+                          "'emb:' = embedding stream; eager launches, mean of %d steps)" % args.phases,
+                  "marks": [[n, round(float(np.mean(acc[n])), 1)] for n in order]}
+        if rank == 0:       # AFTER the bench line (a separate stderr line + file): the bench line stays the one stdout line
+            print("phases " + json.dumps(phases), file=sys.stderr, flush=True)
+            out = args.phases_out or (os.path.join(ROOT, "gpurun_out", "phases_%s_n%d.json" % (args.workload, world))
+                                      if os.path.isdir(os.path.join(ROOT, "gpurun_out")) else None)
+            if out:
+                with open(out, "w") as fh:
+                    json.dump(phases, fh)
     if world > 1:
         dist.barrier()
     dist.destroy_process_group()
@@ -638,6 +644,7 @@ def main():
                          "reads the rows from their owners over NVLink inside the gather (remote)")
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--phases", type=int, default=0, help="also record a per-phase timeline over this many eager steps")
+    ap.add_argument("--phases-out", default=None)
     ap.add_argument("--no-check", action="store_true", help="skip the pre-run parity check against the live-reference golden")
     ap.add_argument("--cpu-budget", type=float, default=15.0)
     ap.add_argument("--no-cpu", action="store_true")
