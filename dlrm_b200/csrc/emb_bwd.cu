@@ -443,9 +443,22 @@ __device__ __noinline__ float4 upd_sum_duplicates(const EmbBwdParams& P, int nxt
   return g;
 }
 
-template <typename idx_t, int PF>      // PF: row PAIRS in flight per warp
-__global__ void __launch_bounds__(256, 3) emb_update_lean_kernel(const __grid_constant__ EmbBwdParams P, int num_tables,
-                                                                 long long total_hint) {
+// One window (32 consecutive occurrence positions, one per lane) in flight between the stages of the update:
+// stage 0 reads the index and the list entry (coalesced), stage 1 the row's list head and accumulator (one random
+// sector), stage 2 updates the rows this window owns.  PIPE: stage 0 of window w+2 and stage 1 of window w+1 are
+// issued BEFORE stage 2 of window w, so their two dependent round trips (a random access over > 100 GB of tables
+// takes microseconds under load) hide behind the row traffic instead of preceding it.
+struct UpdWin {
+  int k;        // table of the lane's position
+  int r;        // row inside the shard, -1: not this kernel's (padding, another shard, a gap between tables)
+  int2 lk;      // list entry of the position: (previous occurrence + 1, bag)
+  int hd;       // the row's list head
+  float m;      // the row's accumulator
+};
+
+template <typename idx_t, int PF, int MINB, bool PIPE>      // PF: row PAIRS in flight per warp
+__global__ void __launch_bounds__(256, MINB) emb_update_lean_kernel(const __grid_constant__ EmbBwdParams P, int num_tables,
+                                                                    long long total_hint) {
   __shared__ long long bound[DLRM_B200_MAX_TABLES_PER_CALL + 1], tend[DLRM_B200_MAX_TABLES_PER_CALL + 1];
   __shared__ UpdTableS ts[DLRM_B200_MAX_TABLES_PER_CALL];
   for (int k = threadIdx.x; k < num_tables; k += blockDim.x) {
@@ -466,41 +479,66 @@ __global__ void __launch_bounds__(256, 3) emb_update_lean_kernel(const __grid_co
   const bool col_ok = lane * 4 < D;                          // full-warp layout of the duplicate path
   const long long first = bound[0], total = bound[num_tables];
   const long long warp0 = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  const long long wstride = (long long)gridDim.x * (blockDim.x >> 5);
+  const long long wstep = (long long)gridDim.x * (blockDim.x >> 5) * 32;
   const float inv_d = 1.0f / (float)D;
   const float nlr = -P.lr;
   const bool adagrad = P.optimizer == DLRM_OPT_RWSADAGRAD;
   const int dbg = P.debug;
 
-  for (long long base = first + warp0 * 32; base < total; base += wstride * 32) {
+  auto stage0 = [&](long long base, UpdWin& w) {
+    w.r = -1;
+    w.k = 0;
+    w.lk = make_int2(0, 0);
+    if (base >= total) return;
     const long long pos = base + lane;
     // table of this window: lane 0's, unless the window crosses into the next table
     int k = table_of(bound, num_tables, base);
     if (base + 31 >= bound[k + 1]) k = table_of(bound, num_tables, pos < total ? pos : base);
-    const bool valid = pos < total && pos < tend[k];       // positions between two tables of the call are not ours
+    w.k = k;
     const UpdTableS& tb = ts[k];
-    float* wptr = nullptr;
-    const float* gptr = nullptr;
-    float* mptr = nullptr;
-    int* hptr = nullptr;
-    int nxt = 0, bag = 0;
-    bool owner = false;
-    if (valid && tb.head != nullptr) {
+    if (pos < total && pos < tend[k] && tb.head != nullptr) {   // positions between two tables of the call are not ours
       const long long r = (long long)static_cast<const idx_t*>(tb.idx)[pos - tb.pair_base] - tb.row_lo;
-      if ((unsigned long long)r < (unsigned long long)tb.row_n) {
-        hptr = tb.head + r * tb.hs;
-        if (*hptr == (int)(pos + 1)) {          // the last occurrence to arrive owns the row
-          owner = true;
-          const int2 lk = P.link[pos];
-          nxt = lk.x;
-          bag = lk.y;
-          wptr = tb.w + r * tb.ld;
-          gptr = dy_row(P, bag) + tb.dy_off;
-          mptr = adagrad ? tb.mom + r * tb.mom_stride : nullptr;
-        }
-      }
+      w.lk = P.link[pos];
+      if ((unsigned long long)r < (unsigned long long)tb.row_n) w.r = (int)r;
     }
-    float m_old = (owner && adagrad) ? *mptr : 0.f;
+  };
+  auto stage1 = [&](UpdWin& w) {
+    w.hd = 0;
+    w.m = 0.f;
+    if (w.r >= 0) {
+      const UpdTableS& tb = ts[w.k];
+      w.hd = tb.head[(long long)w.r * tb.hs];
+      if (adagrad) w.m = tb.mom[(long long)w.r * tb.mom_stride];
+    }
+  };
+
+  long long base = first + warp0 * 32;
+  UpdWin w1, w2;                 // w1: stage 1 issued; w2: stage 0 issued
+  if (PIPE) {
+    stage0(base, w1);
+    stage1(w1);
+    stage0(base + wstep, w2);
+  }
+  for (; base < total; base += wstep) {
+    UpdWin w;
+    if (PIPE) {
+      w = w1;
+      w1 = w2;
+      stage1(w1);                              // head + accumulator of the next window
+      stage0(base + 2 * wstep, w2);            // index + list entry of the one after
+    } else {
+      stage0(base, w);
+      stage1(w);
+    }
+    const long long pos = base + lane;
+    const UpdTableS& tb = ts[w.k];
+    const bool owner = w.r >= 0 && w.hd == (int)(pos + 1);      // the last occurrence to arrive owns the row
+    const int nxt = owner ? w.lk.x : 0, bag = w.lk.y;
+    float* wptr = owner ? tb.w + (long long)w.r * tb.ld : nullptr;
+    const float* gptr = owner ? dy_row(P, bag) + tb.dy_off : nullptr;
+    float* mptr = (owner && adagrad) ? tb.mom + (long long)w.r * tb.mom_stride : nullptr;
+    int* hptr = owner ? tb.head + (long long)w.r * tb.hs : nullptr;
+    const float m_old = owner ? w.m : 0.f;
     unsigned simple = __ballot_sync(0xffffffffu, owner && nxt == 0);
     unsigned dups = __ballot_sync(0xffffffffu, owner && nxt != 0);
 
@@ -719,14 +757,24 @@ static int emb_update_impl(const dlrm_emb_bwd_table_t* tables, int num_tables, i
     long long gl = (total / 32 + block / 32) / (block / 32);
     if (gl > (long long)sms * 3) gl = (long long)sms * 3;
     if (gl < 1) gl = 1;
-    const bool pf2 = get_tunable(TUNE_UPD_LEAN) == 3;     // 2 row pairs in flight (79 registers, no spills) instead of 3
-    if (idx_bytes == 8) {
-      if (pf2) emb_update_lean_kernel<long long, 2><<<(unsigned)gl, block, 0, st>>>(P, num_tables, total_hint);
-      else emb_update_lean_kernel<long long, 3><<<(unsigned)gl, block, 0, st>>>(P, num_tables, total_hint);
-    } else {
-      if (pf2) emb_update_lean_kernel<int, 2><<<(unsigned)gl, block, 0, st>>>(P, num_tables, total_hint);
-      else emb_update_lean_kernel<int, 3><<<(unsigned)gl, block, 0, st>>>(P, num_tables, total_hint);
-    }
+    // TUNE_UPD_LEAN: 1 (default) = software-pipelined windows, 3 row pairs in flight, 2 CTAs/SM (128 registers);
+    // 4 = pipelined, 2 pairs, 3 CTAs/SM; 5 = not pipelined, 3 pairs, 3 CTAs/SM; 3 = not pipelined, 2 pairs; 6 / 7 = 4 pairs,
+    // 2 CTAs/SM, pipelined / not (2 = general kernel)
+    const int var = (int)get_tunable(TUNE_UPD_LEAN);
+    const int per_sm = (var == 1 || var == 0 || var == 6 || var == 7) ? 2 : 3;
+    if (gl > (long long)sms * per_sm) gl = (long long)sms * per_sm;
+#define LEAN(IT)                                                                                                   \
+    do {                                                                                                            \
+      if (var == 3) emb_update_lean_kernel<IT, 2, 3, false><<<(unsigned)gl, block, 0, st>>>(P, num_tables, total_hint);       \
+      else if (var == 5) emb_update_lean_kernel<IT, 3, 3, false><<<(unsigned)gl, block, 0, st>>>(P, num_tables, total_hint);  \
+      else if (var == 4) emb_update_lean_kernel<IT, 2, 3, true><<<(unsigned)gl, block, 0, st>>>(P, num_tables, total_hint);   \
+      else if (var == 6) emb_update_lean_kernel<IT, 4, 2, true><<<(unsigned)gl, block, 0, st>>>(P, num_tables, total_hint);   \
+      else if (var == 7) emb_update_lean_kernel<IT, 4, 2, false><<<(unsigned)gl, block, 0, st>>>(P, num_tables, total_hint);  \
+      else emb_update_lean_kernel<IT, 3, 2, true><<<(unsigned)gl, block, 0, st>>>(P, num_tables, total_hint);                 \
+    } while (0)
+    if (idx_bytes == 8) LEAN(long long);
+    else LEAN(int);
+#undef LEAN
     DLRM_CHECK_LAUNCH("emb_update_lean_kernel");
     return 0;
   }
