@@ -557,6 +557,23 @@ def ours(args, W):
     dist.destroy_process_group()
 
 
+def ncu_traffic(kernel, path="profiles/r2_ncu_full_cfg3_gather_update.csv"):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of `kernel` from the committed ncu --set full capture
+    (cfg3, batch 8192, 1 GPU; tools/gpu_r2_15.sh), in bytes; None when the file is not there."""
+    import csv
+
+    mult = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    try:
+        with open(os.path.join(ROOT, path)) as fh:
+            rows = list(csv.reader(fh))
+        h, units = rows[0], rows[1]
+        ir, iw, ik = h.index("dram__bytes_read.sum"), h.index("dram__bytes_write.sum"), h.index("Kernel Name")
+        v = [float(r[ir]) * mult[units[ir]] + float(r[iw]) * mult[units[iw]] for r in rows[2:] if kernel in r[ik]]
+        return float(np.mean(v)) if v else None
+    except Exception:
+        return None
+
+
 def measure_rooflines(de, stages, load_dev, pre, args, W, cost, hbm_peak, peak_src, train):
     """The HBM-bound kernels timed with CUDA events on the launching stream (N = 1): the forward gather alone
     (back-to-back launches over the batch ring) and, for training, (gather+link, update) pairs."""
@@ -596,8 +613,11 @@ def measure_rooflines(de, stages, load_dev, pre, args, W, cost, hbm_peak, peak_s
     by = nnz * D * 4 + scanned * idx_b + T * B * idx_b + T * B * D * 4  # rows + indices + offsets + pooled out
     ach = by / tg / 1e9
     roof = {"kernel": "emb_fwd_vec_kernel (multi-table EmbeddingBag gather, forward)", "bound": "hbm", "achieved": ach,
-            "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak, "traffic": None,
-            "traffic_source": "see profiles/ (ncu --set full capture of this round)", "peak_source": peak_src,
+            "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak,
+            "traffic": ncu_traffic("emb_fwd_vec_kernel") if (args.workload == "cfg3" and de.world == 1) else None,
+            "traffic_source": "profiles/r2_ncu_full_cfg3_gather_update.csv: dram read + write bytes per launch of the "
+                              "training gather (ncu --set full, same workload; the forward-only gather differs by the "
+                              "14 MB list-entry stream)", "peak_source": peak_src,
             "avg_launch_us": tg * 1e6, "algorithmic_bytes_per_launch": by,
             "how": "CUDA events around each gather launch on the launching stream, median of %d over the batch ring" % n}
     roof_upd = None
@@ -622,7 +642,8 @@ def measure_rooflines(de, stages, load_dev, pre, args, W, cost, hbm_peak, peak_s
         by_u = nnz * (D * 4 * 2 + 8) + T * B * D * 4 + scanned * idx_b  # SURVEY 8(d) bytes_bwd (unique rows ~ nnz)
         achu = by_u / tu / 1e9
         roof_upd = {"kernel": "emb_update_kernel (+ emb_small_*: coalesce + row-wise Adagrad, in place)", "bound": "hbm",
-                    "achieved": achu, "peak": hbm_peak, "unit": "GB/s", "frac": achu / hbm_peak, "traffic": None,
+                    "achieved": achu, "peak": hbm_peak, "unit": "GB/s", "frac": achu / hbm_peak,
+                    "traffic": ncu_traffic("emb_update_lean_kernel") if (args.workload == "cfg3" and de.world == 1) else None,
                     "avg_launch_us": tu * 1e6, "algorithmic_bytes_per_launch": by_u,
                     "train_gather_plus_link_us": t_gl * 1e6,
                     "train_gather": {"achieved": by / t_gl / 1e9, "frac": by / t_gl / 1e9 / hbm_peak},

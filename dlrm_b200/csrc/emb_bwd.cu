@@ -757,20 +757,23 @@ static int emb_update_impl(const dlrm_emb_bwd_table_t* tables, int num_tables, i
     long long gl = (total / 32 + block / 32) / (block / 32);
     if (gl > (long long)sms * 3) gl = (long long)sms * 3;
     if (gl < 1) gl = 1;
-    // TUNE_UPD_LEAN: 1 (default) = software-pipelined windows, 3 row pairs in flight, 2 CTAs/SM (128 registers);
-    // 4 = pipelined, 2 pairs, 3 CTAs/SM; 5 = not pipelined, 3 pairs, 3 CTAs/SM; 3 = not pipelined, 2 pairs; 6 / 7 = 4 pairs,
-    // 2 CTAs/SM, pipelined / not (2 = general kernel)
-    const int var = (int)get_tunable(TUNE_UPD_LEAN);
-    const int per_sm = (var == 1 || var == 0 || var == 6 || var == 7) ? 2 : 3;
+    // TUNE_UPD_LEAN (cfg3 update, us, tools/upd_variants.py on one B200): 0/3 (default) = 2 row pairs in flight per warp,
+    // 3 CTAs/SM: 797; 5 = 3 pairs, 3 CTAs/SM: 838; 4 = 2 pairs, 3 CTAs/SM, software-pipelined windows: 848; 1 = pipelined,
+    // 3 pairs, 2 CTAs/SM: 983-1004; 6 / 7 = 4 pairs, 2 CTAs/SM, pipelined / not: 991 / 984 (2 = the general kernel).
+    // More rows in flight per warp and hiding the two leading round trips do not pay: the kernel is bound by the RATE
+    // of random accesses (list head + accumulator, row read, row write), not by the latency of any one of them.
+    int var = (int)get_tunable(TUNE_UPD_LEAN);
+    if (var == 0) var = 3;
+    const int per_sm = (var == 1 || var == 6 || var == 7) ? 2 : 3;
     if (gl > (long long)sms * per_sm) gl = (long long)sms * per_sm;
 #define LEAN(IT)                                                                                                   \
     do {                                                                                                            \
-      if (var == 3) emb_update_lean_kernel<IT, 2, 3, false><<<(unsigned)gl, block, 0, st>>>(P, num_tables, total_hint);       \
-      else if (var == 5) emb_update_lean_kernel<IT, 3, 3, false><<<(unsigned)gl, block, 0, st>>>(P, num_tables, total_hint);  \
+      if (var == 5) emb_update_lean_kernel<IT, 3, 3, false><<<(unsigned)gl, block, 0, st>>>(P, num_tables, total_hint);  \
       else if (var == 4) emb_update_lean_kernel<IT, 2, 3, true><<<(unsigned)gl, block, 0, st>>>(P, num_tables, total_hint);   \
       else if (var == 6) emb_update_lean_kernel<IT, 4, 2, true><<<(unsigned)gl, block, 0, st>>>(P, num_tables, total_hint);   \
       else if (var == 7) emb_update_lean_kernel<IT, 4, 2, false><<<(unsigned)gl, block, 0, st>>>(P, num_tables, total_hint);  \
-      else emb_update_lean_kernel<IT, 3, 2, true><<<(unsigned)gl, block, 0, st>>>(P, num_tables, total_hint);                 \
+      else if (var == 1) emb_update_lean_kernel<IT, 3, 2, true><<<(unsigned)gl, block, 0, st>>>(P, num_tables, total_hint);   \
+      else emb_update_lean_kernel<IT, 2, 3, false><<<(unsigned)gl, block, 0, st>>>(P, num_tables, total_hint);                \
     } while (0)
     if (idx_bytes == 8) LEAN(long long);
     else LEAN(int);

@@ -319,7 +319,9 @@ def test_cfg2_full_size_one_training_step_matches_oracle():
         errs.append(np.abs(got - params["emb"][k]).ravel())
         m = e.momentum[int(e.row_base[k]):int(e.row_base[k + 1])]
         gm = m[u].cpu().numpy()
-        merr.append(np.abs(gm - state["mom"][k]) / np.maximum(state["mom"][k], 1e-30))
+        # rows whose gradient is at the GEMMs' rounding level have O(1) relative error in mean(g^2): scale those by
+        # the table's typical accumulator instead
+        merr.append(np.abs(gm - state["mom"][k]) / np.maximum(state["mom"][k], 1e-2 * np.median(state["mom"][k])))
         # untouched rows: accumulators still zero, checksum unchanged; every touched row moved
         assert int((m != 0).sum().item()) <= uniq[k].size
         rest1 = float(e.table(k).double().sum().item()) - float(e.table(k)[u].double().sum().item())
