@@ -294,6 +294,59 @@ def parity_check(de_cls, dev, gemm):
     return err      # the (tiny) engine stays alive: its buffers are mapped into the peers
 
 
+class Progress:
+    """Stage log + watchdog.  Every stage is announced on stderr (rank 0; all ranks with DLRM_BENCH_VERBOSE=1) with
+    the seconds since start, so that a stalled run says WHERE it stalled.  A daemon thread watches the time spent in
+    the current stage: past the limit (DLRM_BENCH_STAGE_LIMIT seconds, default 240) rank 0 prints the bench line
+    with whatever has been measured so far plus an "error" field, and every rank leaves with os._exit -- a stuck
+    collective or a spinning kernel would otherwise hold the job until the caller's own timeout with no line at all.
+    Optional stages (parity check, kernel rooflines, phase timeline) run AFTER the timed regions for that reason."""
+
+    def __init__(self, rank):
+        import threading
+
+        self.rank, self.t0 = rank, time.time()
+        self.stage_name, self.stage_t = "start", self.t0
+        self.limit = float(os.environ.get("DLRM_BENCH_STAGE_LIMIT", "240"))
+        self.verbose = rank == 0 or os.environ.get("DLRM_BENCH_VERBOSE") == "1"
+        self.line = None              # filled by the main flow as results arrive (rank 0)
+        self.extra = {}
+        self.printed = False
+        self.lock = threading.Lock()
+        self.done = False
+        threading.Thread(target=self._watch, daemon=True).start()
+
+    def stage(self, name):
+        self.stage_name, self.stage_t = name, time.time()
+        if self.verbose:
+            print("[bench r%d %6.1fs] %s" % (self.rank, self.stage_t - self.t0, name), file=sys.stderr, flush=True)
+
+    def emit(self, error=None):
+        """Print the bench line once (rank 0)."""
+        with self.lock:
+            if self.printed or self.rank != 0 or self.line is None:
+                return
+            self.printed = True
+            line = dict(self.line)
+            line.update(self.extra)
+            if error:
+                line["error"] = error
+            print(json.dumps(line), flush=True)
+
+    def _watch(self):
+        while not self.done:
+            time.sleep(2.0)
+            dt = time.time() - self.stage_t
+            if not self.done and dt > self.limit:
+                msg = "stalled in stage '%s' for %.0f s (rank %d)" % (self.stage_name, dt, self.rank)
+                print("[bench r%d] WATCHDOG: %s" % (self.rank, msg), file=sys.stderr, flush=True)
+                have_value = self.line is not None and self.line.get("value") is not None
+                if self.rank == 0 and self.line is None:
+                    self.line = {"metric": None, "value": None}
+                self.emit(error=msg)
+                os._exit(0 if have_value else 3)
+
+
 def ours(args, W):
     import torch.distributed as dist
     from dlrm_b200 import dist as ddist, placement as P
@@ -303,6 +356,10 @@ def ours(args, W):
     if "RANK" not in os.environ:       # N = 1 without a launcher: a 1-rank group
         os.environ.update(RANK="0", WORLD_SIZE="1", LOCAL_RANK="0", MASTER_ADDR="127.0.0.1",
                           MASTER_PORT=str(_free_port()))
+    prog = Progress(int(os.environ.get("RANK", "0")))
+    prog.stage("process group (NCCL bring-up)")
+    # NCCL only brings the job up (handles, scalars, barriers): no NVLS / multicast setup is needed for that
+    os.environ.setdefault("NCCL_NVLS_ENABLE", "0")
     rank, world = ddist.init_distributed("nccl")
     local = int(os.environ.get("LOCAL_RANK", str(rank)))
     dev = "cuda:%d" % local
@@ -315,8 +372,7 @@ def ours(args, W):
     B, T = W["B"], len(rows)
     cost = lookups_per_sample(W)
     check = None
-    if not args.no_check and train:
-        check = parity_check(ddist.DistEngine, dev, args.gemm)
+    prog.stage("engine: placement, tables, peer mappings")
     pl = P.plan(rows, cost, world)
     de = ddist.DistEngine(D, rows, ln_bot, ln_top, local_batch=B, device=dev, gemm=args.gemm, exchange="p2p",
                           placement=pl, split_forward=args.split_forward)
@@ -327,6 +383,7 @@ def ours(args, W):
     lr = 0.01
     nsets = 2
     fixed = W["hot"] is not None
+    prog.stage("inputs: host batches, device ring, index exchange buffers")
     # ---- inputs: a ring of packed pinned host batches (this rank's share) + their device copies
     if fixed:
         mh = ddist.MultiHotExchange(de, W["hot"], 13, nsets)
@@ -376,6 +433,7 @@ def ours(args, W):
     if world > 1:
         dist.barrier()
     graphs = None
+    prog.stage("CUDA graph capture (3 eager steps + capture per buffer set)")
     if not args.no_graph:
         graphs = [GraphedTrainStep(de.eng, stages[k], lr, "rwsadagrad", train=train, pre=pre(k)) for k in range(nsets)]
 
@@ -399,9 +457,11 @@ def ours(args, W):
         load_dev(k, i)
         return run_set(k)
 
+    prog.stage("warm-up steps")
     for w in range(args.warmup):
         resident_step(w)
     sync_all()
+    prog.stage("timed steps (device-resident inputs)")
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
@@ -421,7 +481,13 @@ def ours(args, W):
     if world > 1:
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     ms = float(ms.item())
+    if rank == 0:       # from here on a stall still yields a line with the device-resident number
+        prog.line = {"metric": metric_name(train), "value": B * world / (ms * 1e-3), "unit": "samples/s", "n_gpus": world,
+                     "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
+                     "scaling": "weak", "vs_baseline": None, "data": "synthetic", "config": config_dict(args, W, world),
+                     "gpu_launches": int(launches), "e2e": None}
 
+    prog.stage("timed steps (end to end: H2D + step + loss D2H)")
     # ---- e2e: host buffers; H2D of the packed batch + D2H of the loss inside the timed region
     copy_stream = torch.cuda.Stream()
     loss_host = torch.zeros(1).pin_memory()
@@ -471,32 +537,16 @@ def ours(args, W):
         gbs = [gb]
     gbs = [float(g.item()) for g in gbs]
 
-    roof = roof_upd = cb = None
-    # Rank 0 ALONE times its gather / update kernels (at N > 1 the other ranks wait in the final barrier): the loop
-    # refreshes the indices between a link and its update without the step's barriers, which is only safe while no
-    # peer is running its own link / update on indices this rank's exchange overwrites.
-    if rank == 0:
-        peaks = {}
-        try:
-            with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as fh:
-                peaks = json.load(fh)
-        except Exception:
-            pass
-        hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
-        peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s"
-        roof, roof_upd = measure_rooflines(de, stages, load_dev, pre, args, W, cost, hbm_peak, peak_src, train)
-        if not args.no_cpu and world == 1:
-            cb = cpu_arm(args, W, budget_s=args.cpu_budget)
     if rank == 0:
         clocks = sampler.stop(t0, t1)
         Bg = B * world
-        line = {
+        prog.line = {
             "metric": metric_name(train), "value": Bg / (ms * 1e-3), "unit": "samples/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None,
             "dtype": {"simt": "fp32", "tc": "fp32 (bf16x3 split on tcgen05, fp32 accumulate)", "tc_bf16": "bf16"}[args.gemm],
             "data": "synthetic", "config": config_dict(args, W, world),
-            "roofline": roof, "roofline_update": roof_upd, "cpu_baseline": cb,
+            "roofline": None, "roofline_update": None, "cpu_baseline": None,
             "e2e": {"value": Bg / (ms2 * 1e-3), "unit": "samples/s", "h2d_bytes_per_step": int(h2d / args.steps),
                     "d2h_bytes_per_step": 4, "ms_per_step": ms2,
                     "note": "per rank: ONE packed pinned buffer with ITS samples (dense, targets, int32 indices of all "
@@ -511,11 +561,45 @@ def ours(args, W):
             "placement": {"split_tables": pl.split_tables(), "imbalance": pl.imbalance(),
                           "gather_bytes_per_rank_per_step": gbs,
                           "gather_bytes_max_over_min": max(gbs) / max(min(gbs), 1.0)},
-            "parity_check": check, "clocks": clocks,
+            "parity_check": None, "clocks": clocks,
         }
-        print(json.dumps(line), flush=True)
+    # ---- the stages below add fields to the line; if one of them stalls the watchdog prints the line without it
+    if not args.no_check and train:
+        prog.stage("parity check: golden cfg0 through the same sharded engine / placement policy / exchange")
+        try:
+            prog.extra["parity_check"] = parity_check(ddist.DistEngine, dev, args.gemm)
+        except Exception as exc:      # the measured numbers above are still reported, with the failure next to them
+            prog.extra["parity_check"] = {"ok": False, "error": repr(exc)[:400]}
+    # Rank 0 ALONE times its gather / update kernels (at N > 1 the other ranks wait in the next collective): the loop
+    # refreshes the indices between a link and its update without the step's barriers, which is only safe while no
+    # peer is running its own link / update on indices this rank's exchange overwrites.
+    if rank == 0:
+        prog.stage("kernel rooflines (gather, gather+link, update between CUDA events)")
+        peaks = {}
+        try:
+            with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as fh:
+                peaks = json.load(fh)
+        except Exception:
+            pass
+        hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+        peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s"
+        try:
+            roof, roof_upd = measure_rooflines(de, stages, load_dev, pre, args, W, cost, hbm_peak, peak_src, train)
+            prog.extra.update(roofline=roof, roofline_update=roof_upd)
+        except Exception as exc:
+            prog.extra["roofline"] = {"error": repr(exc)[:400]}
+        if not args.no_cpu and world == 1:
+            prog.stage("cpu baseline (live reference on the host cores)")
+            prog.stage_t += 600.0          # building the reference model's 13 GB of tables takes a while
+            try:
+                prog.extra["cpu_baseline"] = cpu_arm(args, W, budget_s=args.cpu_budget)
+            except Exception as exc:
+                prog.extra["cpu_baseline"] = {"error": repr(exc)[:400]}
+        prog.stage("bench line")
+        prog.emit()
     # ---- optional phase timeline (eager launches, timing events on every stream): where the step's time goes
     if args.phases > 0:
+        prog.stage("phase timeline (eager steps)")
         acc = {}
         order = []
         for r in range(args.phases + 2):
@@ -552,8 +636,10 @@ def ours(args, W):
             if out:
                 with open(out, "w") as fh:
                     json.dump(phases, fh)
+    prog.stage("teardown")
     if world > 1:
         dist.barrier()
+    prog.done = True
     dist.destroy_process_group()
 
 

@@ -109,11 +109,15 @@ def init_distributed(backend: Optional[str] = None):
     os.environ.setdefault("MASTER_PORT", "29500")
     if backend is None:
         backend = "nccl" if torch.cuda.is_available() else "gloo"
+    import datetime
+
+    # a collective one rank never joins must fail loudly within minutes, not after NCCL's default 10
+    tmo = datetime.timedelta(seconds=float(os.environ.get("DLRM_PG_TIMEOUT_S", "300")))
     if backend == "nccl":
         torch.cuda.set_device(local)
-        dist.init_process_group(backend, rank=rank, world_size=world, device_id=torch.device("cuda", local))
+        dist.init_process_group(backend, rank=rank, world_size=world, device_id=torch.device("cuda", local), timeout=tmo)
     else:
-        dist.init_process_group(backend, rank=rank, world_size=world)
+        dist.init_process_group(backend, rank=rank, world_size=world, timeout=tmo)
     return rank, world
 
 
