@@ -297,7 +297,8 @@ def parity_check(de_cls, dev, gemm):
 class Progress:
     """Stage log + watchdog.  Every stage is announced on stderr (rank 0; all ranks with DLRM_BENCH_VERBOSE=1) with
     the seconds since start, so that a stalled run says WHERE it stalled.  A daemon thread watches the time spent in
-    the current stage: past the limit (DLRM_BENCH_STAGE_LIMIT seconds, default 240) rank 0 prints the bench line
+    the current stage: past the limit (DLRM_BENCH_STAGE_LIMIT seconds, default 240, once a number has been measured;
+    DLRM_BENCH_SETUP_LIMIT, default 1500, before) rank 0 prints the bench line
     with whatever has been measured so far plus an "error" field, and every rank leaves with os._exit -- a stuck
     collective or a spinning kernel would otherwise hold the job until the caller's own timeout with no line at all.
     Optional stages (parity check, kernel rooflines, phase timeline) run AFTER the timed regions for that reason."""
@@ -307,7 +308,10 @@ class Progress:
 
         self.rank, self.t0 = rank, time.time()
         self.stage_name, self.stage_t = "start", self.t0
+        # before a number exists a stall can only be reported, so the limit is long (cold 8-GPU boxes take minutes
+        # to bring NCCL up); after it, the optional stages get DLRM_BENCH_STAGE_LIMIT seconds each
         self.limit = float(os.environ.get("DLRM_BENCH_STAGE_LIMIT", "240"))
+        self.limit_before_value = max(self.limit, float(os.environ.get("DLRM_BENCH_SETUP_LIMIT", "1500")))
         self.verbose = rank == 0 or os.environ.get("DLRM_BENCH_VERBOSE") == "1"
         self.line = None              # filled by the main flow as results arrive (rank 0)
         self.extra = {}
@@ -337,7 +341,8 @@ class Progress:
         while not self.done:
             time.sleep(2.0)
             dt = time.time() - self.stage_t
-            if not self.done and dt > self.limit:
+            measured = self.line is not None or (self.rank != 0 and self.stage_name.startswith(("parity", "teardown", "phase")))
+            if not self.done and dt > (self.limit if measured else self.limit_before_value):
                 msg = "stalled in stage '%s' for %.0f s (rank %d)" % (self.stage_name, dt, self.rank)
                 print("[bench r%d] WATCHDOG: %s" % (self.rank, msg), file=sys.stderr, flush=True)
                 have_value = self.line is not None and self.line.get("value") is not None
@@ -362,7 +367,7 @@ def ours(args, W):
     os.environ.setdefault("NCCL_NVLS_ENABLE", "0")
     rank, world = ddist.init_distributed("nccl")
     local = int(os.environ.get("LOCAL_RANK", str(rank)))
-    dev = "cuda:%d" % local
+    dev = os.environ.get("DLRM_BENCH_TEST_DEVICE") or "cuda:%d" % local     # (tests/test_bench_host.py drives the flow on fakes)
     torch.cuda.set_device(local)
     warm = torch.zeros(1, device=dev)      # create the communicator now: NCCL prints its version line to stdout at
     dist.all_reduce(warm)                  # the first collective, and the JSON line must be the LAST line

@@ -111,8 +111,8 @@ def init_distributed(backend: Optional[str] = None):
         backend = "nccl" if torch.cuda.is_available() else "gloo"
     import datetime
 
-    # a collective one rank never joins must fail loudly within minutes, not after NCCL's default 10
-    tmo = datetime.timedelta(seconds=float(os.environ.get("DLRM_PG_TIMEOUT_S", "300")))
+    # generous: on a cold 8-GPU box the ranks finish importing / creating contexts minutes apart
+    tmo = datetime.timedelta(seconds=float(os.environ.get("DLRM_PG_TIMEOUT_S", "1200")))
     if backend == "nccl":
         torch.cuda.set_device(local)
         dist.init_process_group(backend, rank=rank, world_size=world, device_id=torch.device("cuda", local), timeout=tmo)
