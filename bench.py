@@ -683,8 +683,16 @@ def measure_rooflines(de, stages, load_dev, pre, args, W, cost, hbm_peak, peak_s
         prep(i)
         eng.emb_forward(stages[k].sparse)
     torch.cuda.synchronize()
+    def hold_gpu():
+        # The host needs ~0.1-0.2 ms per iteration to build the launch descriptors; with an empty queue that time would
+        # sit between the two events of a short kernel.  A spin kernel first, so that every launch of the loop is
+        # already queued when the GPU reaches it.
+        if hasattr(torch.cuda, "_sleep"):
+            torch.cuda._sleep(int(4e5) * (n + 8))         # ~0.2 ms of spinning per queued iteration
+
     # gather alone: the index refresh (D2D + exchange) sits between the timed launches, so bracket each launch
     evs = []
+    hold_gpu()
     for i in range(n):
         prep(i)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -716,6 +724,7 @@ def measure_rooflines(de, stages, load_dev, pre, args, W, cost, hbm_peak, peak_s
         eng.dT.normal_()
         eng.head.zero_()
         evs = []
+        hold_gpu()
         for i in range(n + 3):
             prep(i)
             e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))

@@ -111,6 +111,10 @@ def init_distributed(backend: Optional[str] = None):
         backend = "nccl" if torch.cuda.is_available() else "gloo"
     import datetime
 
+    # NCCL only brings the job up here (IPC handles, scalars, host-side barriers); the data path is our own kernels over
+    # peer-mapped memory.  No NVLS / multicast resources are needed for that, and their setup is the slowest part of
+    # creating a communicator on an NVSwitch box.
+    os.environ.setdefault("NCCL_NVLS_ENABLE", "0")
     # generous: on a cold 8-GPU box the ranks finish importing / creating contexts minutes apart
     tmo = datetime.timedelta(seconds=float(os.environ.get("DLRM_PG_TIMEOUT_S", "1200")))
     if backend == "nccl":
