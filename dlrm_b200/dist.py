@@ -282,14 +282,11 @@ class DistEngine:
         e.route_dy = [j * D for j in range(self.Tl)]
         e.dy_stride = self.Tl * D
         # interact_bwd: feature 0 stays local; feature 1 + t goes to slab `rank` of every rank storing rows of t
-        dst, ld, first = [e.dT.data_ptr()], [e.F * D], [0, 1]
-        for t in range(self.Tg):
-            for s in self.pl.of_table(t):
-                own = self.pl.of_rank(s.rank)
-                j = own.index(s)
-                dst.append(pdT[s.rank] + ((self.rank * B) * len(own) + j) * D * 4)
-                ld.append(len(own) * D)
-            first.append(len(dst))
+        from .sharding import grad_routes
+
+        routes, first = grad_routes(self.pl, self.rank, B, D, e.F)
+        dst = [e.dT.data_ptr() if r < 0 else pdT[r] + off * 4 for r, off, _ in routes]
+        ld = [stride for _, _, stride in routes]
         n = len(dst)
         e.dT_route = ((C.c_void_p * n)(*dst), (C.c_int64 * n)(*ld), (C.c_int * (e.F + 1))(*first))
         self._peer_sig = [(C.c_void_p * W)(*[p + 64 * ch for p in psig]) for ch in range(2)]
@@ -462,19 +459,19 @@ class MultiHotExchange:
         self._copies = []
         if W > 1:
             ptrs = de.share([t for k in range(nsets) for t in self.idxg[k]])
+        from .sharding import index_copies
+
         for k in range(nsets):
             src, dst, nb = [], [], []
-            for t, L in enumerate(self.hot):
-                for s in de.pl.of_table(t):
-                    j = de.pl.of_rank(s.rank).index(s)
-                    nloc = len(de.pl.of_rank(s.rank))
-                    if W > 1:
-                        base = ptrs[s.rank][k * nloc + j] if s.rank != de.rank else self.idxg[k][j].data_ptr()
-                    else:
-                        base = self.idxg[k][j].data_ptr()
-                    src.append(self.stage[k].data_ptr() + self.off_idx[t])
-                    dst.append(base + de.rank * B * L * 4)
-                    nb.append(B * L * 4)
+            for t, r, j, off, n in index_copies(de.pl, de.rank, self.hot, B):
+                nloc = len(de.pl.of_rank(r))
+                if W > 1:
+                    base = ptrs[r][k * nloc + j] if r != de.rank else self.idxg[k][j].data_ptr()
+                else:
+                    base = self.idxg[k][j].data_ptr()
+                src.append(self.stage[k].data_ptr() + self.off_idx[t])
+                dst.append(base + off * 4)
+                nb.append(n * 4)
             self._copies.append((src, dst, nb))
         self._C = C
 

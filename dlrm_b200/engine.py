@@ -254,16 +254,10 @@ class Engine:
     def _set_default_routes(self):
         """Single-GPU routes.  out: (offset, sample stride) of shard j's pooled rows inside TP; dy: offset of
         shard j's gradient rows inside one sample of dT (sample stride F*D)."""
+        from .sharding import out_routes
+
         B, F, D = self.max_batch, self.F, self.D
-        self.route_out, self.route_dy = [], []
-        for sh in self.shards:
-            t = int(sh["table"])
-            if int(sh["nparts"]) == 1:
-                self.route_out.append(((1 + t) * D, F * D))
-            else:
-                slab = int(self.slab_first[self.slot_of[t]]) + int(sh["part"])
-                self.route_out.append((B * F * D + slab * B * D, D))
-            self.route_dy.append((1 + t) * D)
+        self.route_out, self.route_dy = out_routes(self.shards, self.split_slots, B, F, D)
         self.dy_stride = F * D
 
     def _emb_forward_remote(self, sp: SparseInput, split, link: bool):
