@@ -81,3 +81,37 @@ def test_unsupported_options_exit_with_an_error_string(cli_on_cpu, flags, msg):
     with pytest.raises(SystemExit) as e:
         cli.run(BASE + ["--num-batches=1"] + flags)
     assert msg in str(e.value)
+
+
+def test_test_pass_checkpoint_and_resume_control_flow(cli_on_cpu, capsys, tmp_path, monkeypatch):
+    """--test-freq / --save-model / --load-model on the stand-in model: the reference's lines in the reference's order
+    (dlrm_s_pytorch.py:1640-1715), its checkpoint key set, and a resume that skips the batches already trained while
+    still drawing them (the generator's order is the reference's)."""
+    cli, seen = cli_on_cpu
+    orig_load = torch.load
+    monkeypatch.setattr(torch, "load", lambda f, map_location=None, **k: orig_load(f, map_location="cpu", **k))   # no GPU here
+    ck = str(tmp_path / "m.pt")
+    common = BASE + ["--num-batches=4", "--round-targets=True", "--numpy-rand-seed=3"]
+    cli.run(common + ["--test-freq=2", "--save-model=" + ck])
+    out = capsys.readouterr().out.splitlines()
+    body = [ln for ln in out if re.match(r"Finished|Testing at| accuracy|Saving model", ln)]
+    kinds = [ln.split()[0] for ln in body]
+    assert kinds == ["Finished", "Finished", "Testing", "accuracy", "Saving", "Finished", "Finished", "Testing", "accuracy",
+                     "Saving"]
+    assert body[2] == "Testing at - 2/4 of epoch 0," and re.fullmatch(r" accuracy \d+\.\d{3} %, best \d+\.\d{3} %", body[3])
+    assert len(seen) == 4 + 2 * 4                         # 4 training batches + two test passes over 4 batches
+    sd = torch.load(ck, weights_only=False)
+    assert set(sd) == {"epoch", "iter", "nepochs", "nbatches", "nbatches_test", "state_dict", "opt_state_dict",
+                       "train_loss", "total_loss", "test_acc"}
+    assert (sd["epoch"], sd["iter"], sd["nepochs"], sd["nbatches"], sd["nbatches_test"]) == (0, 4, 1, 4, 4)
+    # resume: everything of epoch 0 was trained -> every batch is drawn and skipped
+    del seen[:]
+    cli.run(common + ["--load-model=" + ck])
+    out = capsys.readouterr().out
+    assert "Loading saved model " + ck in out and "Saved at: epoch = 0/1, batch = 4/4, ntbatch = 4" in out
+    assert "Finished training" not in out and len(seen) == 0
+    # inference only from the checkpoint: ONE test pass, no training lines
+    cli.run(common + ["--load-model=" + ck, "--inference-only"])
+    out = capsys.readouterr().out
+    assert "Testing for inference only" in out and " accuracy " in out and "Finished" not in out
+    assert len(seen) == 4
