@@ -24,10 +24,13 @@ def sources():
 
 
 def _digest():
+    """Hash of the sources' CONTENTS and names -- not of their absolute paths: the library built in the build
+    container must count as fresh in any copy of the tree (the GPU box runs a snapshot under a scratch path, and a
+    path-dependent digest made every first process there rebuild the library, all ranks of a torchrun at once)."""
     h = hashlib.sha256()
     for f in sources() + sorted(glob.glob(os.path.join(CSRC, "*.cuh"))) + [
             os.path.join(os.path.dirname(HERE), "include", "dlrm_b200.h")]:
-        h.update(f.encode())
+        h.update(os.path.basename(f).encode())
         with open(f, "rb") as fh:
             h.update(fh.read())
     h.update(" ".join(NVCC_FLAGS).encode())
@@ -56,14 +59,30 @@ def build(force=False, verbose=False):
     if nvcc is None:
         raise RuntimeError("nvcc not found: cannot build libdlrm_b200.so")
     os.makedirs(LIBDIR, exist_ok=True)
-    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB] + sources()
-    r = subprocess.run(cmd, capture_output=True, text=True)
-    if r.returncode != 0:
-        raise RuntimeError("nvcc failed:\n" + " ".join(cmd) + "\n" + r.stdout + r.stderr)
-    if verbose:
-        print(r.stderr)
-    with open(STAMP, "w") as fh:
-        fh.write(_digest())
+    # One builder at a time (the ranks of a torchrun all arrive here together): an exclusive lock, a re-check once it
+    # is held, output to a private file that is renamed into place -- nobody ever maps a half-written library.
+    import fcntl
+
+    with open(os.path.join(LIBDIR, ".build.lock"), "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        try:
+            if not force and is_fresh():
+                return LIB
+            tmp = LIB + ".tmp.%d" % os.getpid()
+            cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", tmp] + sources()
+            r = subprocess.run(cmd, capture_output=True, text=True)
+            if r.returncode != 0:
+                if os.path.exists(tmp):
+                    os.remove(tmp)
+                raise RuntimeError("nvcc failed:\n" + " ".join(cmd) + "\n" + r.stdout + r.stderr)
+            if verbose:
+                print(r.stderr)
+            os.replace(tmp, LIB)
+            with open(STAMP + ".tmp", "w") as fh:
+                fh.write(_digest())
+            os.replace(STAMP + ".tmp", STAMP)
+        finally:
+            fcntl.flock(lock, fcntl.LOCK_UN)
     return LIB
 
 

@@ -72,3 +72,23 @@ def test_struct_layouts_match_the_header(tmp_path):
         assert int(got[cname]) == C.sizeof(cls), cname
         for fname, _ in cls._fields_:
             assert int(got[cname + "." + fname]) == getattr(cls, fname).offset, cname + "." + fname
+
+
+def test_library_freshness_does_not_depend_on_where_the_tree_lives(tmp_path, monkeypatch):
+    """The in-tree library is built in one place and run from a copy of the tree under another path (the GPU box): the
+    freshness digest must cover the sources' contents and names, not their absolute paths -- otherwise every first
+    process of a copy rebuilds the library, all ranks of a torchrun at once."""
+    import shutil
+
+    from dlrm_b200 import _build
+
+    want = _build._digest()
+    root = tmp_path / "elsewhere"
+    shutil.copytree(_build.CSRC, root / "dlrm_b200" / "csrc")
+    shutil.copytree(os.path.join(os.path.dirname(_build.HERE), "include"), root / "include")
+    monkeypatch.setattr(_build, "HERE", str(root / "dlrm_b200"))
+    monkeypatch.setattr(_build, "CSRC", str(root / "dlrm_b200" / "csrc"))
+    assert _build._digest() == want
+    with open(root / "dlrm_b200" / "csrc" / "api.cu", "a") as fh:
+        fh.write("\n// edited\n")
+    assert _build._digest() != want
