@@ -376,7 +376,6 @@ def ours(args, W):
     D, rows, ln_bot, ln_top = model_dims(W)
     B, T = W["B"], len(rows)
     cost = lookups_per_sample(W)
-    check = None
     prog.stage("engine: placement, tables, peer mappings")
     pl = P.plan(rows, cost, world)
     de = ddist.DistEngine(D, rows, ln_bot, ln_top, local_batch=B, device=dev, gemm=args.gemm, exchange="p2p",

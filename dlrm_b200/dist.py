@@ -24,9 +24,7 @@ Launch: `torchrun --nproc-per-node N ...` (env RANK/LOCAL_RANK/WORLD_SIZE/MASTER
 """
 from __future__ import annotations
 
-import json
 import os
-import time
 from typing import List, Optional, Sequence, Tuple
 
 import numpy as np
