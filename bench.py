@@ -349,7 +349,8 @@ class Progress:
                 if self.rank == 0 and self.line is None:
                     self.line = {"metric": None, "value": None}
                 self.emit(error=msg)
-                os._exit(0 if have_value else 3)
+                # other ranks past the timed regions: rank 0 reports, they just leave
+                os._exit(0 if have_value or (self.rank != 0 and measured) else 3)
 
 
 def ours(args, W):
