@@ -52,6 +52,9 @@ const char* dlrm_b200_last_error(void);
 int dlrm_b200_check_device_errors(void* stream);
 /* sm count / compute capability of `device`; error unless cc >= 10.0 */
 int dlrm_b200_device_info(int device, int* sm_count, int* cc_major, int* cc_minor);
+/* Experiment knobs of the kernels (ids: csrc/common.cuh `enum Tunable`; dlrm_b200/_lib.py TUNE; env DLRM_TUNE).
+ * Process-wide, read at launch time; 0 restores the default of every knob.  Not part of the reference's surface. */
+int dlrm_b200_set_tunable(int id, int value);
 
 /* ------------------------------------------------------------------------------------------
  * apply_emb  (dlrm_s_pytorch.py:407-462: one nn.EmbeddingBag(mode="sum") call per table)
