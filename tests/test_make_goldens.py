@@ -24,3 +24,20 @@ def test_make_goldens_regenerates_committed_fixtures(tmp_path):
         assert sorted(new.files) == sorted(old.files)
         for k in old.files:
             assert np.array_equal(new[k], old[k]), (name, k)
+
+
+@pytest.mark.skipif(not os.path.exists(os.path.join(REF, "dlrm_s_pytorch.py")), reason="live reference not present")
+def test_make_cli_goldens_reproduces_the_recorded_reference_run(tmp_path):
+    """oracle/make_cli_goldens.py runs the unmodified reference CLI; tag C (test pass + checkpoint) must give the
+    committed lines again (the path inside 'Saving model ...' aside)."""
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "oracle", "make_cli_goldens.py"), "--out", str(tmp_path),
+                        "--tags", "C"], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+
+    def lines(path):
+        return [("Saving model" if ln.startswith("Saving model") else ln) for ln in open(path).read().splitlines()
+                if not ln.startswith("time/loss")]
+
+    assert lines(os.path.join(str(tmp_path), "cli_cfg0_C.txt")) == lines(os.path.join(ROOT, "tests", "golden",
+                                                                                     "cli_cfg0_C.txt"))
+    assert os.path.getsize(os.path.join(str(tmp_path), "cli_cfg0_C_ref.pt")) > 1_000_000
