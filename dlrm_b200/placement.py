@@ -97,13 +97,24 @@ def plan(rows: Sequence[int], cost: Sequence[float], world: int, *, split_above:
             break
         ld = cur.load()
         hot = max(range(world), key=lambda r: ld[r])
-        cands = [s for s in cur.of_rank(hot) if s.whole and s.rows >= world]
+        cands = [s for s in cur.of_rank(hot) if s.whole and s.rows >= world * world]   # no empty parts (ceil split)
         if not cands:
             break
         extra = extra + [min(cands, key=lambda s: (cur.cost[s.table], s.table)).table]
         cur = _plan_once(rows, cost, world, split_above, bytes_per_row, mem_budget_bytes, extra)
         if cur.imbalance() < best.imbalance() - 1e-9:     # one more split may not help, two may
             best = cur
+    if world > 1 and not force_split:
+        # The split heuristic is tuned for tens of tables; on degenerate inputs (two tables, two ranks) a plain
+        # table-wise placement can be better balanced: keep whichever of {heuristic, LPT without hot-table splits,
+        # the reference's contiguous slices when they fit} is best (the heuristic on a tie).
+        cands = [best, _plan_once(rows, cost, world, float("inf"), bytes_per_row, mem_budget_bytes, ())]
+        if len(rows) >= world:
+            ref = contiguous(rows, world)
+            ref.cost = [float(c) for c in cost]
+            if max(ref.rows_per_rank()) * bytes_per_row <= mem_budget_bytes:
+                cands.append(ref)
+        best = min(enumerate(cands), key=lambda ip: (round(ip[1].imbalance(), 3), ip[0]))[1]    # ties: the heuristic
     return best
 
 
@@ -120,10 +131,13 @@ def _plan_once(rows, cost, world, split_above, bytes_per_row, mem_budget_bytes, 
         return Placement(1, shards, cost)
     mean = sum(cost) / world
     split = set(int(t) for t in force_split)
+    for t in split:
+        if rows[t] < world * world:
+            raise ValueError("table %d has %d rows: too few to split over %d ranks" % (t, rows[t], world))
     for t in range(T):
         too_hot = cost[t] > split_above * mean
         too_big = rows[t] * bytes_per_row > mem_budget_bytes
-        if (too_hot or too_big) and rows[t] >= world:
+        if (too_hot or too_big) and rows[t] >= world * world:     # ceil(rows / world) per part: no part is empty
             split.add(t)
     shards: List[Shard] = []
     load = [0.0] * world

@@ -69,3 +69,38 @@ def test_multihot_generator_properties():
     xs = np.array([0, 1, 2 ** 63, 2 ** 64 - 1, 123456789123456789], dtype=np.uint64)
     for n in (3, 40000000, 2 ** 32 - 1):
         assert list(M.mulhi64(xs, n)) == [(int(v) * n) >> 64 for v in xs]
+
+
+def test_placement_properties_random_models():
+    """For random table sets and world sizes: the shards of a table partition its rows exactly (no gap, no overlap,
+    no empty part, parts numbered in row order with equal ceil-sized ranges -- what the remote-read kernel's
+    `row / rows_per_shard` relies on), every table is placed, the plan is deterministic, and it is never worse
+    balanced than the reference's contiguous slices."""
+    from hypothesis import given, settings, strategies as st
+
+    from dlrm_b200 import placement as P
+
+    @settings(max_examples=120, deadline=None)
+    @given(st.lists(st.tuples(st.integers(1, 5_000_000), st.floats(0.5, 120.0)), min_size=1, max_size=30),
+           st.sampled_from([1, 2, 3, 4, 8]))
+    def check(tabs, world):
+        rows, cost = [r for r, _ in tabs], [c for _, c in tabs]
+        pl = P.plan(rows, cost, world)
+        again = P.plan(rows, cost, world)
+        assert [(s.table, s.rank, s.row_lo, s.row_hi, s.part, s.nparts) for s in pl.shards] == \
+               [(s.table, s.rank, s.row_lo, s.row_hi, s.part, s.nparts) for s in again.shards]
+        for t, n in enumerate(rows):
+            sh = pl.of_table(t)
+            assert sh and [s.part for s in sh] == list(range(len(sh))) and all(s.nparts == len(sh) and s.rows == n for s in sh)
+            assert sh[0].row_lo == 0 and sh[-1].row_hi == n
+            assert all(a.row_hi == b.row_lo for a, b in zip(sh, sh[1:])) and all(s.local_rows > 0 for s in sh)
+            if len(sh) > 1:
+                per = -(-n // len(sh))
+                assert len(sh) == world and all(s.row_lo == s.part * per and s.rank == s.part for s in sh)
+        assert abs(sum(pl.load()) - sum(cost)) < 1e-6 * sum(cost)
+        if len(rows) >= world:
+            ref = P.contiguous(rows, world)
+            ref.cost = cost
+            assert pl.imbalance() <= ref.imbalance() + 1e-9
+
+    check()
