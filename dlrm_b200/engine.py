@@ -91,6 +91,8 @@ class Engine:
         self.shards = [dict(s) for s in shards]
         if [int(s["row_n"]) for s in self.shards] != self.ln_emb:
             raise ValueError("ln_emb must list the LOCAL row count of every shard")
+        if any(n <= 0 for n in self.ln_emb):       # (row_n == 0 means "the whole table" to the kernels)
+            raise ValueError("every table / shard needs at least one row")
         n_glob = max([int(s["table"]) for s in self.shards], default=-1) + 1
         self.F = int(n_features) if n_features else n_glob + 1   # interaction features (global)
         # row-split tables of the GLOBAL placement, (table, nparts) each: the rank that owns a sample adds the
