@@ -8,7 +8,7 @@ from dlrm_b200.data import PackedLayout
 from dlrm_b200.dist import a2a_splits, push_route, table_slices
 
 
-@settings(max_examples=200, deadline=None)
+@settings(max_examples=200, deadline=None, derandomize=True, database=None)
 @given(st.integers(1, 4096), st.integers(0, 64), st.integers(1, 64), st.integers(0, 100000))
 def test_packed_layout_sections_are_aligned_and_disjoint(B, T, m_den, cap):
     L = PackedLayout(B, T, m_den, cap)
@@ -21,7 +21,7 @@ def test_packed_layout_sections_are_aligned_and_disjoint(B, T, m_den, cap):
     assert L.used(0) == L.off_i and L.used(cap) == L.off_i + cap * 8
 
 
-@settings(max_examples=200, deadline=None)
+@settings(max_examples=200, deadline=None, derandomize=True, database=None)
 @given(st.integers(0, 300), st.integers(1, 16))
 def test_table_slices_partition_like_the_reference_rule(n_tables, world):
     sl = table_slices(n_tables, world)
@@ -31,7 +31,7 @@ def test_table_slices_partition_like_the_reference_rule(n_tables, world):
     assert max(sizes) - min(sizes) <= 1 and sizes == sorted(sizes, reverse=True)   # extras go to the first ranks
 
 
-@settings(max_examples=100, deadline=None)
+@settings(max_examples=100, deadline=None, derandomize=True, database=None)
 @given(st.integers(1, 40), st.integers(1, 8), st.integers(1, 5), st.sampled_from([1, 2, 4, 16]))
 def test_exchange_splits_and_push_routes_tile_the_receive_buffers(n_tables, world, B, D):
     sl = table_slices(n_tables, world)
